@@ -1,0 +1,110 @@
+// dial_host.h — host-side derivation of the device model (schedules + smem layout).
+// Pure C++ (no CUDA runtime) so that the test-only warp emulator can share it.
+#pragma once
+#include <string.h>
+#include <string>
+#include "dial_device.cuh"
+
+static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::string& err) {
+  memset(&D, 0, sizeof(D));
+  D.m = m;
+  const int nb = m.nbody, nv = m.nv;
+  if (nb < 2 || nb > DIAL_MAXB || nv > DIAL_MAXV || m.nq > DIAL_MAXQ || m.nu > DIAL_MAXU ||
+      m.ngeom > DIAL_MAXG || m.npair > DIAL_MAXP || m.ncon > DIAL_MAXC || m.nsite > DIAL_MAXS ||
+      4 * m.ncon > DIAL_MAXE) {
+    err = "model exceeds the fixed device capacities (DIAL_MAX*)";
+    return false;
+  }
+  if (m.cone != 0) { err = "elliptic friction cones are not supported by the CUDA path"; return false; }
+  bool any_damp = false;
+  for (int d = 0; d < nv; ++d) any_damp |= m.dof_damping[d] != 0.f;
+  if (m.eulerdamp && any_damp) { err = "implicit Euler damping (eulerdamp) is not supported by the CUDA path"; return false; }
+  // depth / children / roots
+  D.maxdepth = 0;
+  for (int b = 1; b < nb; ++b) D.maxdepth = m.body_depth[b] > D.maxdepth ? m.body_depth[b] : D.maxdepth;
+  int nchild = 0;
+  for (int b = 0; b < nb; ++b) {
+    D.child_adr[b] = nchild;
+    for (int c = 1; c < nb; ++c)
+      if (m.body_parentid[c] == b && b > 0) D.child_ids[nchild++] = c;
+    D.child_num[b] = nchild - D.child_adr[b];
+  }
+  D.nroot = 0;
+  for (int b = 1; b < nb; ++b) {
+    int r = m.body_rootid[b], idx = -1;
+    for (int i = 0; i < D.nroot; ++i) if (D.root_body[i] == r) idx = i;
+    if (idx < 0) {
+      if (D.nroot >= 4) { err = "more than 4 kinematic trees"; return false; }
+      idx = D.nroot++;
+      D.root_body[idx] = r;
+    }
+    D.body_rootidx[b] = idx;
+  }
+  for (int i = 0; i < D.nroot; ++i) {
+    double mass = 0;
+    for (int b = 1; b < nb; ++b) if (D.body_rootidx[b] == i) mass += m.body_mass[b];
+    if (mass < 1e-15) { err = "massless kinematic tree"; return false; }
+    D.root_invmass[i] = (float)(1.0 / mass);
+  }
+  // dof ancestor masks, chain length check, elimination levels
+  for (int i = 0; i < nv; ++i) {
+    uint32_t mask = 0;
+    int j = i, n = 0;
+    while (j >= 0) { mask |= 1u << j; j = m.dof_parentid[j]; ++n; }
+    if (n > DIAL_MAXCHAIN) { err = "dof ancestor chain longer than DIAL_MAXCHAIN"; return false; }
+    D.dof_ancmask[i] = mask;
+  }
+  for (int i = nv - 1; i >= 0; --i) {
+    int lv = 0;
+    for (int k = i + 1; k < nv; ++k)
+      if (m.dof_parentid[k] == i) lv = D.dof_level[k] + 1 > lv ? D.dof_level[k] + 1 : lv;
+    D.dof_level[i] = lv;
+    D.nlevel = lv + 1 > D.nlevel ? lv + 1 : D.nlevel;
+  }
+  if (D.nlevel > DIAL_MAXLEVEL) { err = "too many elimination levels"; return false; }
+  int pos = 0;
+  for (int lv = 0; lv < D.nlevel; ++lv) {
+    D.level_adr[lv] = pos;
+    for (int i = 0; i < nv; ++i) if (D.dof_level[i] == lv) D.level_dofs[pos++] = i;
+  }
+  D.level_adr[D.nlevel] = pos;
+  for (int b = 0; b < nb; ++b) {
+    uint32_t mask = 0;
+    int bb = b;
+    while (bb > 0) {
+      if (m.body_jntadr[bb] >= 0)
+        for (int k = 0; k < m.body_dofnum[bb]; ++k) mask |= 1u << (m.body_dofadr[bb] + k);
+      bb = m.body_parentid[bb];
+    }
+    D.body_dofmask[b] = mask;
+  }
+  for (int d = 0; d < nv; ++d) {
+    D.dof_actuator[d] = -1;
+    for (int a = 0; a < m.nu; ++a) if (m.actuator_dofadr[a] == d) D.dof_actuator[d] = a;
+    int j = m.dof_jntid[d];
+    D.dof_limited[d] = (m.jnt_limited[j] && m.jnt_type[j] != JNT_FREE) ? j : -1;
+  }
+  int c = 0;
+  for (int k = 0; k < m.npair; ++k) {
+    if (m.pair_kind[k] != PAIR_PLANE_SPHERE && m.pair_kind[k] != PAIR_PLANE_CAPSULE) {
+      err = "unsupported contact pair kind on the CUDA path";
+      return false;
+    }
+    for (int s = 0; s < m.pair_ncon[k]; ++s) { D.con_pair[c] = k; D.con_sub[c] = s; ++c; }
+  }
+  if (c != m.ncon) { err = "pair_ncon does not sum to ncon"; return false; }
+  D.nedge = 4 * m.ncon;
+  // per-warp slab layout
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  D.o_xpos = take(3 * nb); D.o_xquat = take(4 * nb); D.o_xmat = take(9 * nb); D.o_xipos = take(3 * nb);
+  D.o_cinert = take(10 * nb); D.o_cdof = take(6 * nv); D.o_cdofdot = take(6 * nv);
+  D.o_cvel = take(6 * nb); D.o_cacc = take(6 * nb); D.o_cfrc = take(6 * nb);
+  D.o_M = take(nv * nv); D.o_L = take(nv * nv); D.o_J = take(D.nedge * nv);
+  D.o_qpos = take(m.nq); D.o_qvel = take(nv); D.o_warm = take(nv); D.o_ctrl = take(m.nu);
+  D.o_vec = take(32); D.o_frow = take(32); D.o_cpos = take(3 * m.ncon); D.o_cframe = take(9 * m.ncon);
+  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_ldinv = take(nv); D.o_site = take(3 * m.nsite);
+  D.o_misc = take(8);
+  D.warp_floats = o;
+  return true;
+}

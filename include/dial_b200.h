@@ -1,0 +1,192 @@
+/*
+ * dial_b200.h — C ABI of the B200-native DIAL-MPC sampling core.
+ *
+ * The reference (LeCAR-Lab/dial-mpc) has no FFI for this path: its boundary is the
+ * Python class `MBDPI` plus the env registry, and every function below replaces a
+ * piece of jitted JAX that `MBDPI` calls.  Each entry point cites the reference
+ * code it stands in for (paths relative to the reference root).
+ *
+ * Conventions
+ *   - extern "C", opaque handles, plain pointers and sizes, no torch / C++ types.
+ *   - every `const float* / float*` argument marked [dev] is a CUDA device pointer to
+ *     contiguous row-major fp32 owned by the caller; `stream` is a `cudaStream_t`
+ *     passed as `void*`; all work is enqueued asynchronously on it.
+ *   - return 0 on success, negative on error; `dial_last_error()` returns a static,
+ *     thread-local, NUL-terminated description of the last failure.
+ *   - one plan per GPU; a plan is not thread-safe.
+ *   - no hidden allocations after `dial_plan_create`.
+ */
+#ifndef DIAL_B200_H_
+#define DIAL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIAL_ABI_VERSION 1
+
+/* capacities of the fixed-size device model */
+#define DIAL_MAXB 24   /* bodies incl. world            */
+#define DIAL_MAXV 28   /* dofs                          */
+#define DIAL_MAXQ 29   /* generalized positions         */
+#define DIAL_MAXU 20   /* actuators                     */
+#define DIAL_MAXG 8    /* collision geoms               */
+#define DIAL_MAXP 8    /* contact pairs                 */
+#define DIAL_MAXC 8    /* contacts                      */
+#define DIAL_MAXS 8    /* sites                         */
+#define DIAL_MAXNODE 8 /* Hnode+1                       */
+#define DIAL_MAXH 64   /* Hsample+1                     */
+#define DIAL_MAXSTAGE 8
+
+/* environments (reward functors fused into the rollout kernel) */
+enum {
+  DIAL_ENV_GO2_WALK = 0,    /* UnitreeGo2Env.step         envs/unitree_go2_env.py:126-261 */
+  DIAL_ENV_GO2_SEQJUMP = 1, /* UnitreeGo2SeqJumpEnv.step  envs/unitree_go2_env.py:403-521 */
+  DIAL_ENV_H1_WALK = 2,     /* UnitreeH1WalkEnv.step      envs/unitree_h1_env.py:181-321  */
+};
+
+/* Compiled robot model: what `brax.io.mjcf.load` + `mjx.put_model` give the reference
+ * (envs/unitree_go2_env.py:95-99).  Filled by the host-side model compiler. */
+typedef struct dial_model_desc {
+  int32_t nq, nv, nu, nbody, njnt, ngeom, nsite, npair, ncon;
+  int32_t iterations, ls_iterations, eulerdamp, cone;
+  float timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
+  /* bodies (index 0 = world) */
+  int32_t body_parentid[DIAL_MAXB], body_rootid[DIAL_MAXB], body_depth[DIAL_MAXB];
+  int32_t body_jntadr[DIAL_MAXB], body_dofadr[DIAL_MAXB], body_dofnum[DIAL_MAXB];
+  float body_pos[DIAL_MAXB][3], body_quat[DIAL_MAXB][4];
+  float body_ipos[DIAL_MAXB][3], body_iquat[DIAL_MAXB][4];
+  float body_mass[DIAL_MAXB], body_inertia[DIAL_MAXB][3], body_invweight0[DIAL_MAXB];
+  /* joints (at most one per body) */
+  int32_t jnt_type[DIAL_MAXB], jnt_qposadr[DIAL_MAXB], jnt_dofadr[DIAL_MAXB], jnt_limited[DIAL_MAXB];
+  float jnt_pos[DIAL_MAXB][3], jnt_axis[DIAL_MAXB][3], jnt_range[DIAL_MAXB][2], jnt_margin[DIAL_MAXB];
+  float jnt_solref[DIAL_MAXB][2], jnt_solimp[DIAL_MAXB][5];
+  /* dofs */
+  int32_t dof_bodyid[DIAL_MAXV], dof_jntid[DIAL_MAXV], dof_parentid[DIAL_MAXV];
+  float dof_armature[DIAL_MAXV], dof_damping[DIAL_MAXV], dof_invweight0[DIAL_MAXV];
+  float qpos0[DIAL_MAXQ];
+  /* collision geoms + static contact pairs (MJX fixed-size contact arrays) */
+  int32_t geom_type[DIAL_MAXG], geom_bodyid[DIAL_MAXG];
+  float geom_pos[DIAL_MAXG][3], geom_quat[DIAL_MAXG][4], geom_size[DIAL_MAXG][3];
+  int32_t pair_kind[DIAL_MAXP], pair_geom1[DIAL_MAXP], pair_geom2[DIAL_MAXP], pair_ncon[DIAL_MAXP];
+  float pair_friction[DIAL_MAXP][5], pair_margin[DIAL_MAXP], pair_gap[DIAL_MAXP];
+  float pair_solref[DIAL_MAXP][2], pair_solimp[DIAL_MAXP][5];
+  /* sites */
+  int32_t site_bodyid[DIAL_MAXS];
+  float site_pos[DIAL_MAXS][3];
+  /* actuators (joint transmissions): force = gain*ctrl + b0 + b1*q + b2*qd */
+  int32_t actuator_dofadr[DIAL_MAXU], actuator_qposadr[DIAL_MAXU];
+  int32_t actuator_ctrllimited[DIAL_MAXU], actuator_forcelimited[DIAL_MAXU];
+  float actuator_gear[DIAL_MAXU], actuator_gain[DIAL_MAXU], actuator_bias[DIAL_MAXU][3];
+  float actuator_ctrlrange[DIAL_MAXU][2], actuator_forcerange[DIAL_MAXU][2];
+} dial_model_desc;
+
+/* Environment + planner configuration: DialConfig (core/dial_config.py:4-23),
+ * BaseEnvConfig (config/base_env_config.py:4-20) and the env-specific constants. */
+typedef struct dial_plan_desc {
+  int32_t env_id;
+  int32_t Nsample;   /* samples rolled by THIS rank (shard size)                  */
+  int32_t Ntotal;    /* Nsample of the whole job (== Nsample when not sharded)    */
+  int32_t shard_offset; /* global index of this rank's first sample               */
+  int32_t Hsample, Hnode;
+  int32_t n_frames;  /* int(dt / timestep), base_env.py:17                        */
+  int32_t leg_control_torque; /* 1: act2tau, 0: act2joint -> position actuator    */
+  float temp_sample;
+  float dt, action_scale;
+  float kp[DIAL_MAXU], kd[DIAL_MAXU];
+  float joint_range[DIAL_MAXU][2];          /* env.joint_range (sampling range)   */
+  float physical_joint_range[DIAL_MAXU][2]; /* sys.jnt_range[1:]                  */
+  float joint_torque_range[DIAL_MAXU][2];   /* sys.actuator_ctrlrange (+-inf ok)  */
+  float M_n2u[DIAL_MAXH][DIAL_MAXNODE];     /* node -> action spline matrix       */
+  /* reward constants */
+  int32_t torso_body;       /* MuJoCo body id of the torso (x index + 1)          */
+  int32_t nfeet;
+  int32_t feet_site[4];
+  float gait_duty, gait_cadence, gait_amplitude, gait_phase[4];
+  float vel_cmd[3], ang_cmd[3], ramp_up_time, pos_tar[3];
+  /* seq-jump */
+  int32_t n_stage;
+  float jump_dt;
+  float pose_seq[DIAL_MAXSTAGE][3], yaw_seq[DIAL_MAXSTAGE];
+  float contact_targets[DIAL_MAXSTAGE][4][3], contact_radius[DIAL_MAXSTAGE][4];
+} dial_plan_desc;
+
+/* State handed to the planner: Brax `State.pipeline_state` (qpos, qvel,
+ * qacc_warmstart) + `State.info` counters the rewards read
+ * (envs/unitree_go2_env.py:106-118, :366-381). */
+typedef struct dial_state {
+  const float* qpos;           /* [dev] [nq] */
+  const float* qvel;           /* [dev] [nv] */
+  const float* qacc_warmstart; /* [dev] [nv] */
+  int32_t step;                /* info["step"]          */
+  int32_t stage;               /* info["contact_stage"] */
+} dial_state;
+
+typedef struct dial_plan dial_plan;
+
+int dial_abi_version(void);
+const char* dial_last_error(void);
+
+/* Create / destroy a plan (uploads model + config, allocates all workspaces). */
+dial_plan* dial_plan_create(const dial_model_desc* model, const dial_plan_desc* cfg);
+void dial_plan_destroy(dial_plan* plan);
+
+/* rollout_us_vmap — core/dial_core.py:36-42,80-81: roll B action sequences from one
+ * state.  us [dev] [B, Hsample+1, nu]; outputs (nullable except rewss):
+ * rewss [B,Hs+1], q [B,Hs+1,nq], qd [B,Hs+1,nv], xpos [B,Hs+1,nbody-1,3]. */
+int dial_rollout(dial_plan* plan, const dial_state* s, const float* us, int B, int H,
+                 float* rewss, float* q, float* qd, float* xpos, void* stream);
+
+/* env.step for ONE instance — the `step_env(state, Y0[0])` call at
+ * core/dial_core.py:245.  Writes the successor state (qpos,qvel,qacc_warmstart
+ * [dev]), the reward [dev][1] and ctrl [dev][nu]; step/stage are advanced by the host. */
+int dial_env_step(dial_plan* plan, const dial_state* s, const float* action,
+                  float* qpos_out, float* qvel_out, float* warm_out, float* reward,
+                  float* ctrl_out, void* stream);
+
+/* pipeline_init — envs/unitree_go2_env.py:104: mjx.forward at (qpos, qvel=0):
+ * normalises the quaternion and produces the initial qacc_warmstart. */
+int dial_pipeline_init(dial_plan* plan, const float* qpos, const float* qvel,
+                       float* qpos_out, float* warm_out, void* stream);
+
+/* Stage 1 of MBDPI.reverse_once (core/dial_core.py:103-125): sample Y0s
+ * (eps injected [dev][Ntotal,Hnode+1,nu], or NULL -> Threefry stream keyed by
+ * `key`), pin node 0, append the mean row, clip, spline to actions, roll out
+ * this rank's shard + the mean sample and write per-sample mean rewards
+ * rews_local [dev][Nsample+1] (mean sample last).  Trajectories
+ * (q/qd/xpos [Nsample+1,Hs+1,*]) are kept in the plan's workspace. */
+int dial_reverse_rollout(dial_plan* plan, const dial_state* s, const float* eps,
+                         const uint32_t key[2], const float* Ybar /*[dev][Hn+1,nu]*/,
+                         const float* noise_scale /*[dev][Hn+1]*/, float* rews_local,
+                         void* stream);
+
+/* Stage 2 (core/dial_core.py:126-135): population std, softmax weights over the
+ * Ntotal+1 rewards rews_all [dev] (sample-major, mean sample last) and the weighted
+ * control update Ybar_out [dev][Hn+1,nu].  Every rank recomputes all Y0s from
+ * eps/key, so sharded runs need only the one allgather of rewards.  Optional
+ * (nullable) weights [dev][Ntotal+1]. */
+int dial_reverse_update(dial_plan* plan, const float* eps, const uint32_t key[2],
+                        const float* Ybar, const float* noise_scale, const float* rews_all,
+                        float* Ybar_out, float* weights, void* stream);
+
+/* qbar/qdbar/xbar (core/dial_core.py:133-135): weighted sums of this rank's stored
+ * trajectories with `weights` [dev][Ntotal+1]; sharded runs sum the outputs across
+ * ranks (the mean sample is counted on rank 0 only).  Outputs [dev]:
+ * qbar [Hs+1,nq], qdbar [Hs+1,nv], xbar [Hs+1,nbody-1,3]. */
+int dial_reverse_trajbar(dial_plan* plan, const float* weights, int rank,
+                         float* qbar, float* qdbar, float* xbar, void* stream);
+
+/* jax.random.split(rng) / the planner's key threading (core/dial_core.py:106,145):
+ * host-side Threefry-2x32; out[0] is the new rng, out[1] the sampling key. */
+void dial_key_split(const uint32_t key[2], uint32_t out0[2], uint32_t out1[2]);
+
+/* kernel launches issued by this plan since creation (bench bookkeeping) */
+int64_t dial_launch_count(const dial_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIAL_B200_H_ */

@@ -1,0 +1,42 @@
+// TEST-ONLY: runs the per-warp device code of csrc/dial_device.cuh on the CPU through the
+// lock-step fiber emulator (warp_emul.h).  Used by tests/test_emul_*.py to debug kernel
+// logic without a GPU.  Never loaded by the dial_mpc_b200 package.
+#define DIAL_HOST_EMUL 1
+#include <vector>
+#include <string>
+#include <stdio.h>
+#include "../../dial_mpc_b200/csrc/dial_host.h"
+
+extern "C" int emul_rollout(const dial_model_desc* m, const dial_plan_desc* c, int mode, int nrows,
+                            int H, int step0, int stage0, const float* qpos0, const float* qvel0,
+                            const float* warm0, const float* us, const float* eps, const float* Ybar,
+                            const float* noise, uint32_t key0, uint32_t key1, float* rewss, float* rews,
+                            float* q, float* qd, float* xpos, float* qpos_out, float* qvel_out,
+                            float* warm_out, float* ctrl_out, float* slab_out) {
+  static DevModel D;
+  static DevPlan P;
+  std::string err;
+  if (!derive_model(*m, D, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
+  P.c = *c;
+  RolloutArgs A;
+  memset(&A, 0, sizeof(A));
+  A.nrows = nrows; A.H = H; A.mode = mode; A.step0 = step0; A.stage0 = stage0;
+  A.qpos0 = qpos0; A.qvel0 = qvel0; A.warm0 = warm0; A.us = us; A.eps = eps; A.Ybar = Ybar;
+  A.noise = noise; A.key0 = key0; A.key1 = key1; A.rewss = rewss; A.rews = rews; A.q = q; A.qd = qd;
+  A.xpos = xpos; A.qpos_out = qpos_out; A.qvel_out = qvel_out; A.warm_out = warm_out; A.ctrl_out = ctrl_out;
+  std::vector<float> slab(D.warp_floats, 0.f);
+  for (int row = 0; row < nrows; ++row) {
+    emul::run_warp([&](int lane) { rollout_warp(&D, &P, slab.data(), A, row, lane); });
+    if (slab_out && row == 0) memcpy(slab_out, slab.data(), sizeof(float) * D.warp_floats);
+  }
+  return 0;
+}
+
+extern "C" int emul_layout(const dial_model_desc* m, int* out /*[32]*/) {
+  static DevModel D;
+  std::string err;
+  if (!derive_model(*m, D, err)) return -1;
+  const int32_t* o = &D.o_xpos;
+  for (int i = 0; i < 27; ++i) out[i] = o[i];
+  return 0;
+}
