@@ -1,0 +1,241 @@
+"""DIAL-MPC planner on the B200 sampling core.
+
+Same class and method surface as the reference ``MBDPI`` (dial_mpc/core/dial_core.py:51-172)
+and the same synchronous MPC loop as its ``main()`` (:175-268).  The shift-and-anneal loop
+stays in Python; ``reverse_once`` is two kernel stages (rollout, update) reached through the
+C ABI, with one NCCL allgather of the per-sample rewards between them when the samples are
+sharded over several GPUs (one process per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import os
+import sys
+import time
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import yaml
+
+import dial_mpc_b200.envs as dial_envs
+from dial_mpc_b200 import random as drandom
+from dial_mpc_b200.core.dial_config import DialConfig
+from dial_mpc_b200.plan import Plan
+from dial_mpc_b200.utils.io_utils import get_example_path, load_dataclass_from_dict
+from dial_mpc_b200.utils.spline import interp_matrix
+
+
+def rollout_us(step_env, state, us):
+    """Reference semantics of ``rollout_us`` (dial_core.py:36-42) for a *single* action
+    sequence, expressed with the env's own ``step`` (used by tests / custom callers)."""
+    rews, pipeline_states = [], []
+    for u in us:
+        state = step_env(state, u)
+        rews.append(state.reward)
+        pipeline_states.append(state.pipeline_state)
+    return torch.stack([torch.as_tensor(r) for r in rews]), pipeline_states
+
+
+def softmax_update(weights, Y0s, sigma, mu_0t):
+    """``softmax_update`` (dial_core.py:45-48) on torch tensors (API parity; the planner's
+    own update runs in ``ybar_kernel``)."""
+    return torch.einsum("n,nij->ij", weights, Y0s), sigma
+
+
+class MBDPI:
+    def __init__(self, args: DialConfig, env, rank: int = 0, world_size: int = 1, process_group=None,
+                 compute_bars: bool = True):
+        self.args = args
+        self.env = env
+        self.nu = env.action_size
+        if args.update_method != "mppi":
+            raise KeyError(args.update_method)
+        self.update_fn = softmax_update
+        self.rank, self.world_size, self.pg = rank, world_size, process_group
+        self.compute_bars = compute_bars
+        if args.Nsample % world_size != 0:
+            raise ValueError("Nsample must be divisible by the number of ranks")
+        self.Nlocal = args.Nsample // world_size
+
+        sigma_control = args.horizon_diffuse_factor ** np.arange(args.Hnode + 1)[::-1]
+        self.sigma_control_np = (sigma_control * args.sigma_scale).astype(np.float64)
+
+        # node to u (dial_core.py:73-77; ctrl_dt is hard-coded to 0.02 there)
+        self.ctrl_dt = 0.02
+        self.step_us_np = np.linspace(0, self.ctrl_dt * args.Hsample, args.Hsample + 1)
+        self.step_nodes_np = np.linspace(0, self.ctrl_dt * args.Hsample, args.Hnode + 1)
+        self.node_dt = self.ctrl_dt * (args.Hsample) / (args.Hnode)
+        self.M_n2u_np = interp_matrix(self.step_nodes_np, self.step_us_np)
+        self.M_u2n_np = interp_matrix(self.step_us_np, self.step_nodes_np)
+
+        desc = env.plan_desc(Nsample=self.Nlocal, Ntotal=args.Nsample, shard_offset=rank * self.Nlocal,
+                             Hsample=args.Hsample, Hnode=args.Hnode, temp_sample=args.temp_sample,
+                             M_n2u=self.M_n2u_np)
+        self.plan = Plan(env, desc)
+        dev = self.plan.device
+        self.device = dev
+        f = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32), device=dev)
+        self.sigma_control = f(self.sigma_control_np)
+        self.step_us, self.step_nodes = f(self.step_us_np), f(self.step_nodes_np)
+        self.M_n2u, self.M_u2n = f(self.M_n2u_np), f(self.M_u2n_np)
+        Hs1 = args.Hsample + 1
+        P = np.zeros((Hs1, Hs1))
+        P[np.arange(Hs1 - 1), np.arange(1, Hs1)] = 1.0  # roll(-1) with the last row zeroed
+        self.M_shift = f(self.M_u2n_np @ P @ self.M_n2u_np)
+        # persistent buffers
+        N, Nl = args.Nsample, self.Nlocal
+        self._rews_local = torch.empty(Nl + 1, dtype=torch.float32, device=dev)
+        self._rews_all = torch.empty(N + 1, dtype=torch.float32, device=dev)
+        self._weights = torch.empty(N + 1, dtype=torch.float32, device=dev)
+        m = env.sys
+        self._bars = torch.empty(Hs1 * (m.nq + m.nv + 3 * (m.nbody - 1)), dtype=torch.float32, device=dev)
+
+    # -- spline maps (dial_core.py:82-101) -------------------------------------------------------
+    def node2u(self, nodes):
+        return self.M_n2u @ self._t(nodes)
+
+    def u2node(self, us):
+        return self.M_u2n @ self._t(us)
+
+    def node2u_vmap(self, Y):      # (horizon, node)
+        return self.M_n2u @ self._t(Y)
+
+    def u2node_vmap(self, u):
+        return self.M_u2n @ self._t(u)
+
+    def node2u_vvmap(self, Ys):    # (batch, horizon, node)
+        return torch.einsum("tk,bka->bta", self.M_n2u, self._t(Ys))
+
+    def u2node_vvmap(self, us):
+        return torch.einsum("kt,bta->bka", self.M_u2n, self._t(us))
+
+    def _t(self, x):
+        return self.plan.f32(x)
+
+    # -- batched rollout (dial_core.py:80-81) ------------------------------------------------------
+    def rollout_us_vmap(self, state, us):
+        """-> (rewss [B,H], (q [B,H,nq], qd [B,H,nv], x_pos [B,H,nbody-1,3]))."""
+        rewss, q, qd, x = self.plan.rollout(state, us)
+        return rewss, (q, qd, x)
+
+    # -- the hot path (dial_core.py:103-145) ----------------------------------------------------------
+    def reverse_once(self, state, rng, Ybar_i, noise_scale, eps=None):
+        """One annealing iteration.  ``eps`` (optional, [Nsample,Hnode+1,nu]) injects the noise;
+        otherwise it is drawn in-kernel from the Threefry stream keyed by ``split(rng)[1]``."""
+        rng, Y0s_rng = drandom.split(rng)
+        Ybar_i = self._t(Ybar_i)
+        noise_scale = self._t(noise_scale)
+        if eps is not None:
+            eps = self.plan.f32(eps, (self.args.Nsample, self.args.Hnode + 1, self.nu))
+        key = None if eps is not None else Y0s_rng
+        N, Nl = self.args.Nsample, self.Nlocal
+        self.plan.reverse_rollout(state, eps, key, Ybar_i, noise_scale, self._rews_local)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._rews_all[:N], self._rews_local[:Nl], group=self.pg)
+            self._rews_all[N:].copy_(self._rews_local[Nl:])
+            rews_all = self._rews_all
+        else:
+            rews_all = self._rews_local
+        Ybar = torch.empty_like(Ybar_i)
+        self.plan.reverse_update(eps, key, Ybar_i, noise_scale, rews_all, Ybar, self._weights)
+        info: Dict[str, Any] = {"rews": rews_all.clone(), "new_noise_scale": noise_scale, "weights": self._weights}
+        if self.compute_bars:
+            m = self.env.sys
+            Hs1 = self.args.Hsample + 1
+            n1, n2 = Hs1 * m.nq, Hs1 * m.nv
+            bars = torch.empty_like(self._bars)
+            qbar, qdbar, xbar = bars[:n1], bars[n1:n1 + n2], bars[n1 + n2:]
+            self.plan.reverse_trajbar(self._weights, self.rank, qbar, qdbar, xbar)
+            if self.world_size > 1:
+                import torch.distributed as dist
+                dist.all_reduce(bars, group=self.pg)
+            info["qbar"] = qbar.view(Hs1, m.nq)
+            info["qdbar"] = qdbar.view(Hs1, m.nv)
+            info["xbar"] = xbar.view(Hs1, m.nbody - 1, 3)
+        return rng, Ybar, info
+
+    def reverse_scan(self, state, rng, Y0, factors):
+        """``lax.scan(reverse_scan, (rng, Y0, state), factors)`` of dial_core.py:177-180,262-264."""
+        info = None
+        for i in range(factors.shape[0]):
+            rng, Y0, info = self.reverse_once(state, rng, Y0, factors[i])
+        return rng, Y0, info
+
+    def schedule(self, n_diffuse: int) -> torch.Tensor:
+        """``sigma_control * traj_diffuse_factor ** arange(n_diffuse)[:, None]`` (dial_core.py:259-261)."""
+        f = self.args.traj_diffuse_factor ** torch.arange(n_diffuse, device=self.device, dtype=torch.float32)
+        return self.sigma_control[None, :] * f[:, None]
+
+    # -- shift (dial_core.py:160-172) -------------------------------------------------------------------
+    def shift(self, Y):
+        return self.M_shift @ self._t(Y)
+
+    def shift_Y_from_u(self, u, n_step):
+        u = self._t(u)
+        u = torch.roll(u, -n_step, dims=0)
+        u[-n_step:] = 0.0
+        return self.u2node_vmap(u)
+
+
+def main():
+    """Synchronous MPC loop — dial_core.py:175-268 without the rendering / flask tail."""
+    parser = argparse.ArgumentParser()
+    g = parser.add_mutually_exclusive_group(required=True)
+    g.add_argument("--config", type=str, default=None)
+    g.add_argument("--example", type=str, default=None)
+    g.add_argument("--list-examples", action="store_true")
+    parser.add_argument("--custom-env", type=str, default=None, help="Custom environment to import dynamically")
+    parser.add_argument("--n-steps", type=int, default=None)
+    args = parser.parse_args()
+    from dial_mpc_b200.examples import examples
+    if args.list_examples:
+        print("Examples:")
+        for example in examples:
+            print(f"  {example}")
+        return
+    if args.custom_env is not None:
+        sys.path.append(os.getcwd())
+        importlib.import_module(args.custom_env)
+    if args.example is not None:
+        config_dict = yaml.safe_load(open(get_example_path(args.example + ".yaml")))
+    else:
+        config_dict = yaml.safe_load(open(args.config))
+    dial_config = load_dataclass_from_dict(DialConfig, config_dict)
+    rng = drandom.PRNGKey(seed=dial_config.seed)
+    env_config_type = dial_envs.get_config(dial_config.env_name)
+    env_config = load_dataclass_from_dict(env_config_type, config_dict, convert_list_to_array=True)
+    env = dial_envs.get_environment(dial_config.env_name, config=env_config)
+    mbdpi = MBDPI(dial_config, env)
+    rng, rng_reset = drandom.split(rng)
+    state = env.reset(rng_reset)
+    Y0 = torch.zeros(dial_config.Hnode + 1, mbdpi.nu, device=mbdpi.device)
+    rng_exp, rng = drandom.split(rng)
+    Nstep = args.n_steps or dial_config.n_steps
+    rews, rollout, infos = [], [], []
+    for t in range(Nstep):
+        state = env.step(state, Y0[0])
+        ps = state.pipeline_state
+        rollout.append(torch.cat([torch.tensor([float(t)], device=mbdpi.device), ps.qpos, ps.qvel, ps.ctrl]))
+        rews.append(state.reward)
+        Y0 = mbdpi.shift(Y0)
+        n_diffuse = dial_config.Ndiffuse_init if t == 0 else dial_config.Ndiffuse
+        t0 = time.time()
+        rng, Y0, info = mbdpi.reverse_scan(state, rng, Y0, mbdpi.schedule(n_diffuse))
+        torch.cuda.synchronize()
+        freq = 1 / (time.time() - t0)
+        infos.append(info["xbar"][-1])
+        if t % 10 == 0:
+            print(f"step {t}: rew={float(state.reward):.3e} freq={freq:.1f} Hz")
+    rew = torch.stack([torch.as_tensor(r) for r in rews]).mean()
+    print(f"mean reward = {float(rew):.2e}")
+    os.makedirs(dial_config.output_dir, exist_ok=True)
+    timestamp = time.strftime("%Y%m%d-%H%M%S")
+    np.save(os.path.join(dial_config.output_dir, f"{timestamp}_states"), torch.stack(rollout).cpu().numpy())
+    np.save(os.path.join(dial_config.output_dir, f"{timestamp}_predictions"), torch.stack(infos).cpu().numpy())
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,9 @@
 #ifdef DIAL_HOST_EMUL
 #include "warp_emul.h"
 #define DEV inline
+#define HD inline
 #else
+#define HD __host__ __device__ __forceinline__
 #define DEV __device__ __forceinline__
 #define DEVNI __device__ __noinline__
 DEV void syncwarp() { __syncwarp(); }
@@ -36,7 +38,7 @@ DEV int shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 #define DEVNI inline
 #endif
 
-#define DIAL_MAXCHAIN 14   // longest dof ancestor chain (H1: 6 + 5 = 11)
+#define DIAL_MAXCHAIN 12   // longest dof ancestor chain (H1: 6 + 5 = 11)
 #define DIAL_MAXLEVEL 28
 #define DIAL_MAXE 32       // contact pyramid edge rows (4 per contact)
 #define DIAL_MINVAL 1e-15f
@@ -49,7 +51,7 @@ enum { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1 };
 // ---------------------------------------------------------------------------------
 // device-side model: the C-ABI descriptor + host-derived schedules + smem offsets
 // ---------------------------------------------------------------------------------
-struct DevModel {
+struct alignas(16) DevModel {
   dial_model_desc m;
   // derived on the host (dial_capi.cu: derive_model)
   int32_t maxdepth;
@@ -64,15 +66,18 @@ struct DevModel {
   int32_t dof_actuator[DIAL_MAXV];    // actuator driving the dof or -1
   int32_t dof_limited[DIAL_MAXV];     // joint id if the dof's joint is limited else -1
   int32_t con_pair[DIAL_MAXC], con_sub[DIAL_MAXC];
+  int32_t con_lastdof[DIAL_MAXC];     // deepest dof moving the contact's body (geom1 must be static)
+  int32_t dof_nchain[DIAL_MAXV], dof_ndesc[DIAL_MAXV], nlimited;
+  int32_t chain_tab[DIAL_MAXV][DIAL_MAXCHAIN];
   int32_t nedge;                      // 4 * ncon
   // per-warp shared-memory layout (float offsets)
   int32_t o_xpos, o_xquat, o_xmat, o_xipos, o_cinert, o_cdof, o_cdofdot, o_cvel, o_cacc,
-      o_cfrc, o_M, o_L, o_J, o_qpos, o_qvel, o_warm, o_ctrl, o_vec, o_frow, o_cpos,
-      o_cframe, o_cdist, o_rcom, o_ldinv, o_site, o_misc, warp_floats;
+      o_cfrc, o_Mb, o_L, o_J, o_qpos, o_qvel, o_warm, o_ctrl, o_vec, o_frow, o_cpos,
+      o_cframe, o_cdist, o_rcom, o_xch, o_site, o_misc, warp_floats;
   int32_t pad_[3];
 };
 
-struct DevPlan {
+struct alignas(16) DevPlan {
   dial_plan_desc c;
   int32_t pad_[2];
 };
@@ -189,8 +194,8 @@ DEV void warp_sum3(float& a, float& b, float& c) {
 // Threefry-2x32 (20 rounds) and the JAX legacy normal sampler
 // (jax.random.normal at core/dial_core.py:107-109; third party, restated)
 // ---------------------------------------------------------------------------------
-DEV uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
-DEV void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+HD uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+HD void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
   uint32_t ks2 = k0 ^ k1 ^ 0x1BD11BDAu;
   x0 += k0; x1 += k1;
 #define TF_R(r) { x0 += x1; x1 = rotl32(x1, r); x1 ^= x0; }
@@ -241,130 +246,159 @@ DEV float jax_normal_legacy(uint32_t k0, uint32_t k1, uint32_t i, uint32_t n) {
 // ---------------------------------------------------------------------------------
 // per-warp context
 // ---------------------------------------------------------------------------------
+// "Compact chain coordinates": the mass matrix M and the Newton Hessian H = M + J^T D J of
+// a kinematic tree are non-zero only at (i, j) with j an ancestor-or-self dof of i.  Row i is
+// therefore stored as R[c] = H[i][chain_i[c]], c = 0..n_i-1, where chain_i = (i, parent(i),
+// ..., root dof) — and because the chain of an ancestor is a suffix of the chain of its
+// descendants, every tree operation below (reverse-order Cholesky L^T L without fill-in,
+// triangular solves, J^T D J rank-1 updates, M x) becomes index-free: an ancestor `a` of
+// pivot `k` sits at position n_k - n_a of k's row and needs positions n_k - n_a + c.
 struct WarpCtx {
   const DevModel* M;   // in shared memory
   const DevPlan* P;    // in shared memory
   float* s;            // this warp's slab
   int lane;
-  // lane-as-dof ancestor chain (self first, then parents)
-  int nchain;
+  int nch;             // chain length of this lane's dof (0: lane is not a dof)
+  int ndesc;           // descendant dofs (they follow the dof contiguously, DFS order)
+  int mylevel;         // elimination level of the dof (leaves = 0), -1 for non-dof lanes
+  int parent;          // parent dof or -1
   int chain[DIAL_MAXCHAIN];
 };
 
 #define SM(name) (w.s + w.M->o_##name)
+#define MC DIAL_MAXCHAIN
 
-// ---- sparse reverse-order Cholesky  H = L^T L  on the dof tree (no fill-in) ---------
-// L (lower triangle, dense rows) is overwritten in place.  Level-scheduled: all dofs of
-// one elimination level (never ancestors of each other) are pivots at the same time.
-DEVNI void factor_LTL(WarpCtx& w) {
+// H = L^T L (reverse order, no fill-in).  R: this lane's compact row, overwritten by the
+// factor row (diagonal = sqrt pivot); *invd = 1/L[i][i].  Factor rows are published in
+// SM(L) for the solves.  One syncwarp per elimination level.
+DEV void factor_LTL(WarpCtx& w, float* R, float& invd) {
   const DevModel& M = *w.M;
-  const int nv = M.m.nv, lane = w.lane;
-  float* L = SM(L);
-  float* ldinv = SM(ldinv);
-  const int mylevel = lane < nv ? M.dof_level[lane] : -1;
+  float* Lb = SM(L);
+  const int lane = w.lane;
   for (int lv = 0; lv < M.nlevel; ++lv) {
-    if (mylevel == lv) {
-      float d = sqrtf(fmaxf(L[lane * nv + lane], DIAL_MINVAL));
-      float inv = 1.f / d;
-      L[lane * nv + lane] = d;
-      ldinv[lane] = inv;
+    if (w.mylevel == lv) {
+      float inv = rsqrtf(fmaxf(R[0], DIAL_MINVAL));
+      invd = inv;
+      R[0] = R[0] * inv;
 #pragma unroll
-      for (int c = 1; c < DIAL_MAXCHAIN; ++c)
-        if (c < w.nchain) L[lane * nv + w.chain[c]] *= inv;
+      for (int c = 1; c < MC; ++c) R[c] *= inv;
+#pragma unroll
+      for (int c = 0; c < MC; ++c)
+        if (c < w.nch) Lb[lane * MC + c] = R[c];
     }
     syncwarp();
-    if (lane < nv && mylevel > lv) {
+    if (w.mylevel > lv) {
       for (int pi = M.level_adr[lv]; pi < M.level_adr[lv + 1]; ++pi) {
-        int k = M.level_dofs[pi];
+        const int k = M.level_dofs[pi];
         if ((M.dof_ancmask[k] >> lane) & 1u) {
-          float lki = L[k * nv + lane];
+          const float* Lk = Lb + k * MC + (M.dof_nchain[k] - w.nch);
+          const float l0 = Lk[0];
 #pragma unroll
-          for (int c = 0; c < DIAL_MAXCHAIN; ++c)
-            if (c < w.nchain) L[lane * nv + w.chain[c]] -= lki * L[k * nv + w.chain[c]];
+          for (int c = 0; c < MC; ++c)
+            if (c < w.nch) R[c] -= l0 * Lk[c];
         }
       }
     }
-    syncwarp();
   }
 }
 
-// solve (L^T L) x = g ; lane d holds g_d on entry and x_d on return.  Uses SM(vec).
-DEVNI float solve_LTL(WarpCtx& w, float g) {
+// solve (L^T L) x = g.  Lane d holds g_d / returns x_d; R, invd from factor_LTL.
+DEV float solve_LTL(WarpCtx& w, const float* R, float invd, float g) {
   const DevModel& M = *w.M;
-  const int nv = M.m.nv, lane = w.lane;
-  const float* L = SM(L);
-  const float* ldinv = SM(ldinv);
+  const float* Lb = SM(L);
   float* vec = SM(vec);
-  const int mylevel = lane < nv ? M.dof_level[lane] : -1;
+  float* xch = SM(xch);  // published ancestor chains of x: xch[d][c] = x[chain_d[c]]
+  const int lane = w.lane;
   float y = g;
   // L^T y = g : leaves -> root
   for (int lv = 0; lv < M.nlevel; ++lv) {
-    if (mylevel == lv) { y *= ldinv[lane]; vec[lane] = y; }
+    if (w.mylevel == lv) { y *= invd; vec[lane] = y; }
     syncwarp();
-    if (lane < nv && mylevel > lv) {
+    if (w.mylevel > lv) {
       for (int pi = M.level_adr[lv]; pi < M.level_adr[lv + 1]; ++pi) {
-        int k = M.level_dofs[pi];
-        if ((M.dof_ancmask[k] >> lane) & 1u) y -= L[k * nv + lane] * vec[k];
+        const int k = M.level_dofs[pi];
+        if ((M.dof_ancmask[k] >> lane) & 1u) y -= Lb[k * MC + (M.dof_nchain[k] - w.nch)] * vec[k];
       }
     }
   }
-  // L x = y : root -> leaves
+  // L x = y : root -> leaves; each dof publishes (x_d, x_parent, ...) for its children
   float x = 0.f;
   for (int lv = M.nlevel - 1; lv >= 0; --lv) {
-    if (mylevel == lv) {
+    if (w.mylevel == lv) {
       float acc = y;
+      float xa[MC];
 #pragma unroll
-      for (int c = 1; c < DIAL_MAXCHAIN; ++c)
-        if (c < w.nchain) acc -= L[lane * nv + w.chain[c]] * vec[w.chain[c]];
-      x = acc * ldinv[lane];
-      vec[lane] = x;
+      for (int c = 1; c < MC; ++c) {
+        xa[c] = 0.f;
+        if (c < w.nch) { xa[c] = xch[w.parent * MC + c - 1]; acc -= R[c] * xa[c]; }
+      }
+      x = acc * invd;
+      xch[lane * MC] = x;
+#pragma unroll
+      for (int c = 1; c < MC; ++c)
+        if (c < w.nch) xch[lane * MC + c] = xa[c];
     }
     syncwarp();
   }
   return x;
 }
 
-// y = M x (symmetric, lower triangle stored); lane d holds x_d / returns y_d.  Uses SM(vec).
-DEV float mul_M(WarpCtx& w, float x) {
-  const int nv = w.M->m.nv, lane = w.lane;
-  const float* Mm = SM(M);
+// y = M x; Mrow = this lane's compact row of M (also published in SM(Mb)).  Uses SM(vec).
+DEV float mul_M(WarpCtx& w, const float* Mrow, float x) {
+  const DevModel& M = *w.M;
+  const int lane = w.lane;
+  const float* Mb = SM(Mb);
   float* vec = SM(vec);
   syncwarp();
-  if (lane < nv) vec[lane] = x;
+  vec[lane] = x;
   syncwarp();
   float y = 0.f;
-  if (lane < nv) {
-    for (int j = 0; j <= lane; ++j) y += Mm[lane * nv + j] * vec[j];
-    for (int j = lane + 1; j < nv; ++j) y += Mm[j * nv + lane] * vec[j];
-  }
+#pragma unroll
+  for (int c = 0; c < MC; ++c)
+    if (c < w.nch) y += Mrow[c] * vec[w.chain[c]];
+  for (int k = lane + 1; k <= lane + w.ndesc; ++k) y += Mb[k * MC + (M.dof_nchain[k] - w.nch)] * vec[k];
   return y;
 }
 
-// contact-edge rows times a dof vector: lane e returns sum_d J[e][d] x_d.  Uses SM(vec).
+// contact-edge rows times a dof vector: lane e returns J_e . x.  J rows are stored compactly
+// along the chain of the contact body's last dof.  Uses SM(vec).
 DEV float mul_J(WarpCtx& w, float x) {
-  const int nv = w.M->m.nv, ne = w.M->nedge, lane = w.lane;
-  const float* J = SM(J);
+  const DevModel& M = *w.M;
+  const int lane = w.lane;
+  const float* Jc = SM(J);
   float* vec = SM(vec);
   syncwarp();
-  if (lane < nv) vec[lane] = x;
+  vec[lane] = x;
   syncwarp();
   float y = 0.f;
-  if (lane < ne)
-    for (int d = 0; d < nv; ++d) y += J[lane * nv + d] * vec[d];
+  if (lane < M.nedge) {
+    const int kc = M.con_lastdof[lane >> 2];
+    const int nk = M.dof_nchain[kc];
+    for (int p = 0; p < nk; ++p) y += Jc[lane * MC + p] * vec[M.chain_tab[kc][p]];
+  }
   return y;
 }
 
 // J^T f for the contact-edge rows: lane e holds f_e, lane d returns sum_e J[e][d] f_e.
 DEV float mul_JT(WarpCtx& w, float f) {
-  const int nv = w.M->m.nv, ne = w.M->nedge, lane = w.lane;
-  const float* J = SM(J);
+  const DevModel& M = *w.M;
+  const int lane = w.lane;
+  const float* Jc = SM(J);
   float* frow = SM(frow);
   syncwarp();
-  if (lane < ne) frow[lane] = f;
+  frow[lane] = f;
   syncwarp();
   float y = 0.f;
-  if (lane < nv)
-    for (int e = 0; e < ne; ++e) y += J[e * nv + lane] * frow[e];
+  if (w.nch > 0) {
+    for (int c = 0; c < M.m.ncon; ++c) {
+      const int kc = M.con_lastdof[c];
+      if ((M.dof_ancmask[kc] >> lane) & 1u) {
+        const int off = M.dof_nchain[kc] - w.nch;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) y += Jc[(4 * c + e) * MC + off] * frow[4 * c + e];
+      }
+    }
+  }
   return y;
 }
 
@@ -382,9 +416,14 @@ DEV void kbi(float timestep, const float* solref, const float* solimp, float pos
   if (solref[0] <= 0.f) k = -solref[0] / (dmax * dmax);
   if (solref[1] <= 0.f) b = -solref[1] / dmax;
   float x = fabsf(pos) / width;
-  float a_ = (1.f / powf(mid, power - 1.f)) * powf(x, power);
-  float b_ = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(fmaxf(1.f - x, 0.f), power);
-  float y = x < mid ? a_ : b_;
+  float y;
+  if (power == 2.f) {  // the MuJoCo default; avoids four powf calls
+    y = x < mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+  } else {
+    float a_ = (1.f / powf(mid, power - 1.f)) * powf(x, power);
+    float b_ = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(fmaxf(1.f - x, 0.f), power);
+    y = x < mid ? a_ : b_;
+  }
   imp = dmin + y * (dmax - dmin);
   imp = fminf(fmaxf(imp, dmin), dmax);
   if (x > 1.f) imp = dmax;
@@ -396,115 +435,111 @@ DEV void kbi(float timestep, const float* solref, const float* solimp, float pos
 //   lane e (< nedge): contact pyramid edge row e
 // ---------------------------------------------------------------------------------
 struct Solver {
-  // dof vectors
-  float qacc, Ma, grad, Mgrad, search, qfs, qas;  // qfs = qfrc_smooth, qas = qacc_smooth
-  // limit row (lane = dof)
-  float l_sign, l_D, l_aref, l_Jaref;
-  // contact edge row (lane = edge)
-  float e_D, e_aref, e_Jaref;
-  // scalars (warp-uniform)
-  float gauss, cost, prev_cost;
+  float qacc, Ma, grad, search, qfs, qas;  // qfs = qfrc_smooth, qas = qacc_smooth
+  float l_sign, l_D, l_aref, l_Jaref;      // limit row (lane = dof)
+  float e_D, e_aref, e_Jaref;              // contact edge row (lane = edge)
+  float gauss, cost, prev_cost, gradnorm2; // warp-uniform scalars
 };
 
+// efc_force, qfrc_constraint, costs and the gradient (solver.py _update_constraint + grad)
 DEV void update_constraint(WarpCtx& w, Solver& S) {
-  // efc_force = D * -Jaref * active ; qfrc_constraint = J^T force ; costs
   float fl = (S.l_Jaref < 0.f) ? -S.l_D * S.l_Jaref : 0.f;
   float fe = (S.e_Jaref < 0.f) ? -S.e_D * S.e_Jaref : 0.f;
   float qfc = mul_JT(w, fe) + S.l_sign * fl;
+  S.grad = S.Ma - S.qfs - qfc;
   float g = (S.Ma - S.qfs) * (S.qacc - S.qas);
   float c = ((S.l_Jaref < 0.f) ? S.l_D * S.l_Jaref * S.l_Jaref : 0.f)
           + ((S.e_Jaref < 0.f) ? S.e_D * S.e_Jaref * S.e_Jaref : 0.f);
-  float dummy = 0.f;
-  warp_sum3(g, c, dummy);
+  float g2 = S.grad * S.grad;
+  warp_sum3(g, c, g2);
   S.gauss = 0.5f * g;
   S.prev_cost = S.cost;
   S.cost = 0.5f * c + S.gauss;
-  S.grad = S.Ma - S.qfs - qfc;
+  S.gradnorm2 = g2;
 }
 
-// H = M + J^T D_active J  (tree-sparse), factor, Mgrad = H^-1 grad
-DEV void update_gradient(WarpCtx& w, Solver& S) {
+// compact row of H = M + J^T D_active J for this lane's dof
+DEV void build_H(WarpCtx& w, const Solver& S, const float* Mrow, float* R) {
   const DevModel& M = *w.M;
-  const int nv = M.m.nv, ne = M.nedge, lane = w.lane;
-  const float* Mm = SM(M);
-  const float* J = SM(J);
-  float* L = SM(L);
+  const int lane = w.lane;
+  const float* Jc = SM(J);
   float* frow = SM(frow);
   syncwarp();
-  if (lane < ne) frow[lane] = (S.e_Jaref < 0.f) ? S.e_D : 0.f;
+  frow[lane] = (S.e_Jaref < 0.f) ? S.e_D : 0.f;
   syncwarp();
-  if (lane < nv) {
-    float acc[DIAL_MAXCHAIN];
 #pragma unroll
-    for (int c = 0; c < DIAL_MAXCHAIN; ++c) acc[c] = (c < w.nchain) ? Mm[lane * nv + w.chain[c]] : 0.f;
-    for (int e = 0; e < ne; ++e) {
-      float a = frow[e] * J[e * nv + lane];
-      if (a != 0.f) {
+  for (int c = 0; c < MC; ++c) R[c] = Mrow[c];
+  if (w.nch > 0) {
+    R[0] += (S.l_Jaref < 0.f) ? S.l_D : 0.f;  // limit rows are +-e_d: diagonal only
+    for (int c_ = 0; c_ < M.m.ncon; ++c_) {
+      const int kc = M.con_lastdof[c_];
+      if ((M.dof_ancmask[kc] >> lane) & 1u) {
+        const int off = M.dof_nchain[kc] - w.nch;
+        for (int e = 4 * c_; e < 4 * c_ + 4; ++e) {
+          const float de = frow[e];
+          if (de != 0.f) {
+            const float* Je = Jc + e * MC + off;
+            const float a = de * Je[0];
 #pragma unroll
-        for (int c = 0; c < DIAL_MAXCHAIN; ++c)
-          if (c < w.nchain) acc[c] += a * J[e * nv + w.chain[c]];
+            for (int c = 0; c < MC; ++c)
+              if (c < w.nch) R[c] += a * Je[c];
+          }
+        }
       }
     }
-    acc[0] += (S.l_Jaref < 0.f) ? S.l_D : 0.f;  // limit rows are +-e_d: diagonal only
-#pragma unroll
-    for (int c = 0; c < DIAL_MAXCHAIN; ++c)
-      if (c < w.nchain) L[lane * nv + w.chain[c]] = acc[c];
   }
-  syncwarp();
-  factor_LTL(w);
-  S.Mgrad = solve_LTL(w, S.grad);
 }
 
 struct LSPoint { float alpha, cost, d0, d1; };
 
-// evaluate the 1-D piecewise-quadratic cost at up to three alphas at once
-DEV void ls_points3(const Solver& S, float l_jv, float e_jv, const float* qg,
-                    float a0, float a1, float a2, LSPoint& p0, LSPoint& p1, LSPoint& p2) {
-  float s[9];
+// evaluate the 1-D piecewise-quadratic cost at NA (<= 3) alphas at once
+template <int NA>
+DEV void ls_points(const Solver& S, float l_jv, float e_jv, const float* qg, const float* al, LSPoint* out) {
+  float s[3 * NA];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) s[i] = 0.f;
-  const float al[3] = {a0, a1, a2};
+  for (int i = 0; i < 3 * NA; ++i) s[i] = 0.f;
   {
     float q0 = 0.5f * S.l_Jaref * S.l_Jaref * S.l_D, q1 = l_jv * S.l_Jaref * S.l_D, q2 = 0.5f * l_jv * l_jv * S.l_D;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < NA; ++i)
       if (S.l_Jaref + al[i] * l_jv < 0.f) { s[3 * i] += q0; s[3 * i + 1] += q1; s[3 * i + 2] += q2; }
     q0 = 0.5f * S.e_Jaref * S.e_Jaref * S.e_D; q1 = e_jv * S.e_Jaref * S.e_D; q2 = 0.5f * e_jv * e_jv * S.e_D;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < NA; ++i)
       if (S.e_Jaref + al[i] * e_jv < 0.f) { s[3 * i] += q0; s[3 * i + 1] += q1; s[3 * i + 2] += q2; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) s[i] += shfl_xor(s[i], o);
+    for (int i = 0; i < 3 * NA; ++i) s[i] += shfl_xor(s[i], o);
   }
-  LSPoint* out[3] = {&p0, &p1, &p2};
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < NA; ++i) {
     float t0 = qg[0] + s[3 * i], t1 = qg[1] + s[3 * i + 1], t2 = qg[2] + s[3 * i + 2];
     float a = al[i];
-    out[i]->alpha = a;
-    out[i]->cost = a * a * t2 + a * t1 + t0;
-    out[i]->d0 = 2.f * a * t2 + t1;
-    out[i]->d1 = 2.f * t2 + (t2 == 0.f ? DIAL_MINVAL : 0.f);
+    out[i].alpha = a;
+    out[i].cost = a * a * t2 + a * t1 + t0;
+    out[i].d0 = 2.f * a * t2 + t1;
+    out[i].d1 = 2.f * t2 + (t2 == 0.f ? DIAL_MINVAL : 0.f);
   }
 }
 
-DEV void linesearch(WarpCtx& w, Solver& S) {
+DEV void linesearch(WarpCtx& w, Solver& S, const float* Mrow) {
   const DevModel& M = *w.M;
   const int nv = M.m.nv;
   const float scale = M.m.meaninertia * (float)(nv > 1 ? nv : 1);
-  float mv = mul_M(w, S.search);
+  float mv = mul_M(w, Mrow, S.search);
   float e_jv = mul_J(w, S.search);
   float l_jv = S.l_sign * S.search;
   float ss = S.search * S.search, sMa = S.search * (S.Ma - S.qfs), sMv = S.search * mv;
   warp_sum3(ss, sMa, sMv);
   float gtol = M.m.tolerance * M.m.ls_tolerance * sqrtf(ss) * scale;
   float qg[3] = {S.gauss, sMa, 0.5f * sMv};
-  LSPoint p0, lo, hi, t1, t2;
-  ls_points3(S, l_jv, e_jv, qg, 0.f, 0.f, 0.f, p0, t1, t2);
-  ls_points3(S, l_jv, e_jv, qg, p0.alpha - p0.d0 / p0.d1, 0.f, 0.f, lo, t1, t2);
+  LSPoint p0, lo, hi;
+  float a1[1] = {0.f};
+  ls_points<1>(S, l_jv, e_jv, qg, a1, &p0);
+  a1[0] = p0.alpha - p0.d0 / p0.d1;
+  ls_points<1>(S, l_jv, e_jv, qg, a1, &lo);
   if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
   bool swap = true;
   for (int it = 0; it < M.m.ls_iterations; ++it) {
@@ -512,9 +547,10 @@ DEV void linesearch(WarpCtx& w, Solver& S) {
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
     if (done) break;
-    LSPoint lo_next, hi_next, mid;
-    ls_points3(S, l_jv, e_jv, qg, lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1,
-               0.5f * (lo.alpha + hi.alpha), lo_next, hi_next, mid);
+    LSPoint pt[3];
+    float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+    ls_points<3>(S, l_jv, e_jv, qg, a3, pt);
+    const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
     bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
     if (swap_lo_next) lo = lo_next;
     bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
@@ -534,60 +570,19 @@ DEV void linesearch(WarpCtx& w, Solver& S) {
   S.e_Jaref += alpha * e_jv;
 }
 
-// cost of a candidate start point (warm-start selection, solver.py `_Context.create(grad=False)`)
-DEV float candidate_cost(WarpCtx& w, Solver& S, float qacc) {
-  float Ma = mul_M(w, qacc);
-  float eJ = mul_J(w, qacc) - S.e_aref;
-  float lJ = S.l_sign * qacc - S.l_aref;
-  float g = (Ma - S.qfs) * (qacc - S.qas);
-  float c = ((lJ < 0.f) ? S.l_D * lJ * lJ : 0.f) + ((eJ < 0.f) ? S.e_D * eJ * eJ : 0.f);
-  float dummy = 0.f;
-  warp_sum3(g, c, dummy);
-  return 0.5f * c + 0.5f * g;
-}
-
-DEV float newton_solve(WarpCtx& w, Solver& S, float warmstart) {
-  const DevModel& M = *w.M;
-  const int nv = M.m.nv;
-  const float scale = M.m.meaninertia * (float)(nv > 1 ? nv : 1);
-  float cw = candidate_cost(w, S, warmstart);
-  float cs = candidate_cost(w, S, S.qas);
-  S.qacc = (cw < cs) ? warmstart : S.qas;
-  S.Ma = mul_M(w, S.qacc);
-  S.e_Jaref = mul_J(w, S.qacc) - S.e_aref;
-  S.l_Jaref = S.l_sign * S.qacc - S.l_aref;
-  S.cost = INFINITY;
-  S.prev_cost = 0.f;
-  update_constraint(w, S);
-  update_gradient(w, S);
-  S.search = -S.Mgrad;
-  for (int it = 0; it < M.m.iterations; ++it) {
-    if (M.m.iterations != 1) {
-      float g2 = warp_sum(S.grad * S.grad);
-      float improvement = (S.prev_cost - S.cost) / scale;
-      float gradient = sqrtf(g2) / scale;
-      if (improvement < M.m.tolerance || gradient < M.m.tolerance) break;
-    }
-    linesearch(w, S);
-    update_constraint(w, S);
-    update_gradient(w, S);
-    S.search = -S.Mgrad;
-  }
-  return S.qacc;
-}
 
 // ---------------------------------------------------------------------------------
 // one physics step (mjx.step) for the warp's sample.  State (qpos,qvel,warm,ctrl) in
 // the slab; kinematic arrays of the forward pass are left in the slab for the reward.
 // ---------------------------------------------------------------------------------
-DEVNI void physics_step(WarpCtx& w, bool integrate) {
+DEV void physics_step(WarpCtx& w, bool integrate) {
   const DevModel& M = *w.M;
   const dial_model_desc& m = M.m;
   const int lane = w.lane, nb = m.nbody, nv = m.nv;
   float* xpos = SM(xpos); float* xquat = SM(xquat); float* xmat = SM(xmat); float* xipos = SM(xipos);
   float* cinert = SM(cinert); float* cdof = SM(cdof); float* cdofdot = SM(cdofdot);
   float* cvel = SM(cvel); float* cacc = SM(cacc); float* cfrc = SM(cfrc);
-  float* Mm = SM(M); float* J = SM(J);
+  float* J = SM(J);
   float* qpos = SM(qpos); float* qvel = SM(qvel); float* warm = SM(warm); float* ctrl = SM(ctrl);
   float* cpos = SM(cpos); float* cframe = SM(cframe); float* cdist = SM(cdist); float* rcom = SM(rcom);
 
@@ -767,52 +762,6 @@ DEVNI void physics_step(WarpCtx& w, bool integrate) {
     syncwarp();
   }
 
-  // ---- 6. mass-matrix rows, bias, smooth force (lane = dof) ---------------------------
-  Solver S;
-  S.qfs = 0.f; S.qas = 0.f;
-  S.l_sign = 0.f; S.l_D = 0.f; S.l_aref = 0.f; S.l_Jaref = 0.f;
-  S.e_D = 0.f; S.e_aref = 0.f; S.e_Jaref = 0.f;
-  S.qacc = S.Ma = S.grad = S.Mgrad = S.search = 0.f;
-  S.gauss = S.cost = S.prev_cost = 0.f;
-  const int d = lane;
-  const bool isdof = d < nv;
-  float myqvel = isdof ? qvel[d] : 0.f;
-  if (isdof) {
-    int bi = m.dof_bodyid[d];
-    float f[6];
-    inert_mul(cinert + 10 * bi, cdof + 6 * d, f);
-    for (int j = 0; j <= d; ++j) Mm[d * nv + j] = 0.f;
-#pragma unroll
-    for (int c = 0; c < DIAL_MAXCHAIN; ++c)
-      if (c < w.nchain) Mm[d * nv + w.chain[c]] = dot6(f, cdof + 6 * w.chain[c]);
-    Mm[d * nv + d] += m.dof_armature[d];
-    float bias = dot6(cdof + 6 * d, cfrc + 6 * bi);
-    float act = 0.f;
-    int a = M.dof_actuator[d];
-    if (a >= 0) {
-      float c = ctrl[a];
-      if (m.actuator_ctrllimited[a]) c = fminf(fmaxf(c, m.actuator_ctrlrange[a][0]), m.actuator_ctrlrange[a][1]);
-      float force = m.actuator_gain[a] * c + m.actuator_bias[a][0]
-                  + m.actuator_bias[a][1] * qpos[m.actuator_qposadr[a]] + m.actuator_bias[a][2] * myqvel;
-      if (m.actuator_forcelimited[a]) force = fminf(fmaxf(force, m.actuator_forcerange[a][0]), m.actuator_forcerange[a][1]);
-      act = force * m.actuator_gear[a];
-    }
-    S.qfs = -m.dof_damping[d] * myqvel - bias + act;
-  }
-  syncwarp();
-  // qacc_smooth = M^-1 qfrc_smooth
-  {
-    float* L = SM(L);
-    if (isdof) {
-#pragma unroll
-      for (int c = 0; c < DIAL_MAXCHAIN; ++c)
-        if (c < w.nchain) L[d * nv + w.chain[c]] = Mm[d * nv + w.chain[c]];
-    }
-    syncwarp();
-    factor_LTL(w);
-    S.qas = solve_LTL(w, S.qfs);
-  }
-
   // ---- 7. collision (lane = contact) ---------------------------------------------------
   if (lane < m.ncon) {
     int k = M.con_pair[lane];
@@ -867,26 +816,66 @@ DEVNI void physics_step(WarpCtx& w, bool integrate) {
   }
   syncwarp();
 
+  // ---- 6. compact mass-matrix row, bias, smooth force (lane = dof) ----------------------
+  Solver S;
+  S.qfs = 0.f; S.qas = 0.f;
+  S.l_sign = 0.f; S.l_D = 0.f; S.l_aref = 0.f; S.l_Jaref = 0.f;
+  S.e_D = 0.f; S.e_aref = 0.f; S.e_Jaref = 0.f;
+  S.qacc = S.Ma = S.grad = S.search = 0.f;
+  S.gauss = S.cost = S.prev_cost = S.gradnorm2 = 0.f;
+  const int d = lane;
+  const bool isdof = d < nv;
+  float myqvel = isdof ? qvel[d] : 0.f;
+  float Mrow[MC], R[MC];
+#pragma unroll
+  for (int c = 0; c < MC; ++c) { Mrow[c] = 0.f; R[c] = 0.f; }
+  if (isdof) {
+    int bi = m.dof_bodyid[d];
+    float f[6];
+    inert_mul(cinert + 10 * bi, cdof + 6 * d, f);
+#pragma unroll
+    for (int c = 0; c < MC; ++c)
+      if (c < w.nch) Mrow[c] = dot6(f, cdof + 6 * w.chain[c]);
+    Mrow[0] += m.dof_armature[d];
+    float* Mb = SM(Mb);
+#pragma unroll
+    for (int c = 0; c < MC; ++c)
+      if (c < w.nch) Mb[d * MC + c] = Mrow[c];
+    float bias = dot6(cdof + 6 * d, cfrc + 6 * bi);
+    float act = 0.f;
+    int a = M.dof_actuator[d];
+    if (a >= 0) {
+      float c = ctrl[a];
+      if (m.actuator_ctrllimited[a]) c = fminf(fmaxf(c, m.actuator_ctrlrange[a][0]), m.actuator_ctrlrange[a][1]);
+      float force = m.actuator_gain[a] * c + m.actuator_bias[a][0]
+                  + m.actuator_bias[a][1] * qpos[m.actuator_qposadr[a]] + m.actuator_bias[a][2] * myqvel;
+      if (m.actuator_forcelimited[a]) force = fminf(fmaxf(force, m.actuator_forcerange[a][0]), m.actuator_forcerange[a][1]);
+      act = force * m.actuator_gear[a];
+    }
+    S.qfs = -m.dof_damping[d] * myqvel - bias + act;
+  }
+
   // ---- 8. constraint rows ----------------------------------------------------------------
-  // contact Jacobian columns (lane = dof): J[4c+e][d]
+  // contact Jacobian, compact along the chain of the contact body's last dof (lane = dof)
   if (isdof) {
     V3 ca_ = ld3(cdof + 6 * d), cl_ = ld3(cdof + 6 * d + 3);
     int rootb = M.body_rootidx[m.dof_bodyid[d]];
     V3 rc = ld3(rcom + 3 * rootb);
     for (int c = 0; c < m.ncon; ++c) {
-      int k = M.con_pair[c];
-      int b1 = m.geom_bodyid[m.pair_geom1[k]], b2 = m.geom_bodyid[m.pair_geom2[k]];
-      float sgn = (float)((M.body_dofmask[b2] >> d) & 1u) - (float)((M.body_dofmask[b1] >> d) & 1u);
+      const int kc = M.con_lastdof[c];
+      if (!((M.dof_ancmask[kc] >> d) & 1u)) continue;
+      const int k = M.con_pair[c];
+      const int p_ = M.dof_nchain[kc] - w.nch;
       float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-      if (sgn != 0.f && cdist[c] - (m.pair_margin[k] - m.pair_gap[k]) < 0.f) {
+      if (cdist[c] - (m.pair_margin[k] - m.pair_gap[k]) < 0.f) {
         V3 p = ld3(cpos + 3 * c);
-        V3 jp = (cl_ + cross(ca_, p - rc)) * sgn;
+        V3 jp = cl_ + cross(ca_, p - rc);
         float jn = dot(ld3(cframe + 9 * c), jp), j1 = dot(ld3(cframe + 9 * c + 3), jp), j2 = dot(ld3(cframe + 9 * c + 6), jp);
         float mu0 = m.pair_friction[k][0], mu1 = m.pair_friction[k][1];
         e0 = jn + mu0 * j1; e1 = jn - mu0 * j1; e2 = jn + mu1 * j2; e3 = jn - mu1 * j2;
       }
-      J[(4 * c + 0) * nv + d] = e0; J[(4 * c + 1) * nv + d] = e1;
-      J[(4 * c + 2) * nv + d] = e2; J[(4 * c + 3) * nv + d] = e3;
+      J[(4 * c + 0) * MC + p_] = e0; J[(4 * c + 1) * MC + p_] = e1;
+      J[(4 * c + 2) * MC + p_] = e2; J[(4 * c + 3) * MC + p_] = e3;
     }
     // joint-limit row of this dof
     int lj = M.dof_limited[d];
@@ -898,9 +887,9 @@ DEVNI void physics_step(WarpCtx& w, bool integrate) {
         float sign = dmin < dmax ? 1.f : -1.f;
         float k_, b_, imp;
         kbi(m.timestep, m.jnt_solref[lj], m.jnt_solimp[lj], pos, k_, b_, imp);
-        float R = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, DIAL_MINVAL);
+        float Rr = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, DIAL_MINVAL);
         S.l_sign = sign;
-        S.l_D = 1.f / R;
+        S.l_D = 1.f / Rr;
         S.l_aref = -b_ * (sign * myqvel) - k_ * imp * pos;
       }
     }
@@ -918,15 +907,65 @@ DEVNI void physics_step(WarpCtx& w, bool integrate) {
       float iw = (t + mu * mu * t) * 2.f * mu * mu / m.impratio;
       float k_, b_, imp;
       kbi(m.timestep, m.pair_solref[k], m.pair_solimp[k], pos, k_, b_, imp);
-      float R = fmaxf(iw * (1.f - imp) / imp, DIAL_MINVAL);
-      S.e_D = 1.f / R;
+      float Rr = fmaxf(iw * (1.f - imp) / imp, DIAL_MINVAL);
+      S.e_D = 1.f / Rr;
       S.e_aref = -b_ * ejv - k_ * imp * pos;
     }
   }
 
-  // ---- 9. Newton solve --------------------------------------------------------------------
-  float mywarm = isdof ? warm[d] : 0.f;
-  float qacc = newton_solve(w, S, mywarm);
+  // ---- 9. qacc_smooth and the Newton solve (mjx solver.solve), one factor/solve site ------
+  //   pass 0: R = M, g = qfrc_smooth            -> qacc_smooth, warm-start choice, ctx init
+  //   pass n: R = H(active set), g = grad        -> search = -H^-1 grad, line search
+  const float scale = m.meaninertia * (float)(nv > 1 ? nv : 1);
+  const float mywarm = isdof ? warm[d] : 0.f;
+  float g = S.qfs;
+#pragma unroll
+  for (int c = 0; c < MC; ++c) R[c] = Mrow[c];
+  int phase = 0, it = 0;
+  while (true) {
+    float invd = 0.f;
+    factor_LTL(w, R, invd);
+    float x = solve_LTL(w, R, invd, g);
+    if (phase == 0) {
+      S.qas = x;
+      if (M.nedge == 0 && M.nlimited == 0) { S.qacc = x; break; }
+      // warm start: whichever of qacc_warmstart / qacc_smooth has the lower cost
+      float Maw = mul_M(w, Mrow, mywarm);
+      float eJw = mul_J(w, mywarm) - S.e_aref;
+      float lJw = S.l_sign * mywarm - S.l_aref;
+      float gw = (Maw - S.qfs) * (mywarm - S.qas);
+      float cw = ((lJw < 0.f) ? S.l_D * lJw * lJw : 0.f) + ((eJw < 0.f) ? S.e_D * eJw * eJw : 0.f);
+      float Mas = mul_M(w, Mrow, S.qas);
+      float eJs = mul_J(w, S.qas) - S.e_aref;
+      float lJs = S.l_sign * S.qas - S.l_aref;
+      float cs = ((lJs < 0.f) ? S.l_D * lJs * lJs : 0.f) + ((eJs < 0.f) ? S.e_D * eJs * eJs : 0.f);
+      warp_sum3(gw, cw, cs);
+      const bool usewarm = (0.5f * cw + 0.5f * gw) < (0.5f * cs);  // gauss(qacc_smooth) = 0
+      S.qacc = usewarm ? mywarm : S.qas;
+      S.Ma = usewarm ? Maw : Mas;
+      S.e_Jaref = usewarm ? eJw : eJs;
+      S.l_Jaref = usewarm ? lJw : lJs;
+      S.cost = INFINITY;
+      S.prev_cost = 0.f;
+    } else {
+      S.search = -x;
+      linesearch(w, S, Mrow);
+      ++it;
+    }
+    update_constraint(w, S);
+    // mjx `cond`: iteration budget, cost improvement, gradient norm (rescaled)
+    bool done = (phase == 1) && (it >= m.iterations);
+    if (m.iterations != 1 || phase == 1) {
+      float improvement = (S.prev_cost - S.cost) / scale;
+      float gradient = sqrtf(S.gradnorm2) / scale;
+      if (m.iterations != 1) done = done || (improvement < m.tolerance) || (gradient < m.tolerance);
+    }
+    if (done) break;
+    phase = 1;
+    build_H(w, S, Mrow, R);
+    g = S.grad;
+  }
+  const float qacc = S.qacc;
 
   // ---- 10. semi-implicit Euler -------------------------------------------------------------
   syncwarp();
@@ -1068,16 +1107,17 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
   const dial_plan_desc& c = Pp->c;
   const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody;
   // ancestor chain of this lane's dof
-  w.nchain = 0;
+  w.nch = 0; w.ndesc = 0; w.mylevel = -1; w.parent = -1;
 #pragma unroll
   for (int i = 0; i < DIAL_MAXCHAIN; ++i) w.chain[i] = 0;
   if (lane < nv) {
-    int j = lane, n = 0;
+    w.nch = M.dof_nchain[lane];
+    w.ndesc = M.dof_ndesc[lane];
+    w.mylevel = M.dof_level[lane];
+    w.parent = m.dof_parentid[lane];
 #pragma unroll
-    for (int i = 0; i < DIAL_MAXCHAIN; ++i) {
-      if (j >= 0) { w.chain[i] = j; n = i + 1; j = M.m.dof_parentid[j]; }
-    }
-    w.nchain = n;
+    for (int i = 0; i < DIAL_MAXCHAIN; ++i)
+      if (i < w.nch) w.chain[i] = M.chain_tab[lane][i];
   }
   // initial state + world body constants
   for (int i = lane; i < nq; i += 32) SM(qpos)[i] = A.qpos0[i];
@@ -1093,15 +1133,6 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     SM(cacc)[3] = -m.gravity[0]; SM(cacc)[4] = -m.gravity[1]; SM(cacc)[5] = -m.gravity[2];
   }
   syncwarp();
-
-  if (A.mode == 2) {  // pipeline_init: forward only
-    if (lane < nu) SM(ctrl)[lane] = 0.f;
-    syncwarp();
-    physics_step(w, false);
-    if (A.qpos_out) for (int i = lane; i < nq; i += 32) A.qpos_out[i] = SM(qpos)[i];
-    if (A.warm_out) for (int i = lane; i < nv; i += 32) A.warm_out[i] = SM(warm)[i];
-    return;
-  }
 
   // control knots of this sample (lane = actuator)
   const int Hn1 = c.Hnode + 1;
@@ -1129,9 +1160,13 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
 
   int step = A.step0, stage = A.stage0;
   float rsum = 0.f;
-  for (int t = 0; t < A.H; ++t) {
+  const bool fwd_only = A.mode == 2;  // pipeline_init: mjx.forward only, zero ctrl
+  const int H = fwd_only ? 1 : A.H;
+  const int nfr = fwd_only ? 1 : c.n_frames;
+  for (int t = 0; t < H; ++t) {
     // action -> joint target -> torque (base_env.py:37-66)
-    if (lane < nu) {
+    if (lane < nu && fwd_only) SM(ctrl)[lane] = 0.f;
+    if (lane < nu && !fwd_only) {
       float u;
       if (A.mode == 0) {
         u = A.us[((size_t)row * A.H + t) * nu + lane];
@@ -1152,7 +1187,8 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
       SM(ctrl)[lane] = ctrl;
     }
     syncwarp();
-    for (int f = 0; f < c.n_frames; ++f) physics_step(w, true);
+    for (int f = 0; f < nfr; ++f) physics_step(w, !fwd_only);
+    if (fwd_only) break;
     float rew = 0.f;
     if (lane == 0) rew = reward_lane0(w, step, stage);
     stage = shfl_i(stage, 0);
@@ -1165,7 +1201,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     if (A.qd) for (int i = lane; i < nv; i += 32) A.qd[rt * nv + i] = SM(qvel)[i];
     if (A.xpos) for (int i = lane; i < 3 * (nb - 1); i += 32) A.xpos[rt * 3 * (nb - 1) + i] = SM(xpos)[3 + i];
   }
-  if (A.rews && lane == 0) A.rews[row] = rsum / (float)A.H;
+  if (A.rews && lane == 0 && !fwd_only) A.rews[row] = rsum / (float)A.H;
   if (row == 0) {
     if (A.qpos_out) for (int i = lane; i < nq; i += 32) A.qpos_out[i] = SM(qpos)[i];
     if (A.qvel_out) for (int i = lane; i < nv; i += 32) A.qvel_out[i] = SM(qvel)[i];

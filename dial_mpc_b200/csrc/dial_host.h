@@ -53,6 +53,16 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
     while (j >= 0) { mask |= 1u << j; j = m.dof_parentid[j]; ++n; }
     if (n > DIAL_MAXCHAIN) { err = "dof ancestor chain longer than DIAL_MAXCHAIN"; return false; }
     D.dof_ancmask[i] = mask;
+    D.dof_nchain[i] = n;
+    j = i; n = 0;
+    while (j >= 0) { D.chain_tab[i][n++] = j; j = m.dof_parentid[j]; }
+  }
+  for (int i = 0; i < nv; ++i) {
+    int nd = 0;
+    for (int k = i + 1; k < nv; ++k) if ((D.dof_ancmask[k] >> i) & 1u) ++nd;
+    D.dof_ndesc[i] = nd;
+    for (int k = i + 1; k <= i + nd; ++k)
+      if (!((D.dof_ancmask[k] >> i) & 1u)) { err = "dofs are not in depth-first order"; return false; }
   }
   for (int i = nv - 1; i >= 0; --i) {
     int lv = 0;
@@ -83,6 +93,7 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
     for (int a = 0; a < m.nu; ++a) if (m.actuator_dofadr[a] == d) D.dof_actuator[d] = a;
     int j = m.dof_jntid[d];
     D.dof_limited[d] = (m.jnt_limited[j] && m.jnt_type[j] != JNT_FREE) ? j : -1;
+    if (D.dof_limited[d] >= 0) D.nlimited++;
   }
   int c = 0;
   for (int k = 0; k < m.npair; ++k) {
@@ -90,7 +101,17 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
       err = "unsupported contact pair kind on the CUDA path";
       return false;
     }
-    for (int s = 0; s < m.pair_ncon[k]; ++s) { D.con_pair[c] = k; D.con_sub[c] = s; ++c; }
+    {
+      int b1 = m.geom_bodyid[m.pair_geom1[k]], b2 = m.geom_bodyid[m.pair_geom2[k]];
+      if (D.body_dofmask[b1] != 0u || D.body_dofmask[b2] == 0u) {
+        err = "contact pairs must be (static geom, moving geom) on the CUDA path";
+        return false;
+      }
+      int last = 0;
+      for (int d = 0; d < nv; ++d) if ((D.body_dofmask[b2] >> d) & 1u) last = d;
+      if (D.dof_ancmask[last] != D.body_dofmask[b2]) { err = "contact body dofs do not form one chain"; return false; }
+      for (int s = 0; s < m.pair_ncon[k]; ++s) { D.con_pair[c] = k; D.con_sub[c] = s; D.con_lastdof[c] = last; ++c; }
+    }
   }
   if (c != m.ncon) { err = "pair_ncon does not sum to ncon"; return false; }
   D.nedge = 4 * m.ncon;
@@ -100,10 +121,10 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   D.o_xpos = take(3 * nb); D.o_xquat = take(4 * nb); D.o_xmat = take(9 * nb); D.o_xipos = take(3 * nb);
   D.o_cinert = take(10 * nb); D.o_cdof = take(6 * nv); D.o_cdofdot = take(6 * nv);
   D.o_cvel = take(6 * nb); D.o_cacc = take(6 * nb); D.o_cfrc = take(6 * nb);
-  D.o_M = take(nv * nv); D.o_L = take(nv * nv); D.o_J = take(D.nedge * nv);
+  D.o_Mb = take(nv * DIAL_MAXCHAIN); D.o_L = take(nv * DIAL_MAXCHAIN); D.o_J = take(D.nedge * DIAL_MAXCHAIN);
   D.o_qpos = take(m.nq); D.o_qvel = take(nv); D.o_warm = take(nv); D.o_ctrl = take(m.nu);
   D.o_vec = take(32); D.o_frow = take(32); D.o_cpos = take(3 * m.ncon); D.o_cframe = take(9 * m.ncon);
-  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_ldinv = take(nv); D.o_site = take(3 * m.nsite);
+  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = take(nv * DIAL_MAXCHAIN); D.o_site = take(3 * m.nsite);
   D.o_misc = take(8);
   D.warp_floats = o;
   return true;

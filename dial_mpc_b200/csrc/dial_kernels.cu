@@ -1,0 +1,405 @@
+// dial_kernels.cu — sm_100a kernels + the C ABI of include/dial_b200.h.
+//
+// Kernels
+//   rollout_kernel<WPC>   one warp per sample row, persistent over the horizon; the
+//                         compiled model + plan constants are staged into shared memory
+//                         with one TMA bulk copy (cp.async.bulk + mbarrier) per CTA.
+//   weights_kernel        population std + max-subtracted softmax over all rewards
+//                         (warp-shuffle + one smem stage reductions), single CTA.
+//   ybar_kernel           Ybar = sum_n w_n Y0s_n with Y0s regenerated from eps / Threefry;
+//                         per-CTA partials, last CTA reduces in fixed order (deterministic).
+//   trajbar_kernel        qbar / qdbar / xbar weighted sums over the stored trajectories.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string>
+#include <new>
+#include "dial_host.h"
+
+static thread_local std::string g_err;
+static int fail(const std::string& s) { g_err = s; return -1; }
+#define CUDA_OK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// ---------------------------------------------------------------------------------
+// TMA bulk copy global -> shared (1-D), completion on an mbarrier
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+static_assert(sizeof(DevModel) % 16 == 0, "DevModel must be a multiple of 16 bytes for cp.async.bulk");
+static_assert(sizeof(DevPlan) % 16 == 0, "DevPlan must be a multiple of 16 bytes for cp.async.bulk");
+
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32, 16 / WPC) rollout_kernel(const DevModel* __restrict__ gM,
+                                                            const DevPlan* __restrict__ gP,
+                                                            const RolloutArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  DevModel* sM = reinterpret_cast<DevModel*>(smem);
+  DevPlan* sP = reinterpret_cast<DevPlan*>(smem + sizeof(DevModel));
+  float* slabs = reinterpret_cast<float*>(smem + sizeof(DevModel) + sizeof(DevPlan));
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_expect_tx(&bar, (uint32_t)(sizeof(DevModel) + sizeof(DevPlan)));
+    tma_bulk_g2s(sM, gM, (uint32_t)sizeof(DevModel), &bar);
+    tma_bulk_g2s(sP, gP, (uint32_t)sizeof(DevPlan), &bar);
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WPC + warp;
+  if (row >= A.nrows) return;
+  rollout_warp(sM, sP, slabs + (size_t)warp * sM->warp_floats, A, row, lane);
+}
+
+// ---------------------------------------------------------------------------------
+// softmax weights over all rewards (core/dial_core.py:125-128), single CTA
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : (is_max ? -INFINITY : 0.f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float t = __shfl_xor_sync(0xffffffffu, r, o);
+    r = is_max ? fmaxf(r, t) : r + t;
+  }
+  return r;  // identical in every thread
+}
+
+// rews [n] (mean sample last) -> weights [n].  Non-finite rewards (diverged samples) get
+// weight 0 and are left out of the statistics (the reference has no guard: it would return NaN).
+__global__ void __launch_bounds__(1024) weights_kernel(const float* __restrict__ rews, int n, float temp,
+                                                        float* __restrict__ weights) {
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  float s = 0.f, cnt = 0.f;
+  for (int i = tid; i < n; i += blockDim.x) { float r = rews[i]; if (isfinite(r)) { s += r; cnt += 1.f; } }
+  s = block_reduce(s, red, false);
+  cnt = block_reduce(cnt, red, false);
+  const float mean = s / fmaxf(cnt, 1.f);
+  float v = 0.f;
+  for (int i = tid; i < n; i += blockDim.x) { float r = rews[i]; if (isfinite(r)) v += (r - mean) * (r - mean); }
+  v = block_reduce(v, red, false);
+  const float sd = sqrtf(v / fmaxf(cnt, 1.f));
+  const float rbar = rews[n - 1];
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += blockDim.x) {
+    float r = rews[i];
+    if (isfinite(r)) mx = fmaxf(mx, (r - rbar) / sd / temp);
+  }
+  mx = block_reduce(mx, red, true);
+  float z = 0.f;
+  for (int i = tid; i < n; i += blockDim.x) {
+    float r = rews[i];
+    float e = isfinite(r) ? expf((r - rbar) / sd / temp - mx) : 0.f;
+    weights[i] = e;
+    z += e;
+  }
+  z = block_reduce(z, red, false);
+  __syncthreads();
+  const float inv = 1.f / z;
+  for (int i = tid; i < n; i += blockDim.x) weights[i] *= inv;
+}
+
+// ---------------------------------------------------------------------------------
+// Ybar = sum_n w_n * Y0s_n  (core/dial_core.py:129-132), Y0s regenerated
+// ---------------------------------------------------------------------------------
+#define YBAR_THREADS 256
+__global__ void __launch_bounds__(YBAR_THREADS) ybar_kernel(const float* __restrict__ weights, const float* __restrict__ eps,
+                                                             uint32_t key0, uint32_t key1, const float* __restrict__ Ybar,
+                                                             const float* __restrict__ noise, int Ntotal, int Hn1, int nu,
+                                                             float* __restrict__ partial, unsigned int* __restrict__ counter,
+                                                             float* __restrict__ Ybar_out) {
+  // thread -> (sample slot, output element); elements = Hn1*nu <= 160
+  const int ne = Hn1 * nu;
+  __shared__ float acc[YBAR_THREADS];
+  __shared__ bool is_last;
+  const int slots = YBAR_THREADS / ne;  // samples processed concurrently per CTA
+  const int slot = threadIdx.x / ne, el = threadIdx.x - slot * ne;
+  float a = 0.f;
+  if (slot < slots) {
+    const int k = el / nu;
+    const float yb = Ybar[el], ns = noise[k];
+    const uint32_t ntot = (uint32_t)Ntotal * (uint32_t)ne;
+    for (int n = blockIdx.x * slots + slot; n <= Ntotal; n += gridDim.x * slots) {
+      float y = yb;
+      if (n < Ntotal && k > 0) {
+        uint32_t idx = (uint32_t)n * (uint32_t)ne + (uint32_t)el;
+        float e = eps ? eps[idx] : jax_normal_legacy(key0, key1, idx, ntot);
+        y = e * ns + yb;
+      }
+      y = fminf(fmaxf(y, -1.f), 1.f);
+      a += weights[n] * y;
+    }
+  }
+  acc[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x < ne) {
+    float s = 0.f;
+    for (int sl = 0; sl < slots; ++sl) s += acc[sl * ne + threadIdx.x];
+    partial[blockIdx.x * ne + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x < ne) {
+      float s = 0.f;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partial[b * ne + threadIdx.x]);
+      Ybar_out[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// qbar / qdbar / xbar  (core/dial_core.py:133-135): weighted sums over stored trajectories
+//   grid = H (one CTA per time step); block = (32 columns, 8 sample groups) loops
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trajbar_kernel(const float* __restrict__ traj, int ncol, int nrows, int H,
+                                                       const float* __restrict__ weights, int w_offset, int mean_row,
+                                                       int mean_weight_index, int include_mean, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int t = blockIdx.x, cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < ncol; c0 += 32) {
+    const int c = c0 + cx;
+    float a = 0.f;
+    if (c < ncol) {
+      for (int r = g; r < nrows; r += 8) {
+        float wgt;
+        if (r == mean_row) { if (!include_mean) continue; wgt = weights[mean_weight_index]; }
+        else wgt = weights[w_offset + r];
+        a += wgt * traj[((size_t)r * H + t) * ncol + c];
+      }
+    }
+    __syncthreads();
+    red[g][cx] = a;
+    __syncthreads();
+    if (g == 0 && c < ncol) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += red[i][cx];
+      out[(size_t)t * ncol + c] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// plan object
+// ---------------------------------------------------------------------------------
+struct dial_plan {
+  DevModel hM;
+  DevPlan hP;
+  DevModel* dM = nullptr;
+  DevPlan* dP = nullptr;
+  int wpc = 4;
+  size_t smem_bytes = 0;
+  // workspaces
+  float *traj_q = nullptr, *traj_qd = nullptr, *traj_x = nullptr;  // [Nsample+1, Hs+1, *]
+  float* weights = nullptr;                                        // [Ntotal+1]
+  float* partial = nullptr;
+  unsigned int* counter = nullptr;
+  float* zeros = nullptr;                                          // [nv]
+  int ybar_grid = 0;
+  int64_t launches = 0;
+};
+
+extern "C" int dial_abi_version(void) { return DIAL_ABI_VERSION; }
+extern "C" const char* dial_last_error(void) { return g_err.c_str(); }
+
+template <int WPC>
+static cudaError_t launch_rollout(dial_plan* p, const RolloutArgs& A, cudaStream_t st) {
+  size_t smem = sizeof(DevModel) + sizeof(DevPlan) + (size_t)WPC * p->hM.warp_floats * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(rollout_kernel<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  int grid = (A.nrows + WPC - 1) / WPC;
+  rollout_kernel<WPC><<<grid, WPC * 32, smem, st>>>(p->dM, p->dP, A);
+  p->launches++;
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A, cudaStream_t st) {
+  // few rows: 1 warp per CTA spreads samples over more SMs; many rows: 4 warps per CTA
+  if (A.nrows <= 592) return launch_rollout<1>(p, A, st);
+  if (A.nrows <= 1184) return launch_rollout<2>(p, A, st);
+  return launch_rollout<4>(p, A, st);
+}
+
+extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_plan_desc* cfg) {
+  if (!model || !cfg) { g_err = "null descriptor"; return nullptr; }
+  dial_plan* p = new (std::nothrow) dial_plan();
+  if (!p) { g_err = "out of memory"; return nullptr; }
+  std::string err;
+  if (!derive_model(*model, p->hM, err)) { g_err = err; delete p; return nullptr; }
+  memset(&p->hP, 0, sizeof(DevPlan));
+  p->hP.c = *cfg;
+  const dial_plan_desc& c = *cfg;
+  if (c.Hsample + 1 > DIAL_MAXH || c.Hnode + 1 > DIAL_MAXNODE || c.Hnode < 1 || c.Nsample < 1 || c.Ntotal < c.Nsample ||
+      c.n_frames < 1 || (c.Hnode + 1) * model->nu > YBAR_THREADS || c.n_stage > DIAL_MAXSTAGE) {
+    g_err = "invalid plan configuration (Hsample/Hnode/Nsample/n_frames out of range)";
+    delete p;
+    return nullptr;
+  }
+  if (c.env_id < DIAL_ENV_GO2_WALK || c.env_id > DIAL_ENV_H1_WALK) { g_err = "unknown env_id"; delete p; return nullptr; }
+  auto bad = [&](cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    dial_plan_destroy(p);
+    return (dial_plan*)nullptr;
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc(&p->dM, sizeof(DevModel))) != cudaSuccess) return bad(e, "cudaMalloc(model)");
+  if ((e = cudaMalloc(&p->dP, sizeof(DevPlan))) != cudaSuccess) return bad(e, "cudaMalloc(plan)");
+  if ((e = cudaMemcpy(p->dM, &p->hM, sizeof(DevModel), cudaMemcpyHostToDevice)) != cudaSuccess) return bad(e, "cudaMemcpy(model)");
+  if ((e = cudaMemcpy(p->dP, &p->hP, sizeof(DevPlan), cudaMemcpyHostToDevice)) != cudaSuccess) return bad(e, "cudaMemcpy(plan)");
+  const size_t rows = (size_t)c.Nsample + 1, H = (size_t)c.Hsample + 1;
+  const dial_model_desc& m = *model;
+  if ((e = cudaMalloc(&p->traj_q, rows * H * m.nq * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(traj_q)");
+  if ((e = cudaMalloc(&p->traj_qd, rows * H * m.nv * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(traj_qd)");
+  if ((e = cudaMalloc(&p->traj_x, rows * H * 3 * (m.nbody - 1) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(traj_x)");
+  if ((e = cudaMalloc(&p->weights, ((size_t)c.Ntotal + 1) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(weights)");
+  const int ne = (c.Hnode + 1) * m.nu, slots = YBAR_THREADS / ne;
+  int g = (c.Ntotal + 1 + slots - 1) / slots;
+  p->ybar_grid = g < 1 ? 1 : (g > 296 ? 296 : g);
+  if ((e = cudaMalloc(&p->partial, (size_t)p->ybar_grid * ne * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(partial)");
+  if ((e = cudaMalloc(&p->counter, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMalloc(counter)");
+  if ((e = cudaMemset(p->counter, 0, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMemset(counter)");
+  if ((e = cudaMalloc(&p->zeros, DIAL_MAXV * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(zeros)");
+  if ((e = cudaMemset(p->zeros, 0, DIAL_MAXV * sizeof(float))) != cudaSuccess) return bad(e, "cudaMemset(zeros)");
+  return p;
+}
+
+extern "C" void dial_plan_destroy(dial_plan* p) {
+  if (!p) return;
+  cudaFree(p->dM); cudaFree(p->dP); cudaFree(p->traj_q); cudaFree(p->traj_qd); cudaFree(p->traj_x);
+  cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->counter); cudaFree(p->zeros);
+  delete p;
+}
+
+static void fill_state(RolloutArgs& A, const dial_state* s) {
+  A.qpos0 = s->qpos; A.qvel0 = s->qvel; A.warm0 = s->qacc_warmstart; A.step0 = s->step; A.stage0 = s->stage;
+}
+
+extern "C" int dial_rollout(dial_plan* p, const dial_state* s, const float* us, int B, int H, float* rewss,
+                            float* q, float* qd, float* xpos, void* stream) {
+  if (!p || !s || !us || !rewss) return fail("dial_rollout: null argument");
+  if (B < 1 || H < 1) return fail("dial_rollout: B and H must be positive");
+  RolloutArgs A; memset(&A, 0, sizeof(A));
+  fill_state(A, s);
+  A.nrows = B; A.H = H; A.mode = 0; A.us = us; A.rewss = rewss; A.q = q; A.qd = qd; A.xpos = xpos;
+  CUDA_OK(launch_rollout_any(p, A, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int dial_env_step(dial_plan* p, const dial_state* s, const float* action, float* qpos_out,
+                             float* qvel_out, float* warm_out, float* reward, float* ctrl_out, void* stream) {
+  if (!p || !s || !action || !qpos_out || !qvel_out || !warm_out || !reward) return fail("dial_env_step: null argument");
+  RolloutArgs A; memset(&A, 0, sizeof(A));
+  fill_state(A, s);
+  A.nrows = 1; A.H = 1; A.mode = 0; A.us = action; A.rewss = reward;
+  A.qpos_out = qpos_out; A.qvel_out = qvel_out; A.warm_out = warm_out; A.ctrl_out = ctrl_out;
+  CUDA_OK(launch_rollout<1>(p, A, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int dial_pipeline_init(dial_plan* p, const float* qpos, const float* qvel, float* qpos_out,
+                                  float* warm_out, void* stream) {
+  if (!p || !qpos || !qvel || !qpos_out || !warm_out) return fail("dial_pipeline_init: null argument");
+  RolloutArgs A; memset(&A, 0, sizeof(A));
+  A.qpos0 = qpos; A.qvel0 = qvel; A.warm0 = p->zeros;  // mjx.make_data: qacc_warmstart = 0
+  A.nrows = 1; A.H = 1; A.mode = 2; A.qpos_out = qpos_out; A.warm_out = warm_out;
+  CUDA_OK(launch_rollout<1>(p, A, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int dial_reverse_rollout(dial_plan* p, const dial_state* s, const float* eps, const uint32_t key[2],
+                                    const float* Ybar, const float* noise_scale, float* rews_local, void* stream) {
+  if (!p || !s || !Ybar || !noise_scale || !rews_local) return fail("dial_reverse_rollout: null argument");
+  if (!eps && !key) return fail("dial_reverse_rollout: need eps or key");
+  RolloutArgs A; memset(&A, 0, sizeof(A));
+  fill_state(A, s);
+  const dial_plan_desc& c = p->hP.c;
+  A.nrows = c.Nsample + 1; A.H = c.Hsample + 1; A.mode = 1;
+  A.eps = eps; A.Ybar = Ybar; A.noise = noise_scale;
+  if (key) { A.key0 = key[0]; A.key1 = key[1]; }
+  A.rews = rews_local; A.q = p->traj_q; A.qd = p->traj_qd; A.xpos = p->traj_x;
+  CUDA_OK(launch_rollout_any(p, A, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int dial_reverse_update(dial_plan* p, const float* eps, const uint32_t key[2], const float* Ybar,
+                                   const float* noise_scale, const float* rews_all, float* Ybar_out,
+                                   float* weights, void* stream) {
+  if (!p || !Ybar || !noise_scale || !rews_all || !Ybar_out) return fail("dial_reverse_update: null argument");
+  if (!eps && !key) return fail("dial_reverse_update: need eps or key");
+  const dial_plan_desc& c = p->hP.c;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* w = weights ? weights : p->weights;
+  weights_kernel<<<1, 1024, 0, st>>>(rews_all, c.Ntotal + 1, c.temp_sample, w);
+  p->launches++;
+  CUDA_OK(cudaGetLastError());
+  ybar_kernel<<<p->ybar_grid, YBAR_THREADS, 0, st>>>(w, eps, key ? key[0] : 0u, key ? key[1] : 0u, Ybar, noise_scale,
+                                                     c.Ntotal, c.Hnode + 1, p->hM.m.nu, p->partial, p->counter, Ybar_out);
+  p->launches++;
+  CUDA_OK(cudaGetLastError());
+  if (weights && weights != p->weights)
+    CUDA_OK(cudaMemcpyAsync(p->weights, weights, ((size_t)c.Ntotal + 1) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int dial_reverse_trajbar(dial_plan* p, const float* weights, int rank, float* qbar, float* qdbar,
+                                    float* xbar, void* stream) {
+  if (!p) return fail("dial_reverse_trajbar: null plan");
+  const dial_plan_desc& c = p->hP.c;
+  const dial_model_desc& m = p->hM.m;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* w = weights ? weights : p->weights;
+  const int H = c.Hsample + 1, rows = c.Nsample + 1;
+  struct { const float* traj; int ncol; float* out; } jobs[3] = {
+      {p->traj_q, m.nq, qbar}, {p->traj_qd, m.nv, qdbar}, {p->traj_x, 3 * (m.nbody - 1), xbar}};
+  for (auto& j : jobs) {
+    if (!j.out) continue;
+    trajbar_kernel<<<H, 256, 0, st>>>(j.traj, j.ncol, rows, H, w, c.shard_offset, c.Nsample, c.Ntotal,
+                                      rank == 0 ? 1 : 0, j.out);
+    p->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" void dial_key_split(const uint32_t key[2], uint32_t out0[2], uint32_t out1[2]) {
+  // jax.random.split(key, 2), legacy layout: counters [0,1,2,3] -> halves (0,1) | (2,3)
+  uint32_t a0 = 0, b0 = 2, a1 = 1, b1 = 3;
+  threefry2x32(key[0], key[1], a0, b0);
+  threefry2x32(key[0], key[1], a1, b1);
+  out0[0] = a0; out0[1] = a1; out1[0] = b0; out1[1] = b1;
+}
+
+extern "C" int64_t dial_launch_count(const dial_plan* p) { return p ? p->launches : 0; }

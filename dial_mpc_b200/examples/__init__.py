@@ -1,0 +1,6 @@
+"""Example configs (same names as dial_mpc/examples/__init__.py for the in-scope envs)."""
+examples = [
+    "unitree_h1_jog",
+    "unitree_go2_trot",
+    "unitree_go2_seq_jump",
+]

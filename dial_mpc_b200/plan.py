@@ -1,0 +1,128 @@
+"""Thin Python wrapper over the C-ABI plan handle (include/dial_b200.h).
+
+PyTorch is used only for device memory and streams; every compute call goes to the
+hand-written kernels in ``csrc/libdial_b200.so``."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from dial_mpc_b200 import _capi
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "need contiguous fp32 CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _key(key):
+    if key is None:
+        return None
+    k = np.ascontiguousarray(key, dtype=np.uint32)
+    return (C.c_uint32 * 2)(int(k[0]), int(k[1]))
+
+
+class Plan:
+    def __init__(self, env, desc: "_capi.dial_plan_desc", device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dial_mpc_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = _capi.lib()
+        self.env = env
+        self.desc = desc
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.mdesc = _capi.fill_model_desc(env.sys.model)
+        with torch.cuda.device(self.device):
+            self.handle = self.lib.dial_plan_create(C.byref(self.mdesc), C.byref(desc))
+        if not self.handle:
+            raise RuntimeError(f"dial_plan_create failed: {self.lib.dial_last_error().decode()}")
+        m = self.mdesc
+        self.nq, self.nv, self.nu, self.nbody = m.nq, m.nv, m.nu, m.nbody
+        self.N, self.Ntotal = desc.Nsample, desc.Ntotal
+        self.Hs, self.Hn = desc.Hsample, desc.Hnode
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.dial_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- helpers ------------------------------------------------------------------------------
+    def f32(self, x, shape=None) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            t = x.to(device=self.device, dtype=torch.float32).contiguous()
+        else:
+            t = torch.as_tensor(np.asarray(x, dtype=np.float32), device=self.device).contiguous()
+        if shape is not None:
+            assert tuple(t.shape) == tuple(shape), f"expected shape {shape}, got {tuple(t.shape)}"
+        return t
+
+    def empty(self, *shape) -> torch.Tensor:
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def _state(self, state) -> Tuple["_capi.dial_state", tuple]:
+        ps = state.pipeline_state
+        qpos, qvel, warm = self.f32(ps.qpos, (self.nq,)), self.f32(ps.qvel, (self.nv,)), self.f32(ps.qacc_warmstart, (self.nv,))
+        s = _capi.dial_state()
+        s.qpos, s.qvel, s.qacc_warmstart = qpos.data_ptr(), qvel.data_ptr(), warm.data_ptr()
+        s.step = int(state.info.get("step", 0))
+        s.stage = int(state.info.get("contact_stage", 0))
+        return s, (qpos, qvel, warm)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.dial_launch_count(self.handle))
+
+    # -- API ------------------------------------------------------------------------------------
+    def pipeline_init(self, qpos):
+        from dial_mpc_b200.envs.base_env import PipelineState
+        q = self.f32(qpos, (self.nq,))
+        qv = torch.zeros(self.nv, dtype=torch.float32, device=self.device)
+        qo, wo = self.empty(self.nq), self.empty(self.nv)
+        _capi.check(self.lib.dial_pipeline_init(self.handle, _ptr(q), _ptr(qv), _ptr(qo), _ptr(wo), _stream()))
+        return PipelineState(qo, qv, wo, torch.zeros(self.nu, dtype=torch.float32, device=self.device))
+
+    def env_step(self, state, action):
+        from dial_mpc_b200.envs.base_env import PipelineState
+        s, keep = self._state(state)
+        a = self.f32(action, (self.nu,))
+        qo, vo, wo, r, c = self.empty(self.nq), self.empty(self.nv), self.empty(self.nv), self.empty(1), self.empty(self.nu)
+        _capi.check(self.lib.dial_env_step(self.handle, C.byref(s), _ptr(a), _ptr(qo), _ptr(vo), _ptr(wo), _ptr(r),
+                                           _ptr(c), _stream()))
+        return PipelineState(qo, vo, wo, c), r[0]
+
+    def rollout(self, state, us, want_traj=True):
+        s, keep = self._state(state)
+        us = self.f32(us)
+        B, H, nu = us.shape
+        assert nu == self.nu
+        rewss = self.empty(B, H)
+        q = self.empty(B, H, self.nq) if want_traj else None
+        qd = self.empty(B, H, self.nv) if want_traj else None
+        x = self.empty(B, H, self.nbody - 1, 3) if want_traj else None
+        _capi.check(self.lib.dial_rollout(self.handle, C.byref(s), _ptr(us), B, H, _ptr(rewss), _ptr(q), _ptr(qd),
+                                          _ptr(x), _stream()))
+        return rewss, q, qd, x
+
+    def reverse_rollout(self, state, eps, key, Ybar, noise_scale, rews_local):
+        s, keep = self._state(state)
+        _capi.check(self.lib.dial_reverse_rollout(self.handle, C.byref(s), _ptr(eps), _key(key), _ptr(Ybar),
+                                                  _ptr(noise_scale), _ptr(rews_local), _stream()))
+
+    def reverse_update(self, eps, key, Ybar, noise_scale, rews_all, Ybar_out, weights=None):
+        _capi.check(self.lib.dial_reverse_update(self.handle, _ptr(eps), _key(key), _ptr(Ybar), _ptr(noise_scale),
+                                                 _ptr(rews_all), _ptr(Ybar_out), _ptr(weights), _stream()))
+
+    def reverse_trajbar(self, weights, rank, qbar, qdbar, xbar):
+        _capi.check(self.lib.dial_reverse_trajbar(self.handle, _ptr(weights), int(rank), _ptr(qbar), _ptr(qdbar),
+                                                  _ptr(xbar), _stream()))

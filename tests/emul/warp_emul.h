@@ -72,3 +72,4 @@ inline int shfl_i(int v, int src) {
   return r;
 }
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
