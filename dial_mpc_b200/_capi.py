@@ -120,6 +120,8 @@ class _Lib:
             lib = C.CDLL(LIB_PATH)
             lib.dial_abi_version.restype = C.c_int
             lib.dial_last_error.restype = C.c_char_p
+            lib.dial_sizeof.restype = C.c_size_t
+            lib.dial_sizeof.argtypes = [C.c_int]
             lib.dial_plan_create.restype = C.c_void_p
             lib.dial_plan_create.argtypes = [C.POINTER(dial_model_desc), C.POINTER(dial_plan_desc)]
             lib.dial_plan_destroy.argtypes = [C.c_void_p]
@@ -141,6 +143,9 @@ class _Lib:
                 getattr(lib, fn).restype = C.c_int
             if lib.dial_abi_version() != DEFINES["DIAL_ABI_VERSION"]:
                 raise RuntimeError("libdial_b200.so ABI version does not match include/dial_b200.h")
+            for i, t in enumerate((dial_model_desc, dial_plan_desc, dial_state)):
+                if lib.dial_sizeof(i) != C.sizeof(t):
+                    raise RuntimeError(f"struct layout mismatch for {t.__name__}: C {lib.dial_sizeof(i)} vs ctypes {C.sizeof(t)}")
             cls._lib = lib
         return cls._lib
 
@@ -154,6 +159,6 @@ def check(rc: int) -> None:
         raise RuntimeError(f"dial_b200: {lib().dial_last_error().decode()} (rc={rc})")
 
 
-EXPORTS = ["dial_abi_version", "dial_last_error", "dial_plan_create", "dial_plan_destroy", "dial_rollout",
+EXPORTS = ["dial_abi_version", "dial_last_error", "dial_sizeof", "dial_plan_create", "dial_plan_destroy", "dial_rollout",
            "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout", "dial_reverse_update",
            "dial_reverse_trajbar", "dial_key_split", "dial_launch_count"]

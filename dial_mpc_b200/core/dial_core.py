@@ -46,7 +46,7 @@ def softmax_update(weights, Y0s, sigma, mu_0t):
 
 class MBDPI:
     def __init__(self, args: DialConfig, env, rank: int = 0, world_size: int = 1, process_group=None,
-                 compute_bars: bool = True):
+                 compute_bars: bool = True, plan_factory=None):
         self.args = args
         self.env = env
         self.nu = env.action_size
@@ -73,7 +73,8 @@ class MBDPI:
         desc = env.plan_desc(Nsample=self.Nlocal, Ntotal=args.Nsample, shard_offset=rank * self.Nlocal,
                              Hsample=args.Hsample, Hnode=args.Hnode, temp_sample=args.temp_sample,
                              M_n2u=self.M_n2u_np)
-        self.plan = Plan(env, desc)
+        # plan_factory exists for the CPU test harness (tests/emul); the product path is Plan
+        self.plan = (plan_factory or Plan)(env, desc)
         dev = self.plan.device
         self.device = dev
         f = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32), device=dev)

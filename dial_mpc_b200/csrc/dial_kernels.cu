@@ -230,6 +230,9 @@ struct dial_plan {
 
 extern "C" int dial_abi_version(void) { return DIAL_ABI_VERSION; }
 extern "C" const char* dial_last_error(void) { return g_err.c_str(); }
+extern "C" size_t dial_sizeof(int which) {
+  return which == 0 ? sizeof(dial_model_desc) : which == 1 ? sizeof(dial_plan_desc) : which == 2 ? sizeof(dial_state) : 0;
+}
 
 template <int WPC>
 static cudaError_t launch_rollout(dial_plan* p, const RolloutArgs& A, cudaStream_t st) {

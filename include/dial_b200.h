@@ -129,6 +129,9 @@ typedef struct dial_plan dial_plan;
 
 int dial_abi_version(void);
 const char* dial_last_error(void);
+/* sizeof() of the descriptor structs as compiled into the library: which = 0 model, 1 plan,
+ * 2 state (lets foreign-language bindings verify their struct layout). */
+size_t dial_sizeof(int which);
 
 /* Create / destroy a plan (uploads model + config, allocates all workspaces). */
 dial_plan* dial_plan_create(const dial_model_desc* model, const dial_plan_desc* cfg);

@@ -47,3 +47,65 @@ def rollout(env, plan_desc, qpos, qvel, warm, step0=0, stage0=0, us=None, eps=No
                           _p(out["slab"]))
     assert rc == 0
     return out
+
+
+class EmulPlan:
+    """TEST-ONLY stand-in for dial_mpc_b200.plan.Plan on CPU tensors: stage 1 runs the real
+    device code through the warp emulator, stage 2/3 (weights, Ybar, bars) are NumPy.  Used by
+    the gloo tests to exercise MBDPI's multi-rank plumbing without a GPU."""
+
+    def __init__(self, env, desc):
+        import torch
+        self.env, self.desc = env, desc
+        self.device = torch.device("cpu")
+        m = env.sys
+        self.nq, self.nv, self.nu, self.nbody = m.nq, m.nv, m.nu, m.nbody
+        self.N, self.Ntotal, self.Hs, self.Hn = desc.Nsample, desc.Ntotal, desc.Hsample, desc.Hnode
+        self.launches = 0
+        self._traj = None
+
+    def f32(self, x, shape=None):
+        import torch
+        t = x.to(torch.float32).contiguous() if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float32))
+        if shape is not None:
+            assert tuple(t.shape) == tuple(shape)
+        return t
+
+    def _np(self, t):
+        return None if t is None else t.detach().cpu().numpy()
+
+    def reverse_rollout(self, state, eps, key, Ybar, noise_scale, rews_local):
+        ps = state.pipeline_state
+        key = (0, 0) if key is None else (int(key[0]), int(key[1]))
+        out = rollout(self.env, self.desc, self._np(ps.qpos), self._np(ps.qvel), self._np(ps.qacc_warmstart),
+                      step0=int(state.info.get("step", 0)), stage0=int(state.info.get("contact_stage", 0)),
+                      eps=self._np(eps), Ybar=self._np(Ybar), noise=self._np(noise_scale), key=key, mode=1,
+                      nrows=self.N + 1, H=self.Hs + 1)
+        self._traj = out
+        rews_local.copy_(self.f32(out["rews"]))
+        self.launches += 1
+
+    def _Y0s(self, eps, Ybar, noise):
+        Y0s = eps * noise[None, :, None] + Ybar
+        Y0s[:, 0] = Ybar[0]
+        return np.clip(np.concatenate([Y0s, Ybar[None]], 0), -1, 1)
+
+    def reverse_update(self, eps, key, Ybar, noise_scale, rews_all, Ybar_out, weights=None):
+        assert eps is not None, "EmulPlan.reverse_update needs injected eps"
+        r = self._np(rews_all).astype(np.float64)
+        logp = (r - r[-1]) / r.std() / self.desc.temp_sample
+        w = np.exp(logp - logp.max())
+        w /= w.sum()
+        Y0s = self._Y0s(self._np(eps).astype(np.float64), self._np(Ybar).astype(np.float64), self._np(noise_scale).astype(np.float64))
+        Ybar_out.copy_(self.f32(np.einsum("n,nij->ij", w, Y0s)))
+        if weights is not None:
+            weights.copy_(self.f32(w))
+
+    def reverse_trajbar(self, weights, rank, qbar, qdbar, xbar):
+        w = self._np(weights).astype(np.float64)
+        off, N = self.desc.shard_offset, self.N
+        wl = np.concatenate([w[off:off + N], [w[-1] if rank == 0 else 0.0]])
+        t = self._traj
+        qbar.copy_(self.f32(np.einsum("n,nij->ij", wl, t["q"]).ravel()))
+        qdbar.copy_(self.f32(np.einsum("n,nij->ij", wl, t["qd"]).ravel()))
+        xbar.copy_(self.f32(np.einsum("n,nijk->ijk", wl, t["xpos"]).ravel()))

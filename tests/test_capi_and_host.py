@@ -1,0 +1,132 @@
+"""CPU tests: the C-ABI library loads and exports every symbol the header declares (no compute
+calls without a GPU), struct layouts agree, and the host-side logic mirrors the reference API."""
+import ctypes as C
+import dataclasses
+import os
+import re
+
+import numpy as np
+import pytest
+import yaml
+
+from dial_mpc_b200 import _capi
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = _capi.lib()
+    text = open(_capi.HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(dial_\w+)\s*\(", text))
+    assert declared == set(_capi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dial_abi_version() == _capi.DEFINES["DIAL_ABI_VERSION"]
+    for i, t in enumerate((_capi.dial_model_desc, _capi.dial_plan_desc, _capi.dial_state)):
+        assert lib.dial_sizeof(i) == C.sizeof(t)
+
+
+def test_key_split_matches_oracle(built):
+    from dial_mpc_b200 import random as drandom
+    from oracle.planner_oracle import jax_split_legacy
+    for seed in (0, 1, 12345):
+        key = drandom.PRNGKey(seed)
+        a, b = drandom.split(key)
+        ref = jax_split_legacy((int(key[0]), int(key[1])))
+        assert tuple(a) == tuple(ref[0]) and tuple(b) == tuple(ref[1])
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_capi, "LIB_PATH", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_capi._Lib, "_lib", None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _capi.lib()
+
+
+def test_config_dataclasses_match_reference_fields():
+    from dial_mpc_b200.config.base_env_config import BaseEnvConfig
+    from dial_mpc_b200.core.dial_config import DialConfig
+    assert [f.name for f in dataclasses.fields(DialConfig)] == [
+        "seed", "output_dir", "n_steps", "env_name", "Nsample", "Hsample", "Hnode", "Ndiffuse",
+        "Ndiffuse_init", "temp_sample", "horizon_diffuse_factor", "traj_diffuse_factor",
+        "update_method", "sigma_scale"]
+    d = DialConfig()
+    assert (d.Nsample, d.Hsample, d.Hnode, d.Ndiffuse, d.Ndiffuse_init, d.temp_sample) == (2048, 16, 4, 2, 10, 0.06)
+    assert [f.name for f in dataclasses.fields(BaseEnvConfig)] == [
+        "task_name", "randomize_tasks", "kp", "kd", "debug", "dt", "timestep", "backend",
+        "leg_control", "action_scale"]
+
+
+def test_registry_and_yaml_loading():
+    import dial_mpc_b200.envs as E
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.examples import examples
+    from dial_mpc_b200.utils.io_utils import get_example_path, load_dataclass_from_dict
+    for ex in examples:
+        cfg = yaml.safe_load(open(get_example_path(ex + ".yaml")))
+        dc = load_dataclass_from_dict(DialConfig, cfg)
+        ec = load_dataclass_from_dict(E.get_config(dc.env_name), cfg, convert_list_to_array=True)
+        env = E.get_environment(dc.env_name, config=ec)
+        assert env.action_size == env.sys.nu and abs(env.dt - 0.02) < 1e-12
+        d = env.plan_desc(Nsample=8, Hsample=dc.Hsample, Hnode=dc.Hnode)
+        assert d.env_id == _capi.ENV_IDS[dc.env_name] and d.n_frames == 1
+    E.register_config("custom", E.UnitreeGo2EnvConfig)
+    assert E.get_config("custom") is E.UnitreeGo2EnvConfig
+
+    class MyEnv(E.UnitreeGo2Env):
+        pass
+    E.register_environment("custom", MyEnv)
+    assert isinstance(E.get_environment("custom", config=E.UnitreeGo2EnvConfig()), MyEnv)
+
+
+def test_act2joint_act2tau_match_oracle():
+    from tests.conftest import make_pair
+    for name in ("unitree_go2_walk", "unitree_h1_walk"):
+        env, o = make_pair(name)
+        rng = np.random.default_rng(0)
+        a = rng.uniform(-1.2, 1.2, env.action_size)
+        assert np.abs(env.act2joint(a) - o.act2joint(a)).max() < 1e-12
+        s = o.reset()
+
+        class PS:
+            qpos, qvel = s.qpos[0], s.qvel[0] + 0.1
+        assert np.abs(env.act2tau(a, PS) - o.act2tau(a[None], s.qpos, s.qvel + 0.1)[0]).max() < 1e-9
+    env, _ = make_pair("unitree_go2_walk")
+    assert np.isinf(env.joint_torque_range).all()       # Go2 motors have no ctrlrange
+    d = env.plan_desc()
+    assert np.isfinite(np.ctypeslib.as_array(d.joint_torque_range)).all()
+
+
+def test_seq_jump_targets_match_oracle():
+    from tests.conftest import make_pair
+    env, o = make_pair("unitree_go2_seq_jump")
+    assert np.abs(env._contact_targets - o.contact_targets).max() < 1e-12
+    assert env._contact_targets.shape == (5, 4, 3)
+    yaw = np.array([0.0, 0.3, -0.2])
+    pos = np.array([[0, 0, 0.27], [0.4, 0.1, 0.27], [0.8, 0, 0.27]])
+    t, r, p, y = env.generate_jumping_sequence(pos, yaw, 0.1)
+    c, s = np.cos(0.3), np.sin(0.3)
+    assert np.allclose(t[1, 0, :2], pos[1, :2] + np.array([c * 0.2 + s * 0.135, s * 0.2 - c * 0.135]))
+
+
+def test_mbdpi_host_math_without_gpu():
+    """MBDPI's schedule / shift / spline maps on CPU through the test harness plan."""
+    import torch
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import MBDPI
+    from oracle.planner_oracle import PlannerOracle
+    from tests.conftest import make_pair
+    from tests.emul.emul import EmulPlan
+    env, o = make_pair("unitree_go2_walk")
+    cfg = DialConfig(env_name="unitree_go2_walk", Nsample=4, Hsample=16, Hnode=4, temp_sample=0.05)
+    mb = MBDPI(cfg, env, plan_factory=EmulPlan)
+    po = PlannerOracle(o, 4, 16, 4, 0.05, 0.9, 0.5)
+    assert np.abs(mb.sigma_control.numpy() - po.sigma_control).max() < 1e-6
+    assert np.abs(mb.schedule(3).numpy() - po.schedule(3)).max() < 1e-6
+    Y = np.random.default_rng(0).standard_normal((5, 12))
+    assert np.abs(mb.shift(Y).numpy() - po.shift(Y)).max() < 1e-5
+    assert np.abs(mb.node2u_vmap(Y).numpy() - po.node2u(Y)).max() < 1e-5
+    u = np.random.default_rng(1).standard_normal((3, 17, 12))
+    assert np.abs(mb.u2node_vvmap(u).numpy() - po.u2node(u)).max() < 1e-5
+    assert mb.ctrl_dt == 0.02 and abs(mb.node_dt - 0.08) < 1e-12 and mb.nu == 12
+    sh = mb.shift_Y_from_u(torch.ones(17, 12), 2)
+    assert sh.shape == (5, 12) and abs(float(sh[-1, 0])) < 1e-5

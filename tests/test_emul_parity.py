@@ -1,0 +1,66 @@
+"""CPU tests of the KERNEL LOGIC: csrc/dial_device.cuh compiled by g++ and executed by the
+lock-step warp emulator (tests/emul) against the fp64 oracle.  The emulator is test
+infrastructure only; the GPU tests (test_gpu_parity.py) check the real CUDA build."""
+import numpy as np
+import pytest
+
+from tests.conftest import ENV_CASES, make_pair
+from tests.emul import emul
+
+
+@pytest.mark.parametrize("name,H", [("unitree_go2_walk", 12), ("unitree_go2_seq_jump", 12), ("unitree_h1_walk", 10)])
+def test_emulated_rollout_matches_oracle(name, H):
+    env, o = make_pair(name)
+    s = o.reset()
+    s.step[:] = 55          # exercise the ramp / gait phase / second jump stage
+    s.stage[:] = 1 if "jump" in name else 0
+    rng = np.random.default_rng(1)
+    us = np.clip(rng.normal(size=(3, H, env.action_size)) * 0.6, -1, 1)
+    rew, q, qd, x = o.rollout(s, us)
+    out = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us, step0=55,
+                       stage0=int(s.stage[0]))
+    # fp32 tolerances: positions 1e-4, velocities 5e-3, rewards 1e-3 relative
+    assert np.abs(out["q"] - q).max() < 1e-4
+    assert np.abs(out["qd"] - qd).max() < 5e-3
+    assert np.abs(out["xpos"] - x).max() < 1e-4
+    assert np.abs(out["rewss"] - rew).max() < 1e-3 * (1 + np.abs(rew).max())
+
+
+def test_emulated_pipeline_init_and_env_step():
+    env, o = make_pair("unitree_go2_walk")
+    s = o.reset()
+    out = emul.rollout(env, env.plan_desc(), o.init_q, np.zeros(18), np.zeros(18), mode=2, nrows=1, H=1)
+    assert np.abs(out["qpos_out"] - s.qpos[0]).max() < 1e-6
+    assert np.abs(out["warm_out"] - s.qacc_warmstart[0]).max() < 2e-3
+    a = np.random.default_rng(0).uniform(-1, 1, (1, 1, 12))
+    ns, r, aux = o.step(s, a[:, 0])
+    out = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=a)
+    assert np.abs(out["qpos_out"] - ns.qpos[0]).max() < 1e-5
+    assert np.abs(out["ctrl_out"] - aux["ctrl"][0]).max() < 1e-4
+    assert abs(out["rewss"][0, 0] - r[0]) < 1e-4
+
+
+def test_emulated_planner_rows_and_native_rng():
+    """mode 1: Y0s construction (pin node 0, mean row, clip), spline, shard offsets, and the
+    in-kernel Threefry/erfinv sampler against the oracle's restatement of jax.random.normal."""
+    from oracle.planner_oracle import PlannerOracle, jax_normal_legacy
+    env, o = make_pair("unitree_go2_walk")
+    N, Hs, Hn = 6, 8, 4
+    pl = PlannerOracle(o, N, Hs, Hn, 0.05, 0.9, 0.5)
+    s = o.reset()
+    key = (123, 456)
+    eps = jax_normal_legacy(key, (N, Hn + 1, 12))
+    Ybar = np.clip(np.random.default_rng(0).standard_normal((Hn + 1, 12)) * 0.5, -1.5, 1.5)
+    Yo, info = pl.reverse_once(s, eps, Ybar, pl.sigma_control)
+    from dial_mpc_b200.utils.spline import interp_matrix
+    # rank 1 of 2: rows 3..5 + mean row, native RNG
+    desc = env.plan_desc(Nsample=3, Ntotal=N, shard_offset=3, Hsample=Hs, Hnode=Hn, temp_sample=0.05,
+                         M_n2u=interp_matrix(pl.step_nodes, pl.step_us))
+    out = emul.rollout(env, desc, s.qpos[0], s.qvel[0], s.qacc_warmstart[0], Ybar=Ybar, noise=pl.sigma_control,
+                       key=key, mode=1, nrows=4, H=Hs + 1)
+    ref = np.concatenate([info["rews"][3:6], info["rews"][-1:]])
+    assert np.abs(out["rews"] - ref).max() < 5e-4
+    # injected eps gives the same rows
+    out2 = emul.rollout(env, desc, s.qpos[0], s.qvel[0], s.qacc_warmstart[0], Ybar=Ybar, noise=pl.sigma_control,
+                        eps=eps, mode=1, nrows=4, H=Hs + 1)
+    assert np.abs(out2["rews"] - out["rews"]).max() < 1e-4

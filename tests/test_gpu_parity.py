@@ -1,0 +1,186 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI against the fp64
+oracle, the committed golden fixtures, and size-independent properties at BASELINE sizes.
+
+Tolerances (fp32 kernel vs fp64 oracle): q / x.pos 2e-4 abs, qvel 1e-2 abs,
+per-step rewards 2e-3*(1+|r|), per-sample mean rewards 1e-3*(1+|r|), softmax weights total
+variation 2e-2, Ybar 1e-2 (weights are exp((r-rbar)/std/0.05): reward noise is amplified)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import ENV_CASES, make_pair
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _state_from(env, qpos, qvel, warm, step=0, stage=0):
+    from dial_mpc_b200.envs.base_env import PipelineState, State
+    plan = env._get_plan()
+    return State(PipelineState(plan.f32(qpos), plan.f32(qvel), plan.f32(warm)), None, 0.0, 0.0, {},
+                 {"step": int(step), "contact_stage": int(stage)})
+
+
+@pytest.mark.parametrize("name,H", [("unitree_go2_walk", 17), ("unitree_go2_seq_jump", 26), ("unitree_h1_walk", 31)])
+def test_rollout_matches_oracle(built, name, H):
+    from dial_mpc_b200 import random as drandom
+    env, o = make_pair(name)
+    s = o.reset()
+    st = env.reset(drandom.PRNGKey(0))
+    assert np.abs(st.pipeline_state.qpos.cpu().numpy() - s.qpos[0]).max() < 1e-6
+    assert np.abs(st.pipeline_state.qacc_warmstart.cpu().numpy() - s.qacc_warmstart[0]).max() < 2e-3
+    rng = np.random.default_rng(1)
+    B = 24
+    us = np.clip(rng.normal(size=(B, H, env.action_size)) * 0.6, -1, 1)
+    rew, q, qd, x = o.rollout(s, us)
+    rg, qg, qdg, xg = env._get_plan().rollout(st, us)
+    torch.cuda.synchronize()
+    assert np.abs(qg.cpu().numpy() - q).max() < 2e-4
+    assert np.abs(qdg.cpu().numpy() - qd).max() < 1e-2
+    assert np.abs(xg.cpu().numpy() - x).max() < 2e-4
+    assert (np.abs(rg.cpu().numpy() - rew) < 2e-3 * (1 + np.abs(rew))).all()
+
+
+def test_env_step_sequence_matches_oracle(built):
+    from dial_mpc_b200 import random as drandom
+    env, o = make_pair("unitree_go2_seq_jump")
+    s = o.reset()
+    st = env.reset(drandom.PRNGKey(0))
+    rng = np.random.default_rng(2)
+    for t in range(55):       # crosses the stage boundary at step 50
+        a = np.clip(rng.normal(size=12) * 0.4, -1, 1)
+        s, r, aux = o.step(s, a[None])
+        st = env.step(st, a)
+        assert st.info["step"] == t + 1 and st.info["contact_stage"] == int(s.stage[0])
+        if t < 12:            # contact dynamics are chaotic: compare while trajectories are close
+            assert abs(float(st.reward) - r[0]) < 2e-3 * (1 + abs(r[0]))
+            assert np.abs(st.pipeline_state.qpos.cpu().numpy() - s.qpos[0]).max() < 2e-4
+    assert np.isfinite(float(st.reward))
+
+
+@pytest.mark.parametrize("name", list(ENV_CASES))
+def test_reverse_once_matches_golden(built, name):
+    from dial_mpc_b200 import random as drandom
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import MBDPI
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    env, _ = make_pair(name)
+    cfg = DialConfig(env_name=name, Nsample=int(g["N"]), Hsample=int(g["Hs"]), Hnode=int(g["Hn"]),
+                     temp_sample=float(g["temp"]), horizon_diffuse_factor=0.9 if "go2" in name else 1.0)
+    mb = MBDPI(cfg, env)
+    assert np.abs(mb.sigma_control.cpu().numpy() - g["noise_scale"]).max() < 1e-6
+    st = _state_from(env, g["qpos"], g["qvel"], g["qacc_warmstart"], g["step"], g["stage"])
+    _, Ybar, info = mb.reverse_once(st, drandom.PRNGKey(0), g["Ybar0"], g["noise_scale"], eps=g["eps"])
+    torch.cuda.synchronize()
+    rews = info["rews"].cpu().numpy()
+    assert (np.abs(rews - g["rews"]) < 1e-3 * (1 + np.abs(g["rews"]))).all()
+    w = info["weights"].cpu().numpy()
+    assert abs(w.sum() - 1) < 1e-4
+    assert 0.5 * np.abs(w - g["weights"]).sum() < 2e-2
+    assert np.abs(Ybar.cpu().numpy() - g["Ybar"]).max() < 1e-2
+    assert np.abs(info["qbar"].cpu().numpy() - g["qbar"]).max() < 5e-3
+    assert np.abs(info["xbar"].cpu().numpy() - g["xbar"]).max() < 5e-3
+    # explicit-actions rollout of the same rows reproduces the per-step rewards
+    rewss, (q, qd, x) = mb.rollout_us_vmap(st, g["us"])
+    assert (np.abs(rewss.cpu().numpy() - g["rewss"]) < 2e-3 * (1 + np.abs(g["rewss"]))).all()
+
+
+def test_update_stage_exact_on_given_rewards(built):
+    """weights/Ybar kernels against a float64 evaluation on the SAME rewards (no chaos)."""
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import MBDPI
+    env, _ = make_pair("unitree_go2_walk")
+    N, Hn = 1000, 4
+    mb = MBDPI(DialConfig(env_name="unitree_go2_walk", Nsample=N, Hsample=16, Hnode=Hn, temp_sample=0.05), env)
+    rng = np.random.default_rng(0)
+    rews = rng.normal(size=N + 1).astype(np.float32) * 0.3 - 1.0
+    eps = rng.standard_normal((N, Hn + 1, 12)).astype(np.float32)
+    Ybar = (rng.standard_normal((Hn + 1, 12)) * 0.4).astype(np.float32)
+    noise = mb.sigma_control
+    out, w = torch.empty(Hn + 1, 12, device="cuda"), torch.empty(N + 1, device="cuda")
+    mb.plan.reverse_update(mb.plan.f32(eps), None, mb.plan.f32(Ybar), noise, mb.plan.f32(rews), out, w)
+    r = rews.astype(np.float64)
+    logp = (r - r[-1]) / r.std() / 0.05
+    wr = np.exp(logp - logp.max()); wr /= wr.sum()
+    Y0s = eps.astype(np.float64) * noise.cpu().numpy().astype(np.float64)[None, :, None] + Ybar
+    Y0s[:, 0] = Ybar[0]
+    Y0s = np.clip(np.concatenate([Y0s, Ybar[None].astype(np.float64)], 0), -1, 1)
+    assert np.abs(w.cpu().numpy() - wr).max() < 2e-5
+    assert np.abs(out.cpu().numpy() - np.einsum("n,nij->ij", wr, Y0s)).max() < 2e-5
+    # diverged samples (NaN / inf reward) get weight 0 instead of poisoning the update
+    rews2 = rews.copy(); rews2[5] = np.nan; rews2[7] = np.inf
+    mb.plan.reverse_update(mb.plan.f32(eps), None, mb.plan.f32(Ybar), noise, mb.plan.f32(rews2), out, w)
+    wn = w.cpu().numpy()
+    assert wn[5] == 0 and wn[7] == 0 and np.isfinite(wn).all() and abs(wn.sum() - 1) < 1e-4
+
+
+def test_native_rng_matches_oracle_restatement(built):
+    """In-kernel Threefry + erfinv sampler == the oracle's restatement of jax.random.normal
+    (legacy counter layout): same rewards whether eps is injected or generated."""
+    from dial_mpc_b200 import random as drandom
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import MBDPI
+    from oracle.planner_oracle import jax_normal_legacy, jax_split_legacy
+    env, _ = make_pair("unitree_go2_walk")
+    N, Hs, Hn = 256, 16, 4
+    mb = MBDPI(DialConfig(env_name="unitree_go2_walk", Nsample=N, Hsample=Hs, Hnode=Hn, temp_sample=0.05), env)
+    st = env.reset(drandom.PRNGKey(0))
+    rng = drandom.PRNGKey(3)
+    Y0 = torch.zeros(Hn + 1, 12, device="cuda")
+    rng1, Y1, i1 = mb.reverse_once(st, rng, Y0, mb.sigma_control)
+    sub = jax_split_legacy((int(rng[0]), int(rng[1])))
+    assert tuple(rng1) == tuple(sub[0])
+    eps = jax_normal_legacy(tuple(int(v) for v in sub[1]), (N, Hn + 1, 12)).astype(np.float32)
+    _, Y2, i2 = mb.reverse_once(st, rng, Y0, mb.sigma_control, eps=eps)
+    assert np.abs(i1["rews"].cpu().numpy() - i2["rews"].cpu().numpy()).max() < 2e-4
+    assert np.abs(Y1.cpu().numpy() - Y2.cpu().numpy()).max() < 5e-3
+
+
+def test_full_size_properties(built):
+    """BASELINE configs[1] size (Go2 seq-jump, N=2048, Hs=25): properties that do not need the
+    oracle — determinism, shard invariance, simplex weights, bounded update, finite outputs."""
+    from dial_mpc_b200 import random as drandom
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import MBDPI
+    env, _ = make_pair("unitree_go2_seq_jump")
+    N, Hs, Hn = 2048, 25, 5
+    cfg = DialConfig(env_name="unitree_go2_seq_jump", Nsample=N, Hsample=Hs, Hnode=Hn, temp_sample=0.05)
+    mb = MBDPI(cfg, env)
+    st = env.reset(drandom.PRNGKey(0))
+    rng = drandom.PRNGKey(0)
+    Y0 = torch.zeros(Hn + 1, 12, device="cuda")
+    _, Ya, ia = mb.reverse_once(st, rng, Y0, mb.sigma_control)
+    _, Yb, ib = mb.reverse_once(st, rng, Y0, mb.sigma_control)
+    assert torch.equal(ia["rews"], ib["rews"]) and torch.equal(Ya, Yb)          # bitwise deterministic
+    w = ia["weights"]
+    assert torch.isfinite(ia["rews"]).all() and abs(float(w.sum()) - 1) < 1e-4 and float(w.min()) >= 0
+    assert float(Ya.abs().max()) <= 1.0 + 1e-6                                  # convex combination of clipped knots
+    assert torch.allclose(Ya[0], Y0[0].clamp(-1, 1), atol=1e-6)                # node 0 is pinned
+    assert ia["qbar"].shape == (Hs + 1, 19) and ia["xbar"].shape == (Hs + 1, 13, 3)
+    # a rank owning only samples [1024, 2048) computes bitwise the same per-sample rewards
+    half = MBDPI(cfg, env, rank=1, world_size=2)
+    half.plan.reverse_rollout(st, None, drandom.split(rng)[1], Y0, mb.sigma_control, half._rews_local)
+    torch.cuda.synchronize()
+    assert torch.equal(half._rews_local[:1024], ia["rews"][1024:2048])
+    assert torch.equal(half._rews_local[1024], ia["rews"][2048])
+    # mean of zero-noise rows equals the mean row
+    _, Yz, iz = mb.reverse_once(st, rng, Y0, torch.zeros(Hn + 1, device="cuda"))
+    assert float((iz["rews"] - iz["rews"][-1]).abs().max()) == 0.0
+
+
+def test_error_paths(built):
+    from dial_mpc_b200 import _capi
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import MBDPI
+    env, _ = make_pair("unitree_go2_walk")
+    with pytest.raises(ValueError):
+        MBDPI(DialConfig(env_name="unitree_go2_walk", Nsample=8, Hsample=100, Hnode=4), env)   # Hsample too long
+    with pytest.raises(KeyError):
+        MBDPI(DialConfig(env_name="unitree_go2_walk", update_method="cma"), env)
+    d = env.plan_desc()
+    d.env_id = 99
+    from dial_mpc_b200.plan import Plan
+    with pytest.raises(RuntimeError, match="unknown env_id"):
+        Plan(env, d)
