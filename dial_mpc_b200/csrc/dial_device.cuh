@@ -69,6 +69,9 @@ struct alignas(16) DevModel {
   int32_t con_lastdof[DIAL_MAXC];     // deepest dof moving the contact's body (geom1 must be static)
   int32_t dof_nchain[DIAL_MAXV], dof_ndesc[DIAL_MAXV], nlimited;
   int32_t chain_tab[DIAL_MAXV][DIAL_MAXCHAIN];
+  // star decomposition: root chain + hanging serial chains (0 chains: not a star)
+  int32_t star_nroot, star_nchain, star_maxlen;
+  int32_t star_root[8], star_len[4], star_leaf[4], star_att[4];
   int32_t nedge;                      // 4 * ncon
   // per-warp shared-memory layout (float offsets)
   int32_t o_xpos, o_xquat, o_xmat, o_xipos, o_cinert, o_cdof, o_cdofdot, o_cvel, o_cacc,
@@ -343,6 +346,178 @@ DEV float solve_LTL(WarpCtx& w, const float* R, float invd, float g) {
   return x;
 }
 
+// ---------------------------------------------------------------------------------
+// "Star" solve: root chain (NR dofs, e.g. the floating base) + hanging serial chains
+// (legs, arms; <= NL dofs each).  Block elimination of  [[A_l, C_l],[C_l^T, B]]:
+//   chain lane l : A_l = R^T R,  W = R^-T C_l,  T_l = W^T W,  z = R^-T g_l     (registers)
+//   all lanes    : S = B - sum_l T_l (2 shuffle stages + broadcast), Cholesky of S, x_B
+//   chain lane l : x_l = R^-1 (z - W x_B)
+// Replaces the level-scheduled factor/solve (27 warp barriers) by 3 barriers and a few
+// hundred fully unrolled register instructions.  Rrow: this lane's compact row of H.
+// ---------------------------------------------------------------------------------
+template <int NL, int NR>
+DEV float star_solve(WarpCtx& w, const float* Rrow, float g) {
+  const DevModel& M = *w.M;
+  const int lane = w.lane;
+  float* Hb = SM(L);
+  float* vec = SM(vec);
+  syncwarp();
+#pragma unroll
+  for (int c = 0; c < MC; ++c)
+    if (c < w.nch) Hb[lane * MC + c] = Rrow[c];
+  vec[lane] = g;
+  syncwarp();
+  // ---- gather this lane's chain blocks -----------------------------------------------
+  const bool ischain = lane < M.star_nchain;
+  const int len = ischain ? M.star_len[lane] : 0;
+  const int leaf = ischain ? M.star_leaf[lane] : 0;
+  const int att = ischain ? M.star_att[lane] : NR;
+  float A[NL][NL], Cw[NL][NR], z[NL];
+  int dofs[NL];
+#pragma unroll
+  for (int p = 0; p < NL; ++p) {
+    const bool on = p < len;
+    const int dof = on ? M.chain_tab[leaf][p] : 0;
+    dofs[p] = dof;
+    const float* row = Hb + dof * MC;
+#pragma unroll
+    for (int p2 = p; p2 < NL; ++p2) A[p][p2] = (on && p2 < len) ? row[p2 - p] : (p2 == p ? 1.f : 0.f);
+#pragma unroll
+    for (int a = 0; a < NR; ++a) Cw[p][a] = (on && a >= att) ? row[(len - p) + (a - att)] : 0.f;
+    z[p] = on ? vec[dof] : 0.f;
+  }
+  // root block (every lane holds it)
+  float S[NR][NR], xB[NR];
+#pragma unroll
+  for (int a = 0; a < NR; ++a) {
+    const int dof = M.star_root[a];
+#pragma unroll
+    for (int a2 = a; a2 < NR; ++a2) S[a][a2] = Hb[dof * MC + (a2 - a)];
+    xB[a] = vec[dof];
+  }
+  // ---- chain: A = R^T R (upper R in place), W = R^-T C, z = R^-T g ------------------------
+  float rinv[NL];
+#pragma unroll
+  for (int p = 0; p < NL; ++p) {
+    float d = A[p][p];
+#pragma unroll
+    for (int k = 0; k < p; ++k) d -= A[k][p] * A[k][p];
+    const float inv = rsqrtf(fmaxf(d, DIAL_MINVAL));
+    rinv[p] = inv;
+    A[p][p] = d * inv;
+#pragma unroll
+    for (int p2 = p + 1; p2 < NL; ++p2) {
+      float v = A[p][p2];
+#pragma unroll
+      for (int k = 0; k < p; ++k) v -= A[k][p] * A[k][p2];
+      A[p][p2] = v * inv;
+    }
+#pragma unroll
+    for (int a = 0; a < NR; ++a) {
+      float v = Cw[p][a];
+#pragma unroll
+      for (int k = 0; k < p; ++k) v -= A[k][p] * Cw[k][a];
+      Cw[p][a] = v * inv;
+    }
+    float v = z[p];
+#pragma unroll
+    for (int k = 0; k < p; ++k) v -= A[k][p] * z[k];
+    z[p] = v * inv;
+  }
+  // ---- Schur complement contributions, reduced over the chain lanes -------------------------
+  float T[NR][NR], tb[NR];
+#pragma unroll
+  for (int a = 0; a < NR; ++a) {
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < NL; ++p) s += Cw[p][a] * z[p];
+    tb[a] = s;
+#pragma unroll
+    for (int a2 = a; a2 < NR; ++a2) {
+      float t = 0.f;
+#pragma unroll
+      for (int p = 0; p < NL; ++p) t += Cw[p][a] * Cw[p][a2];
+      T[a][a2] = t;
+    }
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {   // star_nchain <= 4: lanes 0..3 end up with the sum
+#pragma unroll
+    for (int a = 0; a < NR; ++a) {
+      tb[a] += shfl_xor(tb[a], o);
+#pragma unroll
+      for (int a2 = a; a2 < NR; ++a2) T[a][a2] += shfl_xor(T[a][a2], o);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NR; ++a) {
+    xB[a] -= shfl(tb[a], 0);
+#pragma unroll
+    for (int a2 = a; a2 < NR; ++a2) S[a][a2] -= shfl(T[a][a2], 0);
+  }
+  // ---- root: S = U^T U, solve (every lane redundantly) ---------------------------------------
+  float sinv[NR];
+#pragma unroll
+  for (int a = 0; a < NR; ++a) {
+    float d = S[a][a];
+#pragma unroll
+    for (int k = 0; k < a; ++k) d -= S[k][a] * S[k][a];
+    const float inv = rsqrtf(fmaxf(d, DIAL_MINVAL));
+    sinv[a] = inv;
+#pragma unroll
+    for (int a2 = a + 1; a2 < NR; ++a2) {
+      float v = S[a][a2];
+#pragma unroll
+      for (int k = 0; k < a; ++k) v -= S[k][a] * S[k][a2];
+      S[a][a2] = v * inv;
+    }
+    float v = xB[a];
+#pragma unroll
+    for (int k = 0; k < a; ++k) v -= S[k][a] * xB[k];
+    xB[a] = v * inv;
+  }
+#pragma unroll
+  for (int a = NR - 1; a >= 0; --a) {
+    float v = xB[a];
+#pragma unroll
+    for (int a2 = a + 1; a2 < NR; ++a2) v -= S[a][a2] * xB[a2];
+    xB[a] = v * sinv[a];
+  }
+  // ---- chain back-substitution: x_l = R^-1 (z - W x_B) -----------------------------------------
+#pragma unroll
+  for (int p = NL - 1; p >= 0; --p) {
+    float v = z[p];
+#pragma unroll
+    for (int a = 0; a < NR; ++a) v -= Cw[p][a] * xB[a];
+#pragma unroll
+    for (int p2 = p + 1; p2 < NL; ++p2) v -= A[p][p2] * z[p2];
+    z[p] = v * rinv[p];
+  }
+  // ---- scatter back to the dof lanes -------------------------------------------------------------
+  syncwarp();
+#pragma unroll
+  for (int p = 0; p < NL; ++p)
+    if (p < len) vec[dofs[p]] = z[p];
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < NR; ++a) vec[M.star_root[a]] = xB[a];
+  }
+  syncwarp();
+  return vec[lane];
+}
+
+// NL == 0: generic tree (level-scheduled compact Cholesky); otherwise the star solve
+template <int NL, int NR>
+DEV float tree_solve(WarpCtx& w, float* R, float g) {
+  if constexpr (NL == 0) {
+    float invd = 0.f;
+    factor_LTL(w, R, invd);
+    return solve_LTL(w, R, invd, g);
+  } else {
+    return star_solve<NL, NR>(w, R, g);
+  }
+}
+
 // y = M x; Mrow = this lane's compact row of M (also published in SM(Mb)).  Uses SM(vec).
 DEV float mul_M(WarpCtx& w, const float* Mrow, float x) {
   const DevModel& M = *w.M;
@@ -575,6 +750,7 @@ DEV void linesearch(WarpCtx& w, Solver& S, const float* Mrow) {
 // one physics step (mjx.step) for the warp's sample.  State (qpos,qvel,warm,ctrl) in
 // the slab; kinematic arrays of the forward pass are left in the slab for the reward.
 // ---------------------------------------------------------------------------------
+template <int NL, int NR>
 DEV void physics_step(WarpCtx& w, bool integrate) {
   const DevModel& M = *w.M;
   const dial_model_desc& m = M.m;
@@ -923,9 +1099,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   for (int c = 0; c < MC; ++c) R[c] = Mrow[c];
   int phase = 0, it = 0;
   while (true) {
-    float invd = 0.f;
-    factor_LTL(w, R, invd);
-    float x = solve_LTL(w, R, invd, g);
+    float x = tree_solve<NL, NR>(w, R, g);
     if (phase == 0) {
       S.qas = x;
       if (M.nedge == 0 && M.nlimited == 0) { S.qacc = x; break; }
@@ -1098,6 +1272,7 @@ DEV float reward_lane0(WarpCtx& w, int step, int& stage) {
 // ---------------------------------------------------------------------------------
 // the per-warp rollout: one sample row, H env steps
 // ---------------------------------------------------------------------------------
+template <int NL, int NR>
 DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const RolloutArgs& A,
                       int row, int lane) {
   WarpCtx w;
@@ -1187,7 +1362,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
       SM(ctrl)[lane] = ctrl;
     }
     syncwarp();
-    for (int f = 0; f < nfr; ++f) physics_step(w, !fwd_only);
+    for (int f = 0; f < nfr; ++f) physics_step<NL, NR>(w, !fwd_only);
     if (fwd_only) break;
     float rew = 0.f;
     if (lane == 0) rew = reward_lane0(w, step, stage);

@@ -5,6 +5,45 @@
 #include <string>
 #include "dial_device.cuh"
 
+// Star decomposition: hanging chains = maximal serial chains ending at leaf dofs whose dofs
+// all have <= 1 child; the remaining dofs must form one chain from dof 0 (the root block).
+static inline void derive_star(const dial_model_desc& m, DevModel& D) {
+  const int nv = m.nv;
+  D.star_nroot = D.star_nchain = D.star_maxlen = 0;
+  int nchild[DIAL_MAXV] = {0};
+  for (int i = 0; i < nv; ++i) if (m.dof_parentid[i] >= 0) nchild[m.dof_parentid[i]]++;
+  bool inchain[DIAL_MAXV] = {false};
+  int nchain = 0, len[4], leaf[4], top[4];
+  for (int i = 0; i < nv; ++i) {
+    if (nchild[i] != 0) continue;             // leaf dof
+    int l = 0, j = i, t = i;
+    while (j >= 0 && nchild[j] <= 1) { inchain[j] = true; t = j; ++l; j = m.dof_parentid[j]; }
+    if (nchain >= 4) return;
+    len[nchain] = l; leaf[nchain] = i; top[nchain] = t; ++nchain;
+  }
+  // root block: the remaining dofs, must be a chain ending at dof `rl` (deepest root dof)
+  int nroot = 0, rl = -1;
+  for (int i = 0; i < nv; ++i) if (!inchain[i]) { ++nroot; rl = i; }
+  if (nroot == 0) {
+    // a single serial chain (or forest of chains): treat the top of chain 0 ... not a star
+    return;
+  }
+  if (nroot > 8 || D.dof_nchain[rl] != nroot) return;   // root dofs must all be ancestors of rl
+  for (int a = 0; a < nroot; ++a) if (inchain[D.chain_tab[rl][a]]) return;
+  for (int l = 0; l < nchain; ++l) {
+    int par = m.dof_parentid[top[l]], att = nroot;        // no coupling if the chain hangs off the world
+    if (par >= 0) {
+      att = -1;
+      for (int a = 0; a < nroot; ++a) if (D.chain_tab[rl][a] == par) att = a;
+      if (att < 0) return;
+    }
+    D.star_len[l] = len[l]; D.star_leaf[l] = leaf[l]; D.star_att[l] = att;
+    D.star_maxlen = len[l] > D.star_maxlen ? len[l] : D.star_maxlen;
+  }
+  for (int a = 0; a < nroot; ++a) D.star_root[a] = D.chain_tab[rl][a];
+  D.star_nroot = nroot; D.star_nchain = nchain;
+}
+
 static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::string& err) {
   memset(&D, 0, sizeof(D));
   D.m = m;
@@ -114,6 +153,7 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
     }
   }
   if (c != m.ncon) { err = "pair_ncon does not sum to ncon"; return false; }
+  derive_star(m, D);
   D.nedge = 4 * m.ncon;
   // per-warp slab layout
   int o = 0;
@@ -128,4 +168,13 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   D.o_misc = take(8);
   D.warp_floats = o;
   return true;
+}
+
+// which solver instantiation fits the model: 1 = star<3,6>, 2 = star<5,7>, 0 = generic tree
+static inline int star_variant(const DevModel& D) {
+  if (D.star_nchain >= 1 && D.star_nchain <= 4) {
+    if (D.star_nroot == 6 && D.star_maxlen <= 3) return 1;
+    if (D.star_nroot == 7 && D.star_maxlen <= 5) return 2;
+  }
+  return 0;
 }

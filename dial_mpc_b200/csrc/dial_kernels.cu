@@ -11,6 +11,7 @@
 //   trajbar_kernel        qbar / qdbar / xbar weighted sums over the stored trajectories.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <new>
 #include "dial_host.h"
@@ -44,7 +45,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 static_assert(sizeof(DevModel) % 16 == 0, "DevModel must be a multiple of 16 bytes for cp.async.bulk");
 static_assert(sizeof(DevPlan) % 16 == 0, "DevPlan must be a multiple of 16 bytes for cp.async.bulk");
 
-template <int WPC>
+template <int WPC, int NL, int NR>
 __global__ void __launch_bounds__(WPC * 32, 16 / WPC) rollout_kernel(const DevModel* __restrict__ gM,
                                                             const DevPlan* __restrict__ gP,
                                                             const RolloutArgs A) {
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(WPC * 32, 16 / WPC) rollout_kernel(const DevMo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * WPC + warp;
   if (row >= A.nrows) return;
-  rollout_warp(sM, sP, slabs + (size_t)warp * sM->warp_floats, A, row, lane);
+  rollout_warp<NL, NR>(sM, sP, slabs + (size_t)warp * sM->warp_floats, A, row, lane);
 }
 
 // ---------------------------------------------------------------------------------
@@ -217,6 +218,7 @@ struct dial_plan {
   DevModel* dM = nullptr;
   DevPlan* dP = nullptr;
   int wpc = 4;
+  int variant = 0;
   size_t smem_bytes = 0;
   // workspaces
   float *traj_q = nullptr, *traj_qd = nullptr, *traj_x = nullptr;  // [Nsample+1, Hs+1, *]
@@ -234,19 +236,29 @@ extern "C" size_t dial_sizeof(int which) {
   return which == 0 ? sizeof(dial_model_desc) : which == 1 ? sizeof(dial_plan_desc) : which == 2 ? sizeof(dial_state) : 0;
 }
 
-template <int WPC>
-static cudaError_t launch_rollout(dial_plan* p, const RolloutArgs& A, cudaStream_t st) {
+template <int WPC, int NL, int NR>
+static cudaError_t launch_rollout_t(dial_plan* p, const RolloutArgs& A, cudaStream_t st) {
   size_t smem = sizeof(DevModel) + sizeof(DevPlan) + (size_t)WPC * p->hM.warp_floats * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(rollout_kernel<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rollout_kernel<WPC, NL, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
   int grid = (A.nrows + WPC - 1) / WPC;
-  rollout_kernel<WPC><<<grid, WPC * 32, smem, st>>>(p->dM, p->dP, A);
+  rollout_kernel<WPC, NL, NR><<<grid, WPC * 32, smem, st>>>(p->dM, p->dP, A);
   p->launches++;
   return cudaGetLastError();
+}
+
+// solver instantiation by tree shape: star<3,6> (quadruped), star<5,7> (humanoid), generic tree
+template <int WPC>
+static cudaError_t launch_rollout(dial_plan* p, const RolloutArgs& A, cudaStream_t st) {
+  switch (p->variant) {
+    case 1: return launch_rollout_t<WPC, 3, 6>(p, A, st);
+    case 2: return launch_rollout_t<WPC, 5, 7>(p, A, st);
+    default: return launch_rollout_t<WPC, 0, 0>(p, A, st);
+  }
 }
 
 static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A, cudaStream_t st) {
@@ -262,6 +274,7 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
   if (!p) { g_err = "out of memory"; return nullptr; }
   std::string err;
   if (!derive_model(*model, p->hM, err)) { g_err = err; delete p; return nullptr; }
+  p->variant = getenv("DIAL_FORCE_GENERIC_TREE") ? 0 : star_variant(p->hM);
   memset(&p->hP, 0, sizeof(DevPlan));
   p->hP.c = *cfg;
   const dial_plan_desc& c = *cfg;

@@ -7,6 +7,9 @@
 #include <stdio.h>
 #include "../../dial_mpc_b200/csrc/dial_host.h"
 
+int forced_variant = -1;
+extern "C" void emul_force_variant(int v) { forced_variant = v; }
+
 extern "C" int emul_rollout(const dial_model_desc* m, const dial_plan_desc* c, int mode, int nrows,
                             int H, int step0, int stage0, const float* qpos0, const float* qvel0,
                             const float* warm0, const float* us, const float* eps, const float* Ybar,
@@ -26,7 +29,12 @@ extern "C" int emul_rollout(const dial_model_desc* m, const dial_plan_desc* c, i
   A.xpos = xpos; A.qpos_out = qpos_out; A.qvel_out = qvel_out; A.warm_out = warm_out; A.ctrl_out = ctrl_out;
   std::vector<float> slab(D.warp_floats, 0.f);
   for (int row = 0; row < nrows; ++row) {
-    emul::run_warp([&](int lane) { rollout_warp(&D, &P, slab.data(), A, row, lane); });
+    const int variant = forced_variant >= 0 ? forced_variant : star_variant(D);
+    emul::run_warp([&](int lane) {
+      if (variant == 1) rollout_warp<3, 6>(&D, &P, slab.data(), A, row, lane);
+      else if (variant == 2) rollout_warp<5, 7>(&D, &P, slab.data(), A, row, lane);
+      else rollout_warp<0, 0>(&D, &P, slab.data(), A, row, lane);
+    });
     if (slab_out && row == 0) memcpy(slab_out, slab.data(), sizeof(float) * D.warp_floats);
   }
   return 0;
