@@ -33,6 +33,7 @@ DEV void syncwarp() { __syncwarp(); }
 DEV float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEV int shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+DEV void cta_sync() { __syncthreads(); }
 #endif
 #ifndef DEVNI
 #define DEVNI inline
@@ -90,6 +91,7 @@ struct RolloutArgs {
   int32_t nrows;        // sample rows rolled by this launch
   int32_t H;            // env steps per row
   int32_t mode;         // 0: explicit us; 1: planner (Y0s from eps / key); 2: forward only (pipeline_init)
+  int32_t lockstep;     // 1: warps of a CTA re-converge at every env step (shared instruction fetch)
   int32_t step0, stage0;
   const float* qpos0;
   const float* qvel0;
@@ -1339,6 +1341,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
   const int H = fwd_only ? 1 : A.H;
   const int nfr = fwd_only ? 1 : c.n_frames;
   for (int t = 0; t < H; ++t) {
+    if (A.lockstep) cta_sync();
     // action -> joint target -> torque (base_env.py:37-66)
     if (lane < nu && fwd_only) SM(ctrl)[lane] = 0.f;
     if (lane < nu && !fwd_only) {
