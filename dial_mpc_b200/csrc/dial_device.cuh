@@ -1111,7 +1111,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
       float lJw = S.l_sign * mywarm - S.l_aref;
       float gw = (Maw - S.qfs) * (mywarm - S.qas);
       float cw = ((lJw < 0.f) ? S.l_D * lJw * lJw : 0.f) + ((eJw < 0.f) ? S.e_D * eJw * eJw : 0.f);
-      float Mas = mul_M(w, Mrow, S.qas);
+      float Mas = S.qfs;  // M * M^-1 qfrc_smooth (MJX multiplies it out numerically; equal up to rounding)
       float eJs = mul_J(w, S.qas) - S.e_aref;
       float lJs = S.l_sign * S.qas - S.l_aref;
       float cs = ((lJs < 0.f) ? S.l_D * lJs * lJs : 0.f) + ((eJs < 0.f) ? S.e_D * eJs * eJs : 0.f);

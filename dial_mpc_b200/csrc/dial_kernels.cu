@@ -181,23 +181,38 @@ __global__ void __launch_bounds__(YBAR_THREADS) ybar_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------
-// qbar / qdbar / xbar  (core/dial_core.py:133-135): weighted sums over stored trajectories
-//   grid = H (one CTA per time step); block = (32 columns, 8 sample groups) loops
+// qbar / qdbar / xbar  (core/dial_core.py:133-135): weighted sums over stored trajectories.
+//   stage 1: grid (H, TB_CHUNKS, 3 arrays), block = 32 columns x 8 row groups -> per-chunk partials
+//   stage 2: grid H: partials summed in fixed chunk order (bitwise deterministic)
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) trajbar_kernel(const float* __restrict__ traj, int ncol, int nrows, int H,
-                                                       const float* __restrict__ weights, int w_offset, int mean_row,
-                                                       int mean_weight_index, int include_mean, float* __restrict__ out) {
+#define TB_CHUNKS 8
+struct TrajArgs {
+  const float* traj[3];
+  float* out[3];
+  int ncol[3], coloff[3];
+  int coltot, nrows, H;
+  const float* weights;
+  int w_offset, mean_row, mean_weight_index, include_mean;
+  float* partial;  // [TB_CHUNKS][H][coltot]
+};
+
+__global__ void __launch_bounds__(256) trajbar_partial_kernel(const TrajArgs T) {
   __shared__ float red[8][33];
-  const int t = blockIdx.x, cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int t = blockIdx.x, chunk = blockIdx.y, arr = blockIdx.z;
+  const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int ncol = T.ncol[arr];
+  const float* __restrict__ traj = T.traj[arr];
+  const int per = (T.nrows + TB_CHUNKS - 1) / TB_CHUNKS;
+  const int r0 = chunk * per, r1 = min(T.nrows, r0 + per);
   for (int c0 = 0; c0 < ncol; c0 += 32) {
     const int c = c0 + cx;
     float a = 0.f;
     if (c < ncol) {
-      for (int r = g; r < nrows; r += 8) {
+      for (int r = r0 + g; r < r1; r += 8) {
         float wgt;
-        if (r == mean_row) { if (!include_mean) continue; wgt = weights[mean_weight_index]; }
-        else wgt = weights[w_offset + r];
-        a += wgt * traj[((size_t)r * H + t) * ncol + c];
+        if (r == T.mean_row) { if (!T.include_mean) continue; wgt = T.weights[T.mean_weight_index]; }
+        else wgt = T.weights[T.w_offset + r];
+        a += wgt * traj[((size_t)r * T.H + t) * ncol + c];
       }
     }
     __syncthreads();
@@ -207,8 +222,19 @@ __global__ void __launch_bounds__(256) trajbar_kernel(const float* __restrict__ 
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += red[i][cx];
-      out[(size_t)t * ncol + c] = s;
+      T.partial[((size_t)chunk * T.H + t) * T.coltot + T.coloff[arr] + c] = s;
     }
+  }
+}
+
+__global__ void __launch_bounds__(128) trajbar_final_kernel(const TrajArgs T) {
+  const int t = blockIdx.x;
+  for (int col = threadIdx.x; col < T.coltot; col += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < TB_CHUNKS; ++ch) s += T.partial[((size_t)ch * T.H + t) * T.coltot + col];
+    const int arr = col >= T.coloff[2] ? 2 : (col >= T.coloff[1] ? 1 : 0);
+    if (T.out[arr]) T.out[arr][(size_t)t * T.ncol[arr] + (col - T.coloff[arr])] = s;
   }
 }
 
@@ -228,6 +254,7 @@ struct dial_plan {
   float *traj_q = nullptr, *traj_qd = nullptr, *traj_x = nullptr;  // [Nsample+1, Hs+1, *]
   float* weights = nullptr;                                        // [Ntotal+1]
   float* partial = nullptr;
+  float* tb_partial = nullptr;
   unsigned int* counter = nullptr;
   float* zeros = nullptr;                                          // [nv]
   int ybar_grid = 0;
@@ -329,6 +356,7 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
   int g = (c.Ntotal + 1 + slots - 1) / slots;
   p->ybar_grid = g < 1 ? 1 : (g > 296 ? 296 : g);
   if ((e = cudaMalloc(&p->partial, (size_t)p->ybar_grid * ne * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(partial)");
+  if ((e = cudaMalloc(&p->tb_partial, (size_t)TB_CHUNKS * H * (m.nq + m.nv + 3 * (m.nbody - 1)) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(tb_partial)");
   if ((e = cudaMalloc(&p->counter, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMalloc(counter)");
   if ((e = cudaMemset(p->counter, 0, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMemset(counter)");
   if ((e = cudaMalloc(&p->zeros, DIAL_MAXV * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(zeros)");
@@ -339,7 +367,7 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
 extern "C" void dial_plan_destroy(dial_plan* p) {
   if (!p) return;
   cudaFree(p->dM); cudaFree(p->dP); cudaFree(p->traj_q); cudaFree(p->traj_qd); cudaFree(p->traj_x);
-  cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->counter); cudaFree(p->zeros);
+  cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->tb_partial); cudaFree(p->counter); cudaFree(p->zeros);
   delete p;
 }
 
@@ -422,15 +450,20 @@ extern "C" int dial_reverse_trajbar(dial_plan* p, const float* weights, int rank
   cudaStream_t st = (cudaStream_t)stream;
   const float* w = weights ? weights : p->weights;
   const int H = c.Hsample + 1, rows = c.Nsample + 1;
-  struct { const float* traj; int ncol; float* out; } jobs[3] = {
-      {p->traj_q, m.nq, qbar}, {p->traj_qd, m.nv, qdbar}, {p->traj_x, 3 * (m.nbody - 1), xbar}};
-  for (auto& j : jobs) {
-    if (!j.out) continue;
-    trajbar_kernel<<<H, 256, 0, st>>>(j.traj, j.ncol, rows, H, w, c.shard_offset, c.Nsample, c.Ntotal,
-                                      rank == 0 ? 1 : 0, j.out);
-    p->launches++;
-    CUDA_OK(cudaGetLastError());
-  }
+  TrajArgs T;
+  T.traj[0] = p->traj_q; T.traj[1] = p->traj_qd; T.traj[2] = p->traj_x;
+  T.out[0] = qbar; T.out[1] = qdbar; T.out[2] = xbar;
+  T.ncol[0] = m.nq; T.ncol[1] = m.nv; T.ncol[2] = 3 * (m.nbody - 1);
+  T.coloff[0] = 0; T.coloff[1] = m.nq; T.coloff[2] = m.nq + m.nv;
+  T.coltot = m.nq + m.nv + 3 * (m.nbody - 1);
+  T.nrows = rows; T.H = H; T.weights = w; T.w_offset = c.shard_offset; T.mean_row = c.Nsample;
+  T.mean_weight_index = c.Ntotal; T.include_mean = rank == 0 ? 1 : 0; T.partial = p->tb_partial;
+  trajbar_partial_kernel<<<dim3(H, TB_CHUNKS, 3), 256, 0, st>>>(T);
+  p->launches++;
+  CUDA_OK(cudaGetLastError());
+  trajbar_final_kernel<<<H, 128, 0, st>>>(T);
+  p->launches++;
+  CUDA_OK(cudaGetLastError());
   return 0;
 }
 
