@@ -101,6 +101,9 @@ def run_reference(args):
 # clocks sampler
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi sampled every 20 ms from before the warm-up; stop(t0, t1) keeps the samples that
+    fall inside the timed region (falls back to the nearest ones if the region is shorter than
+    the sampling period)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -110,26 +113,33 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
+            self.rows.append((time.perf_counter(), [t.strip() for t in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        inside = [r for t, r in ok if t0 <= t <= t1 + 0.03]
+        where = "timed region"
+        if not inside and ok:
+            mid = 0.5 * (t0 + t1)
+            inside = [r for _, r in sorted(ok, key=lambda tr: abs(tr[0] - mid))[:3]]
+            where = "nearest samples (region shorter than the sampling period)"
+        sm = [float(r[0]) for r in inside]
+        mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in inside for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=reasons, samples=len(sm))
+                    reasons=reasons, samples=len(sm), window=where)
 
 
 # --------------------------------------------------------------------------------------------
@@ -185,12 +195,12 @@ def run_own(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        Y, rng, info = mpc_step(Y, rng)
-    sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        Y, rng, info = mpc_step(Y, rng)
+    sync_all()
     launches0 = mb.plan.launches
     evs = []
     sync_all()
@@ -205,7 +215,7 @@ def run_own(args):
     sync_all()
     t_wall = time.perf_counter() - t_wall0
     launches = mb.plan.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall0 + t_wall) if rank == 0 else None
     t_dev = sum(a.elapsed_time(b) for a, b in evs) / 1e3
     if world > 1:
         t = torch.tensor([t_dev], device=dev, dtype=torch.float64)

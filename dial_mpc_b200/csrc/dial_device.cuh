@@ -349,16 +349,21 @@ DEV float solve_LTL(WarpCtx& w, const float* R, float invd, float g) {
 }
 
 // ---------------------------------------------------------------------------------
-// "Star" solve: root chain (NR dofs, e.g. the floating base) + hanging serial chains
-// (legs, arms; <= NL dofs each).  Block elimination of  [[A_l, C_l],[C_l^T, B]]:
-//   chain lane l : A_l = R^T R,  W = R^-T C_l,  T_l = W^T W,  z = R^-T g_l     (registers)
-//   all lanes    : S = B - sum_l T_l (2 shuffle stages + broadcast), Cholesky of S, x_B
-//   chain lane l : x_l = R^-1 (z - W x_B)
-// Replaces the level-scheduled factor/solve (27 warp barriers) by 3 barriers and a few
-// hundred fully unrolled register instructions.  Rrow: this lane's compact row of H.
+// "Star" solve: root chain (NR dofs, e.g. the floating base) + up to 4 hanging serial chains
+// (legs, arms; <= NL dofs each).  Block elimination of  [[A_l, C_l],[C_l^T, B]] x = g  with the
+// warp split into 4 groups of 8 lanes: group l owns chain l, lane j of the group owns column j
+// of [C_l | g_l] (NR coupling columns + the right-hand side; NR + 1 <= 8):
+//   every lane : A_l = R^T R (3x3 / 5x5, redundantly per group)        registers, unrolled
+//   lane (l,j) : w_j = R^-T c_j ;  row j of  W^T [W | z]  via 8-lane shuffles
+//   all lanes  : sum over chains (2 xor-shuffle stages), S = B - sum_l W^T W, all-gather of S
+//                inside the group, Cholesky + solve of the NR x NR root block (redundantly)
+//   group l    : x_l = R^-1 (z - W x_B)  (3 xor-shuffle stages over the columns)
+// Replaces the level-scheduled factor/solve (27 warp barriers) by 3 barriers and a few hundred
+// unrolled register instructions with short dependency chains.  Rrow: compact row of H.
 // ---------------------------------------------------------------------------------
 template <int NL, int NR>
 DEV float star_solve(WarpCtx& w, const float* Rrow, float g) {
+  static_assert(NR + 1 <= 8, "root block + rhs must fit the 8 lanes of a group");
   const DevModel& M = *w.M;
   const int lane = w.lane;
   float* Hb = SM(L);
@@ -369,12 +374,13 @@ DEV float star_solve(WarpCtx& w, const float* Rrow, float g) {
     if (c < w.nch) Hb[lane * MC + c] = Rrow[c];
   vec[lane] = g;
   syncwarp();
-  // ---- gather this lane's chain blocks -----------------------------------------------
-  const bool ischain = lane < M.star_nchain;
-  const int len = ischain ? M.star_len[lane] : 0;
-  const int leaf = ischain ? M.star_leaf[lane] : 0;
-  const int att = ischain ? M.star_att[lane] : NR;
-  float A[NL][NL], Cw[NL][NR], z[NL];
+  const int grp = lane >> 3, j = lane & 7, gbase = lane & ~7;
+  const bool ischain = grp < M.star_nchain;
+  const int len = ischain ? M.star_len[grp] : 0;
+  const int leaf = ischain ? M.star_leaf[grp] : 0;
+  const int att = ischain ? M.star_att[grp] : NR;
+  // ---- gather: chain block A (whole group) and this lane's column of [C | g] -------------------
+  float A[NL][NL], wv[NL];
   int dofs[NL];
 #pragma unroll
   for (int p = 0; p < NL; ++p) {
@@ -384,20 +390,12 @@ DEV float star_solve(WarpCtx& w, const float* Rrow, float g) {
     const float* row = Hb + dof * MC;
 #pragma unroll
     for (int p2 = p; p2 < NL; ++p2) A[p][p2] = (on && p2 < len) ? row[p2 - p] : (p2 == p ? 1.f : 0.f);
-#pragma unroll
-    for (int a = 0; a < NR; ++a) Cw[p][a] = (on && a >= att) ? row[(len - p) + (a - att)] : 0.f;
-    z[p] = on ? vec[dof] : 0.f;
+    float cv = 0.f;
+    if (on && j < NR && j >= att) cv = row[(len - p) + (j - att)];
+    if (on && j == NR) cv = vec[dof];
+    wv[p] = cv;
   }
-  // root block (every lane holds it)
-  float S[NR][NR], xB[NR];
-#pragma unroll
-  for (int a = 0; a < NR; ++a) {
-    const int dof = M.star_root[a];
-#pragma unroll
-    for (int a2 = a; a2 < NR; ++a2) S[a][a2] = Hb[dof * MC + (a2 - a)];
-    xB[a] = vec[dof];
-  }
-  // ---- chain: A = R^T R (upper R in place), W = R^-T C, z = R^-T g ------------------------
+  // ---- A = R^T R (upper R in place), w = R^-T c ------------------------------------------------------
   float rinv[NL];
 #pragma unroll
   for (int p = 0; p < NL; ++p) {
@@ -406,7 +404,6 @@ DEV float star_solve(WarpCtx& w, const float* Rrow, float g) {
     for (int k = 0; k < p; ++k) d -= A[k][p] * A[k][p];
     const float inv = rsqrtf(fmaxf(d, DIAL_MINVAL));
     rinv[p] = inv;
-    A[p][p] = d * inv;
 #pragma unroll
     for (int p2 = p + 1; p2 < NL; ++p2) {
       float v = A[p][p2];
@@ -414,92 +411,97 @@ DEV float star_solve(WarpCtx& w, const float* Rrow, float g) {
       for (int k = 0; k < p; ++k) v -= A[k][p] * A[k][p2];
       A[p][p2] = v * inv;
     }
+    float v = wv[p];
 #pragma unroll
-    for (int a = 0; a < NR; ++a) {
-      float v = Cw[p][a];
-#pragma unroll
-      for (int k = 0; k < p; ++k) v -= A[k][p] * Cw[k][a];
-      Cw[p][a] = v * inv;
-    }
-    float v = z[p];
-#pragma unroll
-    for (int k = 0; k < p; ++k) v -= A[k][p] * z[k];
-    z[p] = v * inv;
+    for (int k = 0; k < p; ++k) v -= A[k][p] * wv[k];
+    wv[p] = v * inv;
   }
-  // ---- Schur complement contributions, reduced over the chain lanes -------------------------
-  float T[NR][NR], tb[NR];
+  // ---- row j of W^T [W | z], summed over the chains ---------------------------------------------------
+  float t[NR + 1];
+#pragma unroll
+  for (int j2 = 0; j2 <= NR; ++j2) {
+    float acc = 0.f;
+#pragma unroll
+    for (int p = 0; p < NL; ++p) acc += wv[p] * shfl(wv[p], gbase + j2);
+    t[j2] = acc;
+  }
+#pragma unroll
+  for (int j2 = 0; j2 <= NR; ++j2) {
+    t[j2] += shfl_xor(t[j2], 8);
+    t[j2] += shfl_xor(t[j2], 16);
+  }
+  // ---- root block: lane j holds row j of S and rhs_j, then all-gather inside the group ---------------
+  float srow[NR], rhs = 0.f;
+  {
+    const int jj = j < NR ? j : 0;
+    const int dofj = M.star_root[jj];
+#pragma unroll
+    for (int a2 = 0; a2 < NR; ++a2) {
+      const float b = (a2 >= jj) ? Hb[dofj * MC + (a2 - jj)] : Hb[M.star_root[a2] * MC + (jj - a2)];
+      srow[a2] = b - t[a2];
+    }
+    rhs = vec[dofj] - t[NR];
+  }
+  float S_[NR][NR], xB[NR];
 #pragma unroll
   for (int a = 0; a < NR; ++a) {
-    float s = 0.f;
 #pragma unroll
-    for (int p = 0; p < NL; ++p) s += Cw[p][a] * z[p];
-    tb[a] = s;
-#pragma unroll
-    for (int a2 = a; a2 < NR; ++a2) {
-      float t = 0.f;
-#pragma unroll
-      for (int p = 0; p < NL; ++p) t += Cw[p][a] * Cw[p][a2];
-      T[a][a2] = t;
-    }
+    for (int a2 = a; a2 < NR; ++a2) S_[a][a2] = shfl(srow[a2], gbase + a);
+    xB[a] = shfl(rhs, gbase + a);
   }
-#pragma unroll
-  for (int o = 1; o <= 2; o <<= 1) {   // star_nchain <= 4: lanes 0..3 end up with the sum
-#pragma unroll
-    for (int a = 0; a < NR; ++a) {
-      tb[a] += shfl_xor(tb[a], o);
-#pragma unroll
-      for (int a2 = a; a2 < NR; ++a2) T[a][a2] += shfl_xor(T[a][a2], o);
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < NR; ++a) {
-    xB[a] -= shfl(tb[a], 0);
-#pragma unroll
-    for (int a2 = a; a2 < NR; ++a2) S[a][a2] -= shfl(T[a][a2], 0);
-  }
-  // ---- root: S = U^T U, solve (every lane redundantly) ---------------------------------------
+  // S = U^T U, solve (every lane redundantly)
   float sinv[NR];
 #pragma unroll
   for (int a = 0; a < NR; ++a) {
-    float d = S[a][a];
+    float d = S_[a][a];
 #pragma unroll
-    for (int k = 0; k < a; ++k) d -= S[k][a] * S[k][a];
+    for (int k = 0; k < a; ++k) d -= S_[k][a] * S_[k][a];
     const float inv = rsqrtf(fmaxf(d, DIAL_MINVAL));
     sinv[a] = inv;
 #pragma unroll
     for (int a2 = a + 1; a2 < NR; ++a2) {
-      float v = S[a][a2];
+      float v = S_[a][a2];
 #pragma unroll
-      for (int k = 0; k < a; ++k) v -= S[k][a] * S[k][a2];
-      S[a][a2] = v * inv;
+      for (int k = 0; k < a; ++k) v -= S_[k][a] * S_[k][a2];
+      S_[a][a2] = v * inv;
     }
     float v = xB[a];
 #pragma unroll
-    for (int k = 0; k < a; ++k) v -= S[k][a] * xB[k];
+    for (int k = 0; k < a; ++k) v -= S_[k][a] * xB[k];
     xB[a] = v * inv;
   }
 #pragma unroll
   for (int a = NR - 1; a >= 0; --a) {
     float v = xB[a];
 #pragma unroll
-    for (int a2 = a + 1; a2 < NR; ++a2) v -= S[a][a2] * xB[a2];
+    for (int a2 = a + 1; a2 < NR; ++a2) v -= S_[a][a2] * xB[a2];
     xB[a] = v * sinv[a];
   }
-  // ---- chain back-substitution: x_l = R^-1 (z - W x_B) -----------------------------------------
+  // ---- chain back-substitution: x_l = R^-1 (z - W x_B) ----------------------------------------------
+  float xb_j = 0.f;
+#pragma unroll
+  for (int a = 0; a < NR; ++a) xb_j = (j == a) ? xB[a] : xb_j;
+  float xl[NL];
+#pragma unroll
+  for (int p = 0; p < NL; ++p) {
+    float v = (j < NR) ? wv[p] * xb_j : 0.f;
+    v += shfl_xor(v, 1); v += shfl_xor(v, 2); v += shfl_xor(v, 4);
+    xl[p] = shfl(wv[p], gbase + NR) - v;
+  }
 #pragma unroll
   for (int p = NL - 1; p >= 0; --p) {
-    float v = z[p];
+    float v = xl[p];
 #pragma unroll
-    for (int a = 0; a < NR; ++a) v -= Cw[p][a] * xB[a];
-#pragma unroll
-    for (int p2 = p + 1; p2 < NL; ++p2) v -= A[p][p2] * z[p2];
-    z[p] = v * rinv[p];
+    for (int p2 = p + 1; p2 < NL; ++p2) v -= A[p][p2] * xl[p2];
+    xl[p] = v * rinv[p];
   }
-  // ---- scatter back to the dof lanes -------------------------------------------------------------
+  // ---- scatter back to the dof lanes -------------------------------------------------------------------
   syncwarp();
+  if (j == 0) {
 #pragma unroll
-  for (int p = 0; p < NL; ++p)
-    if (p < len) vec[dofs[p]] = z[p];
+    for (int p = 0; p < NL; ++p)
+      if (p < len) vec[dofs[p]] = xl[p];
+  }
   if (lane == 0) {
 #pragma unroll
     for (int a = 0; a < NR; ++a) vec[M.star_root[a]] = xB[a];
