@@ -60,6 +60,7 @@ struct alignas(16) DevModel {
   float root_invmass[4];
   int32_t body_rootidx[DIAL_MAXB];
   int32_t child_adr[DIAL_MAXB], child_num[DIAL_MAXB], child_ids[DIAL_MAXB];
+  int32_t body_ndesc[DIAL_MAXB];      // descendant bodies (contiguous after b: depth-first order)
   int32_t dof_level[DIAL_MAXV], nlevel;
   int32_t level_adr[DIAL_MAXLEVEL + 1], level_dofs[DIAL_MAXV];
   uint32_t dof_ancmask[DIAL_MAXV];    // bit j: dof j is ancestor-or-self of dof i
@@ -77,7 +78,7 @@ struct alignas(16) DevModel {
   // per-warp shared-memory layout (float offsets)
   int32_t o_xpos, o_xquat, o_xmat, o_xipos, o_cinert, o_cdof, o_cdofdot, o_cvel, o_cacc,
       o_cfrc, o_Mb, o_L, o_J, o_qpos, o_qvel, o_warm, o_ctrl, o_vec, o_frow, o_cpos,
-      o_cframe, o_cdist, o_rcom, o_xch, o_site, o_misc, warp_floats;
+      o_cframe, o_cdist, o_rcom, o_xch, o_site, o_crb, o_cfs, o_misc, warp_floats;
   int32_t pad_[3];
 };
 
@@ -361,7 +362,7 @@ DEV float solve_LTL(WarpCtx& w, const float* R, float invd, float g) {
 // Replaces the level-scheduled factor/solve (27 warp barriers) by 3 barriers and a few hundred
 // unrolled register instructions with short dependency chains.  Rrow: compact row of H.
 // ---------------------------------------------------------------------------------
-template <int NL, int NR>
+template <int NL, int NR, int MCU>
 DEV float star_solve(WarpCtx& w, const float* Rrow, float g) {
   static_assert(NR + 1 <= 8, "root block + rhs must fit the 8 lanes of a group");
   const DevModel& M = *w.M;
@@ -370,7 +371,7 @@ DEV float star_solve(WarpCtx& w, const float* Rrow, float g) {
   float* vec = SM(vec);
   syncwarp();
 #pragma unroll
-  for (int c = 0; c < MC; ++c)
+  for (int c = 0; c < MCU; ++c)
     if (c < w.nch) Hb[lane * MC + c] = Rrow[c];
   vec[lane] = g;
   syncwarp();
@@ -511,18 +512,19 @@ DEV float star_solve(WarpCtx& w, const float* Rrow, float g) {
 }
 
 // NL == 0: generic tree (level-scheduled compact Cholesky); otherwise the star solve
-template <int NL, int NR>
+template <int NL, int NR, int MCU>
 DEV float tree_solve(WarpCtx& w, float* R, float g) {
   if constexpr (NL == 0) {
     float invd = 0.f;
     factor_LTL(w, R, invd);
     return solve_LTL(w, R, invd, g);
   } else {
-    return star_solve<NL, NR>(w, R, g);
+    return star_solve<NL, NR, MCU>(w, R, g);
   }
 }
 
 // y = M x; Mrow = this lane's compact row of M (also published in SM(Mb)).  Uses SM(vec).
+template <int MCU>
 DEV float mul_M(WarpCtx& w, const float* Mrow, float x) {
   const DevModel& M = *w.M;
   const int lane = w.lane;
@@ -533,7 +535,7 @@ DEV float mul_M(WarpCtx& w, const float* Mrow, float x) {
   syncwarp();
   float y = 0.f;
 #pragma unroll
-  for (int c = 0; c < MC; ++c)
+  for (int c = 0; c < MCU; ++c)
     if (c < w.nch) y += Mrow[c] * vec[w.chain[c]];
   for (int k = lane + 1; k <= lane + w.ndesc; ++k) y += Mb[k * MC + (M.dof_nchain[k] - w.nch)] * vec[k];
   return y;
@@ -638,6 +640,7 @@ DEV void update_constraint(WarpCtx& w, Solver& S) {
 }
 
 // compact row of H = M + J^T D_active J for this lane's dof
+template <int MCU>
 DEV void build_H(WarpCtx& w, const Solver& S, const float* Mrow, float* R) {
   const DevModel& M = *w.M;
   const int lane = w.lane;
@@ -647,7 +650,7 @@ DEV void build_H(WarpCtx& w, const Solver& S, const float* Mrow, float* R) {
   frow[lane] = (S.e_Jaref < 0.f) ? S.e_D : 0.f;
   syncwarp();
 #pragma unroll
-  for (int c = 0; c < MC; ++c) R[c] = Mrow[c];
+  for (int c = 0; c < MCU; ++c) R[c] = Mrow[c];
   if (w.nch > 0) {
     R[0] += (S.l_Jaref < 0.f) ? S.l_D : 0.f;  // limit rows are +-e_d: diagonal only
     for (int c_ = 0; c_ < M.m.ncon; ++c_) {
@@ -660,7 +663,7 @@ DEV void build_H(WarpCtx& w, const Solver& S, const float* Mrow, float* R) {
             const float* Je = Jc + e * MC + off;
             const float a = de * Je[0];
 #pragma unroll
-            for (int c = 0; c < MC; ++c)
+            for (int c = 0; c < MCU; ++c)
               if (c < w.nch) R[c] += a * Je[c];
           }
         }
@@ -703,11 +706,12 @@ DEV void ls_points(const Solver& S, float l_jv, float e_jv, const float* qg, con
   }
 }
 
+template <int MCU>
 DEV void linesearch(WarpCtx& w, Solver& S, const float* Mrow) {
   const DevModel& M = *w.M;
   const int nv = M.m.nv;
   const float scale = M.m.meaninertia * (float)(nv > 1 ? nv : 1);
-  float mv = mul_M(w, Mrow, S.search);
+  float mv = mul_M<MCU>(w, Mrow, S.search);
   float e_jv = mul_J(w, S.search);
   float l_jv = S.l_sign * S.search;
   float ss = S.search * S.search, sMa = S.search * (S.Ma - S.qfs), sMv = S.search * mv;
@@ -756,6 +760,7 @@ DEV void linesearch(WarpCtx& w, Solver& S, const float* Mrow) {
 // ---------------------------------------------------------------------------------
 template <int NL, int NR>
 DEV void physics_step(WarpCtx& w, bool integrate) {
+  constexpr int MCU = (NL == 3 && NR == 6) ? 9 : DIAL_MAXCHAIN;  // longest dof chain of the variant
   const DevModel& M = *w.M;
   const dial_model_desc& m = M.m;
   const int lane = w.lane, nb = m.nbody, nv = m.nv;
@@ -928,19 +933,27 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
     syncwarp();
   }
 
-  // ---- 5. composite inertia and RNE force up the tree (parents pull children) ----------
-  for (int lv = M.maxdepth - 1; lv >= 1; --lv) {
-    if (depth == lv) {
-      for (int ci = M.child_adr[b]; ci < M.child_adr[b] + M.child_num[b]; ++ci) {
-        int c = M.child_ids[ci];
-#pragma unroll
-        for (int i = 0; i < 10; ++i) cinert[10 * b + i] += cinert[10 * c + i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) cfrc[6 * b + i] += cfrc[6 * c + i];
+  // ---- 5. composite inertia and RNE force of every subtree ---------------------------------
+  // Bodies are in depth-first order, so the subtree of b is the index range [b, b + ndesc_b].
+  // 16 component lanes (10 of crb, 6 of cfrc) x 2 bodies per pass; no level loop, no barriers.
+  {
+    float* crb = SM(crb);
+    float* cfs = SM(cfs);
+    const int comp = lane & 15, half = lane >> 4;
+    const float* src = comp < 10 ? cinert + comp : cfrc + (comp - 10);
+    const int stride = comp < 10 ? 10 : 6;
+    float* dst = comp < 10 ? crb + comp : cfs + (comp - 10);
+    for (int b0 = 1; b0 < nb; b0 += 2) {
+      const int bb = b0 + half;
+      if (bb < nb) {
+        float acc = 0.f;
+        const int last = bb + M.body_ndesc[bb];
+        for (int jb = bb; jb <= last; ++jb) acc += src[jb * stride];
+        dst[bb * stride] = acc;
       }
     }
-    syncwarp();
   }
+  syncwarp();
 
   // ---- 7. collision (lane = contact) ---------------------------------------------------
   if (lane < m.ncon) {
@@ -1008,20 +1021,20 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   float myqvel = isdof ? qvel[d] : 0.f;
   float Mrow[MC], R[MC];
 #pragma unroll
-  for (int c = 0; c < MC; ++c) { Mrow[c] = 0.f; R[c] = 0.f; }
+  for (int c = 0; c < MCU; ++c) { Mrow[c] = 0.f; R[c] = 0.f; }
   if (isdof) {
     int bi = m.dof_bodyid[d];
     float f[6];
-    inert_mul(cinert + 10 * bi, cdof + 6 * d, f);
+    inert_mul(SM(crb) + 10 * bi, cdof + 6 * d, f);
 #pragma unroll
-    for (int c = 0; c < MC; ++c)
+    for (int c = 0; c < MCU; ++c)
       if (c < w.nch) Mrow[c] = dot6(f, cdof + 6 * w.chain[c]);
     Mrow[0] += m.dof_armature[d];
     float* Mb = SM(Mb);
 #pragma unroll
-    for (int c = 0; c < MC; ++c)
+    for (int c = 0; c < MCU; ++c)
       if (c < w.nch) Mb[d * MC + c] = Mrow[c];
-    float bias = dot6(cdof + 6 * d, cfrc + 6 * bi);
+    float bias = dot6(cdof + 6 * d, SM(cfs) + 6 * bi);
     float act = 0.f;
     int a = M.dof_actuator[d];
     if (a >= 0) {
@@ -1100,15 +1113,15 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   const float mywarm = isdof ? warm[d] : 0.f;
   float g = S.qfs;
 #pragma unroll
-  for (int c = 0; c < MC; ++c) R[c] = Mrow[c];
+  for (int c = 0; c < MCU; ++c) R[c] = Mrow[c];
   int phase = 0, it = 0;
   while (true) {
-    float x = tree_solve<NL, NR>(w, R, g);
+    float x = tree_solve<NL, NR, MCU>(w, R, g);
     if (phase == 0) {
       S.qas = x;
       if (M.nedge == 0 && M.nlimited == 0) { S.qacc = x; break; }
       // warm start: whichever of qacc_warmstart / qacc_smooth has the lower cost
-      float Maw = mul_M(w, Mrow, mywarm);
+      float Maw = mul_M<MCU>(w, Mrow, mywarm);
       float eJw = mul_J(w, mywarm) - S.e_aref;
       float lJw = S.l_sign * mywarm - S.l_aref;
       float gw = (Maw - S.qfs) * (mywarm - S.qas);
@@ -1127,7 +1140,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
       S.prev_cost = 0.f;
     } else {
       S.search = -x;
-      linesearch(w, S, Mrow);
+      linesearch<MCU>(w, S, Mrow);
       ++it;
     }
     update_constraint(w, S);
@@ -1140,7 +1153,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
     }
     if (done) break;
     phase = 1;
-    build_H(w, S, Mrow, R);
+    build_H<MCU>(w, S, Mrow, R);
     g = S.grad;
   }
   const float qacc = S.qacc;

@@ -68,6 +68,20 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
       if (m.body_parentid[c] == b && b > 0) D.child_ids[nchild++] = c;
     D.child_num[b] = nchild - D.child_adr[b];
   }
+  for (int b = 1; b < nb; ++b) {
+    int nd = 0;
+    for (int c = b + 1; c < nb; ++c) {
+      int a = c;
+      while (a > 0 && a != b) a = m.body_parentid[a];
+      if (a == b) ++nd;
+    }
+    D.body_ndesc[b] = nd;
+    for (int c = b + 1; c <= b + nd; ++c) {
+      int a = c;
+      while (a > 0 && a != b) a = m.body_parentid[a];
+      if (a != b) { err = "bodies are not in depth-first order"; return false; }
+    }
+  }
   D.nroot = 0;
   for (int b = 1; b < nb; ++b) {
     int r = m.body_rootid[b], idx = -1;
@@ -164,7 +178,7 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   D.o_Mb = take(nv * DIAL_MAXCHAIN); D.o_L = take(nv * DIAL_MAXCHAIN); D.o_J = take(D.nedge * DIAL_MAXCHAIN);
   D.o_qpos = take(m.nq); D.o_qvel = take(nv); D.o_warm = take(nv); D.o_ctrl = take(m.nu);
   D.o_vec = take(32); D.o_frow = take(32); D.o_cpos = take(3 * m.ncon); D.o_cframe = take(9 * m.ncon);
-  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = take(nv * DIAL_MAXCHAIN); D.o_site = take(3 * m.nsite);
+  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = take(nv * DIAL_MAXCHAIN); D.o_site = take(3 * m.nsite); D.o_crb = take(10 * nb); D.o_cfs = take(6 * nb);
   D.o_misc = take(8);
   D.warp_floats = o;
   return true;
@@ -173,7 +187,9 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
 // which solver instantiation fits the model: 1 = star<3,6>, 2 = star<5,7>, 0 = generic tree
 static inline int star_variant(const DevModel& D) {
   if (D.star_nchain >= 1 && D.star_nchain <= 4) {
-    if (D.star_nroot == 6 && D.star_maxlen <= 3) return 1;
+    int maxchain = 0;
+    for (int i = 0; i < D.m.nv; ++i) maxchain = D.dof_nchain[i] > maxchain ? D.dof_nchain[i] : maxchain;
+    if (D.star_nroot == 6 && D.star_maxlen <= 3 && maxchain <= 9) return 1;
     if (D.star_nroot == 7 && D.star_maxlen <= 5) return 2;
   }
   return 0;
