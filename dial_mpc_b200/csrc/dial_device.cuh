@@ -92,7 +92,7 @@ struct RolloutArgs {
   int32_t nrows;        // sample rows rolled by this launch
   int32_t H;            // env steps per row
   int32_t mode;         // 0: explicit us; 1: planner (Y0s from eps / key); 2: forward only (pipeline_init)
-  int32_t lockstep;     // 1: warps of a CTA re-converge at every env step (shared instruction fetch)
+  int32_t lockstep;     // >=1: warps of a CTA re-converge at every env step (shared instruction fetch); 2: and before the Newton loop
   int32_t step0, stage0;
   const float* qpos0;
   const float* qvel0;
@@ -268,6 +268,7 @@ struct WarpCtx {
   int ndesc;           // descendant dofs (they follow the dof contiguously, DFS order)
   int mylevel;         // elimination level of the dof (leaves = 0), -1 for non-dof lanes
   int parent;          // parent dof or -1
+  int midsync;         // lock-step CTAs: extra CTA barrier before the Newton loop
   int chain[DIAL_MAXCHAIN];
 };
 
@@ -1109,6 +1110,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   // ---- 9. qacc_smooth and the Newton solve (mjx solver.solve), one factor/solve site ------
   //   pass 0: R = M, g = qfrc_smooth            -> qacc_smooth, warm-start choice, ctx init
   //   pass n: R = H(active set), g = grad        -> search = -H^-1 grad, line search
+  if (w.midsync) cta_sync();
   const float scale = m.meaninertia * (float)(nv > 1 ? nv : 1);
   const float mywarm = isdof ? warm[d] : 0.f;
   float g = S.qfs;
@@ -1294,6 +1296,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
                       int row, int lane) {
   WarpCtx w;
   w.M = Mp; w.P = Pp; w.s = slab; w.lane = lane;
+  w.midsync = A.lockstep >= 2;
   const DevModel& M = *Mp;
   const dial_model_desc& m = M.m;
   const dial_plan_desc& c = Pp->c;

@@ -187,3 +187,34 @@ def test_error_paths(built):
     from dial_mpc_b200.plan import Plan
     with pytest.raises(RuntimeError, match="unknown env_id"):
         Plan(env, d)
+
+
+def test_generic_tree_solver_fallback(built):
+    """The level-scheduled compact Cholesky (used for trees that are not 'root chain + hanging
+    chains') must agree with the star solve: run the golden case with the fallback forced."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.getcwd())
+from tests.conftest import make_pair
+from tests.test_gpu_parity import _state_from, GOLD
+from dial_mpc_b200 import random as drandom
+from dial_mpc_b200.core.dial_config import DialConfig
+from dial_mpc_b200.core.dial_core import MBDPI
+for name, hdf in (("unitree_go2_walk", 0.9), ("unitree_h1_walk", 1.0)):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    env, _ = make_pair(name)
+    mb = MBDPI(DialConfig(env_name=name, Nsample=int(g["N"]), Hsample=int(g["Hs"]), Hnode=int(g["Hn"]),
+                          temp_sample=float(g["temp"]), horizon_diffuse_factor=hdf), env)
+    st = _state_from(env, g["qpos"], g["qvel"], g["qacc_warmstart"], g["step"], g["stage"])
+    _, Y, info = mb.reverse_once(st, drandom.PRNGKey(0), g["Ybar0"], g["noise_scale"], eps=g["eps"])
+    r = info["rews"].cpu().numpy()
+    assert (np.abs(r - g["rews"]) < 1e-3 * (1 + np.abs(g["rews"]))).all(), np.abs(r - g["rews"]).max()
+    assert np.abs(Y.cpu().numpy() - g["Ybar"]).max() < 1e-2
+print("GENERIC_OK")
+'''
+    env = dict(os.environ, DIAL_FORCE_GENERIC_TREE="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+    assert "GENERIC_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
