@@ -59,7 +59,6 @@ struct alignas(16) DevModel {
   int32_t nroot, root_body[4];
   float root_invmass[4];
   int32_t body_rootidx[DIAL_MAXB];
-  int32_t child_adr[DIAL_MAXB], child_num[DIAL_MAXB], child_ids[DIAL_MAXB];
   int32_t body_ndesc[DIAL_MAXB];      // descendant bodies (contiguous after b: depth-first order)
   int32_t dof_level[DIAL_MAXV], nlevel;
   int32_t level_adr[DIAL_MAXLEVEL + 1], level_dofs[DIAL_MAXV];
@@ -78,7 +77,7 @@ struct alignas(16) DevModel {
   // per-warp shared-memory layout (float offsets)
   int32_t o_xpos, o_xquat, o_xmat, o_xipos, o_cinert, o_cdof, o_cdofdot, o_cvel, o_cacc,
       o_cfrc, o_Mb, o_L, o_J, o_qpos, o_qvel, o_warm, o_ctrl, o_vec, o_frow, o_cpos,
-      o_cframe, o_cdist, o_rcom, o_xch, o_site, o_crb, o_cfs, o_misc, warp_floats;
+      o_cframe, o_cdist, o_rcom, o_xch, o_crb, o_cfs, warp_floats;
   int32_t pad_[3];
 };
 

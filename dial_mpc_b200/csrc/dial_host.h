@@ -61,13 +61,6 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   // depth / children / roots
   D.maxdepth = 0;
   for (int b = 1; b < nb; ++b) D.maxdepth = m.body_depth[b] > D.maxdepth ? m.body_depth[b] : D.maxdepth;
-  int nchild = 0;
-  for (int b = 0; b < nb; ++b) {
-    D.child_adr[b] = nchild;
-    for (int c = 1; c < nb; ++c)
-      if (m.body_parentid[c] == b && b > 0) D.child_ids[nchild++] = c;
-    D.child_num[b] = nchild - D.child_adr[b];
-  }
   for (int b = 1; b < nb; ++b) {
     int nd = 0;
     for (int c = b + 1; c < nb; ++c) {
@@ -178,8 +171,7 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   D.o_Mb = take(nv * DIAL_MAXCHAIN); D.o_L = take(nv * DIAL_MAXCHAIN); D.o_J = take(D.nedge * DIAL_MAXCHAIN);
   D.o_qpos = take(m.nq); D.o_qvel = take(nv); D.o_warm = take(nv); D.o_ctrl = take(m.nu);
   D.o_vec = take(32); D.o_frow = take(32); D.o_cpos = take(3 * m.ncon); D.o_cframe = take(9 * m.ncon);
-  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = take(nv * DIAL_MAXCHAIN); D.o_site = take(3 * m.nsite); D.o_crb = take(10 * nb); D.o_cfs = take(6 * nb);
-  D.o_misc = take(8);
+  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = take(nv * DIAL_MAXCHAIN); D.o_crb = take(10 * nb); D.o_cfs = take(6 * nb);
   D.warp_floats = o;
   return true;
 }

@@ -246,7 +246,6 @@ struct dial_plan {
   DevPlan hP;
   DevModel* dM = nullptr;
   DevPlan* dP = nullptr;
-  int wpc = 4;
   int variant = 0;
   int num_sms = 148;
   size_t smem_bytes = 0;

@@ -40,11 +40,3 @@ extern "C" int emul_rollout(const dial_model_desc* m, const dial_plan_desc* c, i
   return 0;
 }
 
-extern "C" int emul_layout(const dial_model_desc* m, int* out /*[32]*/) {
-  static DevModel D;
-  std::string err;
-  if (!derive_model(*m, D, err)) return -1;
-  const int32_t* o = &D.o_xpos;
-  for (int i = 0; i < 27; ++i) out[i] = o[i];
-  return 0;
-}
