@@ -66,7 +66,7 @@ dial_model_desc = _mk("dial_model_desc")
 dial_plan_desc = _mk("dial_plan_desc")
 dial_state = _mk("dial_state")
 
-ENV_IDS = {"unitree_go2_walk": 0, "unitree_go2_seq_jump": 1, "unitree_h1_walk": 2}
+ENV_IDS = {"unitree_go2_walk": 0, "unitree_go2_seq_jump": 1, "unitree_h1_walk": 2, "allegro_reorient": 3}
 
 
 def _set(field, value):
@@ -98,12 +98,13 @@ def fill_model_desc(cm) -> dial_model_desc:
               "jnt_margin", "jnt_solref", "jnt_solimp",
               "dof_bodyid", "dof_jntid", "dof_parentid", "dof_armature", "dof_damping", "dof_invweight0",
               "qpos0", "geom_type", "geom_bodyid", "geom_pos", "geom_quat", "geom_size",
-              "pair_kind", "pair_geom1", "pair_geom2", "pair_ncon", "pair_friction", "pair_margin",
+              "pair_kind", "pair_geom1", "pair_geom2", "pair_ncon", "pair_condim", "pair_friction", "pair_margin",
               "pair_gap", "pair_solref", "pair_solimp", "site_bodyid", "site_pos",
               "actuator_dofadr", "actuator_qposadr", "actuator_ctrllimited", "actuator_forcelimited",
               "actuator_gear", "actuator_gain", "actuator_bias", "actuator_ctrlrange", "actuator_forcerange"):
         _set(getattr(d, k), A[k])
     _set(d.body_invweight0, A["body_invweight0"][:, 0])
+    _set(d.body_invweight0_rot, A["body_invweight0"][:, 1])
     return d
 
 

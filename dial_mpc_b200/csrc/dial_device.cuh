@@ -47,7 +47,7 @@ DEV void cta_sync() { __syncthreads(); }
 #define DIAL_MAXIMP 0.9999f
 
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
-enum { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1 };
+enum { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_SPHERE_SPHERE = 2, PAIR_SPHERE_CAPSULE = 3, PAIR_CAPSULE_CAPSULE = 4 };
 
 // ---------------------------------------------------------------------------------
 // device-side model: the C-ABI descriptor + host-derived schedules + smem offsets
@@ -67,6 +67,8 @@ struct alignas(16) DevModel {
   int32_t dof_actuator[DIAL_MAXV];    // actuator driving the dof or -1
   int32_t dof_limited[DIAL_MAXV];     // joint id if the dof's joint is limited else -1
   int32_t con_pair[DIAL_MAXC], con_sub[DIAL_MAXC];
+  int32_t dense;                      // 1: dense / elliptic solver path (NL < 0)
+  int32_t con_row0[DIAL_MAXC], con_dim[DIAL_MAXC], nrow_c;
   int32_t con_lastdof[DIAL_MAXC];     // deepest dof moving the contact's body (geom1 must be static)
   int32_t dof_nchain[DIAL_MAXV], dof_ndesc[DIAL_MAXV], nlimited;
   int32_t chain_tab[DIAL_MAXV][DIAL_MAXCHAIN];
@@ -77,7 +79,7 @@ struct alignas(16) DevModel {
   // per-warp shared-memory layout (float offsets)
   int32_t o_xpos, o_xquat, o_xmat, o_xipos, o_cinert, o_cdof, o_cdofdot, o_cvel, o_cacc,
       o_cfrc, o_Mb, o_L, o_J, o_qpos, o_qvel, o_warm, o_ctrl, o_vec, o_frow, o_cpos,
-      o_cframe, o_cdist, o_rcom, o_xch, o_crb, o_cfs, warp_floats;
+      o_cframe, o_cdist, o_rcom, o_xch, o_crb, o_cfs, o_Md, o_Ld, o_Jd, o_Gd, o_frow2, o_cact, warp_floats;
   int32_t pad_[3];
 };
 
@@ -620,6 +622,7 @@ struct Solver {
   float l_sign, l_D, l_aref, l_Jaref;      // limit row (lane = dof)
   float e_D, e_aref, e_Jaref;              // contact edge row (lane = edge)
   float gauss, cost, prev_cost, gradnorm2; // warp-uniform scalars
+  float qfc;                               // qfrc_constraint (dense path, for eulerdamp)
 };
 
 // efc_force, qfrc_constraint, costs and the gradient (solver.py _update_constraint + grad)
@@ -753,6 +756,611 @@ DEV void linesearch(WarpCtx& w, Solver& S, const float* Mrow) {
   S.e_Jaref += alpha * e_jv;
 }
 
+
+// ---------------------------------------------------------------------------------
+// Dense / elliptic-cone solver path (NL < 0): models whose contacts couple two moving bodies
+// or use elliptic friction cones (allegro_reorient: 19 contacts, condim 3/6, nv = 22).  H is no
+// longer tree-sparse, so M, H and the contact Jacobian are dense in shared memory:
+//   lane d (< nv)   : dof vectors + the limit row of dof d, row d of M / H / the Cholesky factor
+//   lane c (< ncon) : the contact's rows (<= 6: normal, 2 tangents, torsion, 2 rolling)
+// Cone cost (MuJoCo primal, restated in oracle/mjx_oracle.py): with N = mu x0, T = |fri o x_1..|
+// top (N >= mu T): 0; bottom (mu N + T <= 0): plain quadratic; middle: 0.5 Dm (N - mu T)^2.
+// ---------------------------------------------------------------------------------
+struct ConeLane {
+  float x[6], D[6], aref[6], fri[5];
+  float mu, Dm;
+  int dim, r0;
+  bool inst;
+};
+
+DEV void dense_mul_J(WarpCtx& w, const ConeLane& C, float xd, float* out) {
+  const int nv = w.M->m.nv, lane = w.lane;
+  const float* Jd = SM(Jd);
+  float* vec = SM(vec);
+  syncwarp();
+  vec[lane] = xd;
+  syncwarp();
+#pragma unroll
+  for (int i = 0; i < 6; ++i) out[i] = 0.f;
+  if (C.inst) {
+    for (int d = 0; d < nv; ++d) {
+      const float xv = vec[d];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        if (i < C.dim) out[i] += Jd[(C.r0 + i) * nv + d] * xv;
+    }
+  }
+}
+
+// rows of G (same shape as J) times ... J^T f: contact lanes publish f, dof lanes gather
+DEV float dense_mul_JT(WarpCtx& w, const ConeLane& C, const float* f) {
+  const DevModel& M = *w.M;
+  const int nv = M.m.nv, lane = w.lane;
+  const float* Jd = SM(Jd);
+  float* fr = SM(frow2);
+  const int* cact = reinterpret_cast<const int*>(SM(cact));
+  syncwarp();
+  if (lane < M.m.ncon) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i < C.dim) fr[C.r0 + i] = f[i];
+  }
+  syncwarp();
+  float y = 0.f;
+  if (lane < nv) {
+    for (int c = 0; c < M.m.ncon; ++c) {
+      if (!cact[c]) continue;
+      const int r0 = M.con_row0[c], dim = M.con_dim[c];
+      for (int i = 0; i < dim; ++i) y += Jd[(r0 + i) * nv + lane] * fr[r0 + i];
+    }
+  }
+  return y;
+}
+
+// zone: 0 top, 1 middle, 2 bottom.  cost and force of one contact at rows x.
+DEV int cone_eval(const ConeLane& C, const float* x, float& cost, float* force, float& N, float& T) {
+  cost = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) force[i] = 0.f;
+  N = 0.f; T = 0.f;
+  if (!C.inst) return 0;
+  if (C.dim == 1) {   // frictionless: plain inequality row
+    if (x[0] < 0.f) { cost = 0.5f * C.D[0] * x[0] * x[0]; force[0] = -C.D[0] * x[0]; return 2; }
+    return 0;
+  }
+  N = C.mu * x[0];
+  float tt = 0.f;
+#pragma unroll
+  for (int i = 1; i < 6; ++i)
+    if (i < C.dim) { float u = x[i] * C.fri[i - 1]; tt += u * u; }
+  T = sqrtf(tt);
+  const bool bottom = (T <= 0.f && N < 0.f) || (T > 0.f && C.mu * N + T <= 0.f);
+  const bool middle = (T > 0.f) && (N < C.mu * T) && (C.mu * N + T > 0.f);
+  if (bottom) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i < C.dim) { cost += 0.5f * C.D[i] * x[i] * x[i]; force[i] = -C.D[i] * x[i]; }
+    return 2;
+  }
+  if (middle) {
+    const float NmT = N - C.mu * T;
+    const float f0 = -C.Dm * NmT * C.mu;
+    cost = 0.5f * C.Dm * NmT * NmT;
+    force[0] = f0;
+#pragma unroll
+    for (int i = 1; i < 6; ++i)
+      if (i < C.dim) force[i] = -(f0 / T) * (x[i] * C.fri[i - 1]) * C.fri[i - 1];
+    return 1;
+  }
+  return 0;
+}
+
+DEV void dense_update_constraint(WarpCtx& w, Solver& S, const ConeLane& C) {
+  float cc, f[6], N, T;
+  cone_eval(C, C.x, cc, f, N, T);
+  float fl = (S.l_Jaref < 0.f) ? -S.l_D * S.l_Jaref : 0.f;
+  float qfc = dense_mul_JT(w, C, f) + S.l_sign * fl;
+  S.qfc = qfc;
+  S.grad = S.Ma - S.qfs - qfc;
+  float g = (S.Ma - S.qfs) * (S.qacc - S.qas);
+  float c = ((S.l_Jaref < 0.f) ? S.l_D * S.l_Jaref * S.l_Jaref : 0.f) + 2.f * cc;
+  float g2 = S.grad * S.grad;
+  warp_sum3(g, c, g2);
+  S.gauss = 0.5f * g;
+  S.prev_cost = S.cost;
+  S.cost = 0.5f * c + S.gauss;
+  S.gradnorm2 = g2;
+}
+
+// dense Cholesky H = L L^T in SM(Ld) (lane = row) and solve; g / x on the dof lanes
+DEV float dense_factor_solve(WarpCtx& w, float g) {
+  const int nv = w.M->m.nv, lane = w.lane;
+  float* L = SM(Ld);
+  for (int k = 0; k < nv; ++k) {
+    syncwarp();
+    const float d = sqrtf(fmaxf(L[k * nv + k], DIAL_MINVAL));
+    const float inv = 1.f / d;
+    syncwarp();
+    if (lane == k) L[k * nv + k] = d;
+    if (lane > k && lane < nv) L[lane * nv + k] *= inv;
+    syncwarp();
+    if (lane > k && lane < nv) {
+      const float lik = L[lane * nv + k];
+      for (int j = k + 1; j <= lane; ++j) L[lane * nv + j] -= lik * L[j * nv + k];
+    }
+  }
+  syncwarp();
+  float y = g;
+  for (int k = 0; k < nv; ++k) {       // L y = g
+    float yk = shfl(y, k) / L[k * nv + k];
+    if (lane == k) y = yk;
+    if (lane > k && lane < nv) y -= L[lane * nv + k] * yk;
+  }
+  for (int k = nv - 1; k >= 0; --k) {  // L^T x = y
+    float xk = shfl(y, k) / L[k * nv + k];
+    if (lane == k) y = xk;
+    if (lane < k) y -= L[k * nv + lane] * xk;
+  }
+  return y;
+}
+
+// H = Md + J^T G with G = D o J (bottom-zone contacts) or Hc J_c (middle-zone cone Hessian)
+DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C) {
+  const DevModel& M = *w.M;
+  const int nv = M.m.nv, lane = w.lane;
+  const float* Jd = SM(Jd);
+  float* Gd = SM(Gd);
+  float* L = SM(Ld);
+  const float* Md = SM(Md);
+  int* cact = reinterpret_cast<int*>(SM(cact));
+  syncwarp();
+  if (lane < M.m.ncon) {
+    float cc, f[6], N, T;
+    const int zone = cone_eval(C, C.x, cc, f, N, T);
+    cact[lane] = C.inst ? (zone != 0 ? 2 : 1) : 0;   // 2: contributes to H
+    if (zone == 2) {
+      for (int d = 0; d < nv; ++d)
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+          if (i < C.dim) Gd[(C.r0 + i) * nv + d] = C.D[i] * Jd[(C.r0 + i) * nv + d];
+    } else if (zone == 1) {
+      // analytic Hessian of 0.5 Dm mu^2 (x0 - T)^2, y_i = fri_i x_i, s = x0 - T
+      float Hc[6][6];
+      const float sc = C.Dm * C.mu * C.mu, s = C.x[0] - T, iT = 1.f / T;
+      float y[6];
+#pragma unroll
+      for (int i = 1; i < 6; ++i) y[i] = (i < C.dim) ? C.x[i] * C.fri[i - 1] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Hc[i][j] = 0.f;
+      Hc[0][0] = sc;
+#pragma unroll
+      for (int i = 1; i < 6; ++i) {
+        if (i < C.dim) {
+          Hc[0][i] = Hc[i][0] = -sc * C.fri[i - 1] * y[i] * iT;
+#pragma unroll
+          for (int j = 1; j < 6; ++j)
+            if (j < C.dim)
+              Hc[i][j] = sc * C.fri[i - 1] * C.fri[j - 1] * (y[i] * y[j] * iT * iT * (1.f + s * iT) - (i == j ? s * iT : 0.f));
+        }
+      }
+      for (int d = 0; d < nv; ++d) {
+        float jc[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) jc[i] = (i < C.dim) ? Jd[(C.r0 + i) * nv + d] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          if (i < C.dim) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) a += Hc[i][j] * jc[j];
+            Gd[(C.r0 + i) * nv + d] = a;
+          }
+        }
+      }
+    }
+  }
+  syncwarp();
+  if (lane < nv) {
+    for (int j = 0; j <= lane; ++j) L[lane * nv + j] = Md[lane * nv + j];
+    L[lane * nv + lane] += (S.l_Jaref < 0.f) ? S.l_D : 0.f;
+    for (int c = 0; c < M.m.ncon; ++c) {
+      if (cact[c] != 2) continue;
+      const int r0 = M.con_row0[c], dim = M.con_dim[c];
+      for (int i = 0; i < dim; ++i) {
+        const float a = Jd[(r0 + i) * nv + lane];
+        const float* Gr = Gd + (r0 + i) * nv;
+        for (int j = 0; j <= lane; ++j) L[lane * nv + j] += a * Gr[j];
+      }
+    }
+  }
+  syncwarp();
+}
+
+// dense M x (lane = dof)
+DEV float dense_mul_M(WarpCtx& w, float x) {
+  const int nv = w.M->m.nv, lane = w.lane;
+  const float* Md = SM(Md);
+  float* vec = SM(vec);
+  syncwarp();
+  vec[lane] = x;
+  syncwarp();
+  float y = 0.f;
+  if (lane < nv)
+    for (int j = 0; j < nv; ++j) y += Md[(j <= lane ? lane * nv + j : j * nv + lane)] * vec[j];
+  return y;
+}
+
+// line-search point: cost and derivatives at up to NA alphas (limit rows + cones)
+template <int NA>
+DEV void dense_ls_points(const Solver& S, const ConeLane& C, float l_jv, const float* cv, const float* qg,
+                         const float* al, LSPoint* out) {
+  float s[3 * NA];
+#pragma unroll
+  for (int i = 0; i < 3 * NA; ++i) s[i] = 0.f;
+  {
+    const float q0 = 0.5f * S.l_Jaref * S.l_Jaref * S.l_D, q1 = l_jv * S.l_Jaref * S.l_D, q2 = 0.5f * l_jv * l_jv * S.l_D;
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+      if (S.l_Jaref + al[i] * l_jv < 0.f) {
+        s[3 * i] += al[i] * al[i] * q2 + al[i] * q1 + q0;
+        s[3 * i + 1] += 2.f * al[i] * q2 + q1;
+        s[3 * i + 2] += 2.f * q2;
+      }
+  }
+  if (C.inst) {
+    float Q0 = 0.f, Q1 = 0.f, Q2 = 0.f, UU = 0.f, UV = 0.f, VV = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i < C.dim) {
+        Q0 += 0.5f * C.x[i] * C.x[i] * C.D[i]; Q1 += cv[i] * C.x[i] * C.D[i]; Q2 += 0.5f * cv[i] * cv[i] * C.D[i];
+        if (i > 0) {
+          const float f2 = C.fri[i - 1] * C.fri[i - 1];
+          UU += C.x[i] * C.x[i] * f2; UV += C.x[i] * cv[i] * f2; VV += cv[i] * cv[i] * f2;
+        }
+      }
+    }
+    const float U0 = C.mu * C.x[0], V0 = C.mu * cv[0];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const float a = al[i];
+      if (C.dim == 1) {
+        if (C.x[0] + a * cv[0] < 0.f) { s[3 * i] += a * a * Q2 + a * Q1 + Q0; s[3 * i + 1] += 2.f * a * Q2 + Q1; s[3 * i + 2] += 2.f * Q2; }
+        continue;
+      }
+      const float N = U0 + a * V0;
+      const float Tsq = UU + a * (2.f * UV + a * VV);
+      const float T = sqrtf(fmaxf(Tsq, 0.f));
+      const bool bottom = (Tsq <= 0.f && N < 0.f) || (Tsq > 0.f && C.mu * N + T <= 0.f);
+      const bool middle = (Tsq > 0.f) && (N < C.mu * T) && (C.mu * N + T > 0.f);
+      if (bottom) {
+        s[3 * i] += a * a * Q2 + a * Q1 + Q0; s[3 * i + 1] += 2.f * a * Q2 + Q1; s[3 * i + 2] += 2.f * Q2;
+      } else if (middle) {
+        const float T1 = (UV + a * VV) / T;
+        const float T2 = VV / T - (UV + a * VV) * T1 / Tsq;
+        const float NmT = N - C.mu * T, dN = V0 - C.mu * T1;
+        s[3 * i] += 0.5f * C.Dm * NmT * NmT;
+        s[3 * i + 1] += C.Dm * NmT * dN;
+        s[3 * i + 2] += C.Dm * (dN * dN + NmT * (-C.mu * T2));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 3 * NA; ++i) s[i] += shfl_xor(s[i], o);
+  }
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const float a = al[i];
+    out[i].alpha = a;
+    out[i].cost = a * a * qg[2] + a * qg[1] + qg[0] + s[3 * i];
+    out[i].d0 = 2.f * a * qg[2] + qg[1] + s[3 * i + 1];
+    const float d1 = 2.f * qg[2] + s[3 * i + 2];
+    out[i].d1 = d1 + (d1 == 0.f ? DIAL_MINVAL : 0.f);
+  }
+}
+
+DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
+  const DevModel& M = *w.M;
+  const int nv = M.m.nv;
+  const float scale = M.m.meaninertia * (float)(nv > 1 ? nv : 1);
+  float mv = dense_mul_M(w, S.search);
+  float cv[6];
+  dense_mul_J(w, C, S.search, cv);
+  float l_jv = S.l_sign * S.search;
+  float ss = S.search * S.search, sMa = S.search * (S.Ma - S.qfs), sMv = S.search * mv;
+  warp_sum3(ss, sMa, sMv);
+  float gtol = M.m.tolerance * M.m.ls_tolerance * sqrtf(ss) * scale;
+  float qg[3] = {S.gauss, sMa, 0.5f * sMv};
+  LSPoint p0, lo, hi;
+  float a1[1] = {0.f};
+  dense_ls_points<1>(S, C, l_jv, cv, qg, a1, &p0);
+  a1[0] = p0.alpha - p0.d0 / p0.d1;
+  dense_ls_points<1>(S, C, l_jv, cv, qg, a1, &lo);
+  if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+  bool swap = true;
+  for (int it = 0; it < M.m.ls_iterations; ++it) {
+    bool done = !swap;
+    done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
+    done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
+    if (done) break;
+    LSPoint pt[3];
+    float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+    dense_ls_points<3>(S, C, l_jv, cv, qg, a3, pt);
+    const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
+    bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
+    if (swap_lo_next) lo = lo_next;
+    bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
+    if (swap_lo_mid) lo = mid;
+    bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
+    if (swap_hi_next) hi = hi_next;
+    bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
+    if (swap_hi_mid) hi = mid;
+    swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+  }
+  bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+  float alpha = (lo.cost < hi.cost) ? lo.alpha : hi.alpha;
+  if (!improved) alpha = 0.f;
+  S.qacc += alpha * S.search;
+  S.Ma += alpha * mv;
+  S.l_Jaref += alpha * l_jv;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) C.x[i] += alpha * cv[i];
+}
+
+// sections 8-9 of the physics step for the dense path; returns qacc, leaves S.qfc
+DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float myqvel) {
+  const DevModel& M = *w.M;
+  const dial_model_desc& m = M.m;
+  const int lane = w.lane, nv = m.nv, d = lane;
+  const bool isdof = d < nv;
+  float* Jd = SM(Jd);
+  float* Md = SM(Md);
+  float* L = SM(Ld);
+  const float* cdof = SM(cdof);
+  const float* rcom = SM(rcom);
+  const float* cdist = SM(cdist);
+  const float* cpos = SM(cpos);
+  const float* cframe = SM(cframe);
+  const float* qpos = SM(qpos);
+  int* cact = reinterpret_cast<int*>(SM(cact));
+  // dense M (lower triangle) from the compact rows
+  if (isdof) {
+    for (int j = 0; j <= d; ++j) Md[d * nv + j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < MC; ++c)
+      if (c < w.nch) Md[d * nv + w.chain[c]] = Mrow[c];
+  }
+  // contact rows: Jacobian columns (lane = dof), frame @ (jac(b2) - jac(b1))
+  if (lane < m.ncon) {
+    const int k = M.con_pair[lane];
+    cact[lane] = (cdist[lane] - (m.pair_margin[k] - m.pair_gap[k]) < 0.f) ? 1 : 0;
+  }
+  syncwarp();
+  if (isdof) {
+    V3 ca_ = ld3(cdof + 6 * d), cl_ = ld3(cdof + 6 * d + 3);
+    V3 rc = ld3(rcom + 3 * M.body_rootidx[m.dof_bodyid[d]]);
+    for (int c = 0; c < m.ncon; ++c) {
+      if (!cact[c]) continue;
+      const int k = M.con_pair[c];
+      const int b1 = m.geom_bodyid[m.pair_geom1[k]], b2 = m.geom_bodyid[m.pair_geom2[k]];
+      const float sgn = (float)((M.body_dofmask[b2] >> d) & 1u) - (float)((M.body_dofmask[b1] >> d) & 1u);
+      const int r0 = M.con_row0[c], dim = M.con_dim[c];
+      V3 jp = (cl_ + cross(ca_, ld3(cpos + 3 * c) - rc)) * sgn, jr = ca_ * sgn;
+      for (int i = 0; i < dim; ++i) {
+        V3 fr = ld3(cframe + 9 * c + 3 * (i % 3));
+        Jd[(r0 + i) * nv + d] = dot(fr, i < 3 ? jp : jr);
+      }
+    }
+    // joint-limit row of this dof
+    int lj = M.dof_limited[d];
+    if (lj >= 0) {
+      float qv = qpos[m.jnt_qposadr[lj]];
+      float dmin = qv - m.jnt_range[lj][0], dmax = m.jnt_range[lj][1] - qv;
+      float pos = fminf(dmin, dmax) - m.jnt_margin[lj];
+      if (pos < 0.f) {
+        float sign = dmin < dmax ? 1.f : -1.f;
+        float k_, b_, imp;
+        kbi(m.timestep, m.jnt_solref[lj], m.jnt_solimp[lj], pos, k_, b_, imp);
+        float Rr = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, DIAL_MINVAL);
+        S.l_sign = sign;
+        S.l_D = 1.f / Rr;
+        S.l_aref = -b_ * (sign * myqvel) - k_ * imp * pos;
+      }
+    }
+  }
+  // per-contact row data (lane = contact)
+  ConeLane C;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { C.x[i] = 0.f; C.D[i] = 0.f; C.aref[i] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) C.fri[i] = 0.f;
+  C.mu = 0.f; C.Dm = 0.f; C.dim = 0; C.r0 = 0; C.inst = false;
+  if (lane < m.ncon) {
+    C.dim = M.con_dim[lane]; C.r0 = M.con_row0[lane];
+    C.inst = cact[lane] != 0;
+  }
+  float jq[6];
+  dense_mul_J(w, C, myqvel, jq);
+  if (C.inst) {
+    const int k = M.con_pair[lane];
+    const int b1 = m.geom_bodyid[m.pair_geom1[k]], b2 = m.geom_bodyid[m.pair_geom2[k]];
+    const float pos = cdist[lane] - (m.pair_margin[k] - m.pair_gap[k]);
+    const float t = m.body_invweight0[b1] + m.body_invweight0[b2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) C.fri[i] = m.pair_friction[k][i];
+    float k_, b_, imp;
+    kbi(m.timestep, m.pair_solref[k], m.pair_solimp[k], pos, k_, b_, imp);
+    const float Rn = fmaxf(t * (1.f - imp) / imp, DIAL_MINVAL);
+    C.D[0] = 1.f / Rn;
+    C.aref[0] = -b_ * jq[0] - k_ * imp * pos;
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+      if (i < C.dim) {
+        const float Ri = fmaxf(Rn / m.impratio * C.fri[0] * C.fri[0] / (C.fri[i - 1] * C.fri[i - 1]), DIAL_MINVAL);
+        C.D[i] = 1.f / Ri;
+        C.aref[i] = -b_ * jq[i];
+      }
+    }
+    C.mu = C.fri[0] * rsqrtf(m.impratio);
+    C.Dm = C.D[0] / fmaxf(C.mu * C.mu * (1.f + C.mu * C.mu), DIAL_MINVAL);
+  }
+
+  // ---- qacc_smooth, warm-start choice, Newton iterations (solver.solve) ------------------------
+  const float scale = m.meaninertia * (float)(nv > 1 ? nv : 1);
+  const float mywarm = isdof ? SM(warm)[d] : 0.f;
+  syncwarp();
+  if (isdof)
+    for (int j = 0; j <= d; ++j) L[d * nv + j] = Md[d * nv + j];
+  S.qas = dense_factor_solve(w, S.qfs);
+  {
+    float xw[6], xs[6], cw, cs, f[6], N, T;
+    float Maw = dense_mul_M(w, mywarm);
+    dense_mul_J(w, C, mywarm, xw);
+    dense_mul_J(w, C, S.qas, xs);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { xw[i] -= C.aref[i]; xs[i] -= C.aref[i]; }
+    cone_eval(C, xw, cw, f, N, T);
+    cone_eval(C, xs, cs, f, N, T);
+    float lJw = S.l_sign * mywarm - S.l_aref, lJs = S.l_sign * S.qas - S.l_aref;
+    float gw = (Maw - S.qfs) * (mywarm - S.qas);
+    float tw = ((lJw < 0.f) ? S.l_D * lJw * lJw : 0.f) + 2.f * cw;
+    float ts = ((lJs < 0.f) ? S.l_D * lJs * lJs : 0.f) + 2.f * cs;
+    warp_sum3(gw, tw, ts);
+    const bool usewarm = (0.5f * tw + 0.5f * gw) < (0.5f * ts);
+    S.qacc = usewarm ? mywarm : S.qas;
+    S.Ma = usewarm ? Maw : S.qfs;
+    S.l_Jaref = usewarm ? lJw : lJs;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) C.x[i] = usewarm ? xw[i] : xs[i];
+    S.cost = INFINITY;
+    S.prev_cost = 0.f;
+  }
+  int it = 0;
+  while (true) {
+    dense_update_constraint(w, S, C);
+    bool done = it >= m.iterations;
+    if (m.iterations != 1 || it > 0) {
+      float improvement = (S.prev_cost - S.cost) / scale;
+      float gradient = sqrtf(S.gradnorm2) / scale;
+      if (m.iterations != 1) done = done || (improvement < m.tolerance) || (gradient < m.tolerance);
+    }
+    if (done) break;
+    dense_build_H(w, S, C);
+    S.search = -dense_factor_solve(w, S.grad);
+    dense_linesearch(w, S, C);
+    ++it;
+  }
+  return S.qacc;
+}
+
+// ---------------------------------------------------------------------------------
+// collision (lane = contact): MJX collision_primitive plane-sphere, plane-capsule (2 contacts),
+// sphere-sphere, sphere-capsule, capsule-capsule; fixed-size contact arrays.
+// ---------------------------------------------------------------------------------
+DEV V3 mat_z(const float* X, const float* q) {   // z axis of  X * quat_to_mat(q)
+  float Rg[9];
+  qmat(ldq(q), Rg);
+  return v3(X[0] * Rg[2] + X[1] * Rg[5] + X[2] * Rg[8], X[3] * Rg[2] + X[4] * Rg[5] + X[5] * Rg[8],
+            X[6] * Rg[2] + X[7] * Rg[5] + X[8] * Rg[8]);
+}
+DEV V3 mat_apply(const float* X, const float* p) {
+  return v3(X[0] * p[0] + X[1] * p[1] + X[2] * p[2], X[3] * p[0] + X[4] * p[1] + X[5] * p[2],
+            X[6] * p[0] + X[7] * p[1] + X[8] * p[2]);
+}
+DEV V3 vnormalize(V3 a, float& n) {
+  n = sqrtf(dot(a, a));
+  return a * (1.f / (n + 1e-6f * (n == 0.f ? 1.f : 0.f)));
+}
+DEV V3 closest_segment_point(V3 a, V3 b, V3 pt) {
+  V3 ab = b - a;
+  float t = dot(pt - a, ab) / (dot(ab, ab) + 1e-6f);
+  return a + ab * fminf(fmaxf(t, 0.f), 1.f);
+}
+DEV void closest_segment_to_segment(V3 a0, V3 a1, V3 b0, V3 b1, V3& pa, V3& pb) {
+  float len_a, len_b;
+  V3 dir_a = vnormalize(a1 - a0, len_a), dir_b = vnormalize(b1 - b0, len_b);
+  float ha = 0.5f * len_a, hb = 0.5f * len_b;
+  V3 a_mid = a0 + dir_a * ha, b_mid = b0 + dir_b * hb;
+  V3 trans = a_mid - b_mid;
+  float dd = dot(dir_a, dir_b), dat = dot(dir_a, trans), dbt = dot(dir_b, trans);
+  float denom = 1.f - dd * dd;
+  float ta = (-dat + dd * dbt) / (denom + 1e-6f);
+  float tb = dbt + ta * dd;
+  ta = fminf(fmaxf(ta, -ha), ha);
+  tb = fminf(fmaxf(tb, -hb), hb);
+  V3 best_a = a_mid + dir_a * ta, best_b = b_mid + dir_b * tb;
+  V3 new_a = closest_segment_point(a0, a1, best_b), new_b = closest_segment_point(b0, b1, best_a);
+  V3 e1 = new_a - best_b, e2 = new_b - best_a;
+  if (dot(e1, e1) < dot(e2, e2)) { pa = new_a; pb = best_b; } else { pa = best_a; pb = new_b; }
+}
+DEV V3 frame_tangent(V3 n) {   // second row of mjx math.make_frame(n)
+  V3 alt = (n.y > -0.5f && n.y < 0.5f) ? v3(0, 1, 0) : v3(0, 0, 1);
+  float bn;
+  return vnormalize(alt - n * dot(n, alt), bn);
+}
+
+DEV void collide(WarpCtx& w) {
+  const DevModel& M = *w.M;
+  const dial_model_desc& m = M.m;
+  const int lane = w.lane;
+  if (lane >= m.ncon) return;
+  const float* xpos = SM(xpos);
+  const float* xmat = SM(xmat);
+  const int k = M.con_pair[lane];
+  const int g1 = m.pair_geom1[k], g2 = m.pair_geom2[k];
+  const int b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2];
+  const float* X1 = xmat + 9 * b1;
+  const float* X2 = xmat + 9 * b2;
+  const V3 gp1 = mat_apply(X1, m.geom_pos[g1]) + ld3(xpos + 3 * b1);
+  const V3 gp2 = mat_apply(X2, m.geom_pos[g2]) + ld3(xpos + 3 * b2);
+  const int kind = m.pair_kind[k];
+  V3 n, t1, p;
+  float dist;
+  if (kind == PAIR_PLANE_SPHERE || kind == PAIR_PLANE_CAPSULE) {
+    n = mat_z(X1, m.geom_quat[g1]);
+    const float radius = m.geom_size[g2][0];
+    V3 center = gp2;
+    if (kind == PAIR_PLANE_CAPSULE) {
+      V3 ax = mat_z(X2, m.geom_quat[g2]);
+      float bn;
+      V3 bd = vnormalize(ax - n * dot(n, ax), bn);
+      V3 alt = (n.y > -0.5f && n.y < 0.5f) ? v3(0, 1, 0) : v3(0, 0, 1);
+      t1 = bn < 0.5f ? alt : bd;
+      center = gp2 + ax * ((M.con_sub[lane] == 0 ? 1.f : -1.f) * m.geom_size[g2][1]);
+    } else {
+      t1 = frame_tangent(n);
+    }
+    dist = dot(center - gp1, n) - radius;
+    p = center - n * (radius + 0.5f * dist);
+  } else {
+    V3 q1 = gp1, q2 = gp2;
+    if (kind == PAIR_SPHERE_CAPSULE) {
+      V3 seg = mat_z(X2, m.geom_quat[g2]) * m.geom_size[g2][1];
+      q2 = closest_segment_point(gp2 - seg, gp2 + seg, gp1);
+    } else if (kind == PAIR_CAPSULE_CAPSULE) {
+      V3 s1 = mat_z(X1, m.geom_quat[g1]) * m.geom_size[g1][1];
+      V3 s2 = mat_z(X2, m.geom_quat[g2]) * m.geom_size[g2][1];
+      closest_segment_to_segment(gp1 - s1, gp1 + s1, gp2 - s2, gp2 + s2, q1, q2);
+    }
+    float dn;
+    n = vnormalize(q2 - q1, dn);
+    if (dn == 0.f) n = v3(1, 0, 0);
+    const float r1 = m.geom_size[g1][0], r2 = m.geom_size[g2][0];
+    dist = dn - (r1 + r2);
+    p = q1 + n * (r1 + 0.5f * dist);
+    float nn;
+    n = vnormalize(n, nn);
+    t1 = frame_tangent(n);
+  }
+  SM(cdist)[lane] = dist;
+  st3(SM(cpos) + 3 * lane, p);
+  st3(SM(cframe) + 9 * lane, n);
+  st3(SM(cframe) + 9 * lane + 3, t1);
+  st3(SM(cframe) + 9 * lane + 6, cross(n, t1));
+}
 
 // ---------------------------------------------------------------------------------
 // one physics step (mjx.step) for the warp's sample.  State (qpos,qvel,warm,ctrl) in
@@ -956,57 +1564,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   syncwarp();
 
   // ---- 7. collision (lane = contact) ---------------------------------------------------
-  if (lane < m.ncon) {
-    int k = M.con_pair[lane];
-    int g1 = m.pair_geom1[k], g2 = m.pair_geom2[k];
-    int b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2];
-    // plane (geom1): normal = z axis of its world frame
-    float R1[9], Rg[9];
-    qmat(ldq(m.geom_quat[g1]), Rg);
-    const float* X1 = xmat + 9 * b1;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) R1[3 * r + c] = X1[3 * r] * Rg[c] + X1[3 * r + 1] * Rg[3 + c] + X1[3 * r + 2] * Rg[6 + c];
-    V3 n = v3(R1[2], R1[5], R1[8]);
-    V3 gp1 = v3(X1[0] * m.geom_pos[g1][0] + X1[1] * m.geom_pos[g1][1] + X1[2] * m.geom_pos[g1][2],
-                X1[3] * m.geom_pos[g1][0] + X1[4] * m.geom_pos[g1][1] + X1[5] * m.geom_pos[g1][2],
-                X1[6] * m.geom_pos[g1][0] + X1[7] * m.geom_pos[g1][1] + X1[8] * m.geom_pos[g1][2]) + ld3(xpos + 3 * b1);
-    const float* X2 = xmat + 9 * b2;
-    V3 gp2 = v3(X2[0] * m.geom_pos[g2][0] + X2[1] * m.geom_pos[g2][1] + X2[2] * m.geom_pos[g2][2],
-                X2[3] * m.geom_pos[g2][0] + X2[4] * m.geom_pos[g2][1] + X2[5] * m.geom_pos[g2][2],
-                X2[6] * m.geom_pos[g2][0] + X2[7] * m.geom_pos[g2][1] + X2[8] * m.geom_pos[g2][2]) + ld3(xpos + 3 * b2);
-    float radius = m.geom_size[g2][0];
-    V3 center = gp2;
-    V3 t1;
-    V3 ydir = v3(0, 1, 0), zdir = v3(0, 0, 1);
-    V3 alt = (n.y > -0.5f && n.y < 0.5f) ? ydir : zdir;
-    if (m.pair_kind[k] == PAIR_PLANE_CAPSULE) {
-      float Rg2[9];
-      qmat(ldq(m.geom_quat[g2]), Rg2);
-      V3 ax = v3(X2[0] * Rg2[2] + X2[1] * Rg2[5] + X2[2] * Rg2[8],
-                 X2[3] * Rg2[2] + X2[4] * Rg2[5] + X2[5] * Rg2[8],
-                 X2[6] * Rg2[2] + X2[7] * Rg2[5] + X2[8] * Rg2[8]);
-      V3 bv = ax - n * dot(n, ax);
-      float bn = sqrtf(dot(bv, bv));
-      V3 bd = bv * (1.f / (bn + 1e-6f * (bn == 0.f ? 1.f : 0.f)));
-      t1 = bn < 0.5f ? alt : bd;
-      float sgn = M.con_sub[lane] == 0 ? 1.f : -1.f;
-      center = gp2 + ax * (sgn * m.geom_size[g2][1]);
-    } else {
-      // make_frame(n)
-      V3 bv = alt - n * dot(n, alt);
-      float bn = sqrtf(dot(bv, bv));
-      t1 = bv * (1.f / (bn + 1e-6f * (bn == 0.f ? 1.f : 0.f)));
-    }
-    float dist = dot(center - gp1, n) - radius;
-    V3 p = center - n * (radius + 0.5f * dist);
-    cdist[lane] = dist;
-    st3(cpos + 3 * lane, p);
-    st3(cframe + 9 * lane, n);
-    st3(cframe + 9 * lane + 3, t1);
-    st3(cframe + 9 * lane + 6, cross(n, t1));
-  }
+  collide(w);
   syncwarp();
 
   // ---- 6. compact mass-matrix row, bias, smooth force (lane = dof) ----------------------
@@ -1016,6 +1574,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   S.e_D = 0.f; S.e_aref = 0.f; S.e_Jaref = 0.f;
   S.qacc = S.Ma = S.grad = S.search = 0.f;
   S.gauss = S.cost = S.prev_cost = S.gradnorm2 = 0.f;
+  S.qfc = 0.f;
   const int d = lane;
   const bool isdof = d < nv;
   float myqvel = isdof ? qvel[d] : 0.f;
@@ -1048,6 +1607,21 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
     S.qfs = -m.dof_damping[d] * myqvel - bias + act;
   }
 
+  float qacc, qacc_int;
+  if constexpr (NL < 0) {
+    qacc = dense_constraint_solve(w, S, Mrow, myqvel);
+    qacc_int = qacc;
+    if (m.eulerdamp) {   // implicit joint damping: (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
+      float* Ld_ = SM(Ld);
+      const float* Md_ = SM(Md);
+      syncwarp();
+      if (isdof) {
+        for (int j = 0; j <= d; ++j) Ld_[d * nv + j] = Md_[d * nv + j];
+        Ld_[d * nv + d] += m.timestep * m.dof_damping[d];
+      }
+      qacc_int = dense_factor_solve(w, S.qfs + S.qfc);
+    }
+  } else {
   // ---- 8. constraint rows ----------------------------------------------------------------
   // contact Jacobian, compact along the chain of the contact body's last dof (lane = dof)
   if (isdof) {
@@ -1157,13 +1731,16 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
     build_H<MCU>(w, S, Mrow, R);
     g = S.grad;
   }
-  const float qacc = S.qacc;
+  qacc = S.qacc;
+  qacc_int = qacc;
+
+  }
 
   // ---- 10. semi-implicit Euler -------------------------------------------------------------
   syncwarp();
   if (isdof) {
     warm[d] = qacc;
-    if (integrate) qvel[d] = myqvel + m.timestep * qacc;
+    if (integrate) qvel[d] = myqvel + m.timestep * qacc_int;
   }
   syncwarp();
   if (integrate && isbody && jid >= 0) {
@@ -1229,6 +1806,16 @@ DEV float reward_lane0(WarpCtx& w, int step, int& stage) {
   V3 up = qrot(rot0, v3(0, 0, 1));
   float r_upright = -(up.x * up.x + up.y * up.y + (up.z - 1.f) * (up.z - 1.f));
   BaseKin bk = base_kin(w, c.torso_body);
+  if (c.env_id == DIAL_ENV_ALLEGRO) {
+    // manipulation.py:75-84: ball angular velocity / position tracking + joint deviation
+    const int ob = c.torso_body;
+    V3 wv = ld3(SM(cvel) + 6 * ob) * (3.14159265358979f / 180.f);
+    V3 dw = wv - ld3(c.ang_cmd);
+    V3 dp = ld3(SM(xpos) + 3 * ob) - ld3(c.pos_tar);
+    float rj = 0.f;
+    for (int a = 0; a < m.nu; ++a) { float e = SM(qpos)[7 + a] - c.joint_offset[a]; rj -= e * e; }
+    return -dot(dw, dw) - 5.f * dot(dp, dp) + 0.1f * rj;
+  }
   if (c.env_id == DIAL_ENV_GO2_WALK || c.env_id == DIAL_ENV_H1_WALK) {
     float ramp = stepf * c.dt / c.ramp_up_time;
     float vtx = fminf(c.vel_cmd[0] * ramp, c.vel_cmd[0]), vty = fminf(c.vel_cmd[1] * ramp, c.vel_cmd[1]);
@@ -1372,7 +1959,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
           if (k < Hn1) u += c.M_n2u[t][k] * Y[k];
       }
       float an = (u * c.action_scale + 1.f) * 0.5f;
-      float jt = c.joint_range[lane][0] + an * (c.joint_range[lane][1] - c.joint_range[lane][0]);
+      float jt = c.joint_range[lane][0] + c.joint_offset[lane] + an * (c.joint_range[lane][1] - c.joint_range[lane][0]);
       jt = fminf(fmaxf(jt, c.physical_joint_range[lane][0]), c.physical_joint_range[lane][1]);
       float ctrl = jt;
       if (c.leg_control_torque) {

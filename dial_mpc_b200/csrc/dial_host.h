@@ -49,15 +49,19 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   D.m = m;
   const int nb = m.nbody, nv = m.nv;
   if (nb < 2 || nb > DIAL_MAXB || nv > DIAL_MAXV || m.nq > DIAL_MAXQ || m.nu > DIAL_MAXU ||
-      m.ngeom > DIAL_MAXG || m.npair > DIAL_MAXP || m.ncon > DIAL_MAXC || m.nsite > DIAL_MAXS ||
-      4 * m.ncon > DIAL_MAXE) {
+      m.ngeom > DIAL_MAXG || m.npair > DIAL_MAXP || m.ncon > DIAL_MAXC || m.nsite > DIAL_MAXS) {
     err = "model exceeds the fixed device capacities (DIAL_MAX*)";
     return false;
   }
-  if (m.cone != 0) { err = "elliptic friction cones are not supported by the CUDA path"; return false; }
+  // dense / elliptic path: elliptic cones (contacts may then couple two moving bodies, condim 1/3/6)
+  D.dense = m.cone == 1 ? 1 : 0;
   bool any_damp = false;
   for (int d = 0; d < nv; ++d) any_damp |= m.dof_damping[d] != 0.f;
-  if (m.eulerdamp && any_damp) { err = "implicit Euler damping (eulerdamp) is not supported by the CUDA path"; return false; }
+  if (!D.dense && m.eulerdamp && any_damp) {
+    err = "implicit Euler damping (eulerdamp) is only supported on the dense (elliptic) solver path";
+    return false;
+  }
+  if (!D.dense && 4 * m.ncon > DIAL_MAXE) { err = "too many pyramidal contact edges"; return false; }
   // depth / children / roots
   D.maxdepth = 0;
   for (int b = 1; b < nb; ++b) D.maxdepth = m.body_depth[b] > D.maxdepth ? m.body_depth[b] : D.maxdepth;
@@ -143,25 +147,34 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   }
   int c = 0;
   for (int k = 0; k < m.npair; ++k) {
+    const int b1 = m.geom_bodyid[m.pair_geom1[k]], b2 = m.geom_bodyid[m.pair_geom2[k]];
+    if (D.dense) {
+      if (m.pair_kind[k] < PAIR_PLANE_SPHERE || m.pair_kind[k] > PAIR_CAPSULE_CAPSULE) { err = "unsupported contact pair kind"; return false; }
+      if (m.pair_condim[k] != 1 && m.pair_condim[k] != 3 && m.pair_condim[k] != 6) { err = "condim must be 1, 3 or 6"; return false; }
+      for (int s = 0; s < m.pair_ncon[k]; ++s) {
+        D.con_pair[c] = k; D.con_sub[c] = s; D.con_lastdof[c] = 0;
+        D.con_dim[c] = m.pair_condim[k]; D.con_row0[c] = D.nrow_c; D.nrow_c += m.pair_condim[k];
+        ++c;
+      }
+      continue;
+    }
     if (m.pair_kind[k] != PAIR_PLANE_SPHERE && m.pair_kind[k] != PAIR_PLANE_CAPSULE) {
-      err = "unsupported contact pair kind on the CUDA path";
+      err = "unsupported contact pair kind on the tree (pyramidal) path";
       return false;
     }
-    {
-      int b1 = m.geom_bodyid[m.pair_geom1[k]], b2 = m.geom_bodyid[m.pair_geom2[k]];
-      if (D.body_dofmask[b1] != 0u || D.body_dofmask[b2] == 0u) {
-        err = "contact pairs must be (static geom, moving geom) on the CUDA path";
-        return false;
-      }
-      int last = 0;
-      for (int d = 0; d < nv; ++d) if ((D.body_dofmask[b2] >> d) & 1u) last = d;
-      if (D.dof_ancmask[last] != D.body_dofmask[b2]) { err = "contact body dofs do not form one chain"; return false; }
-      for (int s = 0; s < m.pair_ncon[k]; ++s) { D.con_pair[c] = k; D.con_sub[c] = s; D.con_lastdof[c] = last; ++c; }
+    if (m.pair_condim[k] != 3) { err = "pyramidal contacts must have condim 3"; return false; }
+    if (D.body_dofmask[b1] != 0u || D.body_dofmask[b2] == 0u) {
+      err = "pyramidal contact pairs must be (static geom, moving geom)";
+      return false;
     }
+    int last = 0;
+    for (int d = 0; d < nv; ++d) if ((D.body_dofmask[b2] >> d) & 1u) last = d;
+    if (D.dof_ancmask[last] != D.body_dofmask[b2]) { err = "contact body dofs do not form one chain"; return false; }
+    for (int s = 0; s < m.pair_ncon[k]; ++s) { D.con_pair[c] = k; D.con_sub[c] = s; D.con_lastdof[c] = last; ++c; }
   }
   if (c != m.ncon) { err = "pair_ncon does not sum to ncon"; return false; }
-  derive_star(m, D);
-  D.nedge = 4 * m.ncon;
+  if (!D.dense) derive_star(m, D);
+  D.nedge = D.dense ? 0 : 4 * m.ncon;
   // per-warp slab layout
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
@@ -172,12 +185,17 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   D.o_qpos = take(m.nq); D.o_qvel = take(nv); D.o_warm = take(nv); D.o_ctrl = take(m.nu);
   D.o_vec = take(32); D.o_frow = take(32); D.o_cpos = take(3 * m.ncon); D.o_cframe = take(9 * m.ncon);
   D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = take(nv * DIAL_MAXCHAIN); D.o_crb = take(10 * nb); D.o_cfs = take(6 * nb);
+  if (D.dense) {
+    D.o_Md = take(nv * nv); D.o_Ld = take(nv * nv); D.o_Jd = take(D.nrow_c * nv); D.o_Gd = take(D.nrow_c * nv);
+    D.o_frow2 = take(D.nrow_c); D.o_cact = take(DIAL_MAXC);
+  }
   D.warp_floats = o;
   return true;
 }
 
 // which solver instantiation fits the model: 1 = star<3,6>, 2 = star<5,7>, 0 = generic tree
 static inline int star_variant(const DevModel& D) {
+  if (D.dense) return 3;
   if (D.star_nchain >= 1 && D.star_nchain <= 4) {
     int maxchain = 0;
     for (int i = 0; i < D.m.nv; ++i) maxchain = D.dof_nchain[i] > maxchain ? D.dof_nchain[i] : maxchain;

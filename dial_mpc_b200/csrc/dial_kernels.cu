@@ -287,6 +287,7 @@ static cudaError_t launch_rollout(dial_plan* p, const RolloutArgs& A, cudaStream
   switch (p->variant) {
     case 1: return launch_rollout_t<WPC, 3, 6>(p, A, st);
     case 2: return launch_rollout_t<WPC, 5, 7>(p, A, st);
+    case 3: return launch_rollout_t<WPC, -1, 0>(p, A, st);
     default: return launch_rollout_t<WPC, 0, 0>(p, A, st);
   }
 }
@@ -301,6 +302,11 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
   if (wpc == 0) {
     const int per_sm = (A.nrows + p->num_sms - 1) / p->num_sms;
     wpc = per_sm <= 1 ? 1 : per_sm <= 2 ? 2 : per_sm <= 4 ? 4 : per_sm <= 8 ? 8 : per_sm <= 14 ? 14 : 16;
+    // respect the 227 KB shared-memory limit of one CTA
+    const size_t fixed = sizeof(DevModel) + sizeof(DevPlan), slab = (size_t)p->hM.warp_floats * sizeof(float);
+    const int opts[6] = {16, 14, 8, 4, 2, 1};
+    for (int o = 0; o < 6; ++o)
+      if (opts[o] <= wpc && fixed + opts[o] * slab <= 227 * 1024) { wpc = opts[o]; break; }
   }
   A.lockstep = (wpc >= 2 && !getenv("DIAL_NO_LOCKSTEP")) ? 1 : 0;
   if (A.lockstep && !getenv("DIAL_NO_MIDSYNC")) A.lockstep = 2;  // second barrier before the Newton loop (+1-3 %)
@@ -335,7 +341,7 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
     delete p;
     return nullptr;
   }
-  if (c.env_id < DIAL_ENV_GO2_WALK || c.env_id > DIAL_ENV_H1_WALK) { g_err = "unknown env_id"; delete p; return nullptr; }
+  if (c.env_id < DIAL_ENV_GO2_WALK || c.env_id > DIAL_ENV_ALLEGRO) { g_err = "unknown env_id"; delete p; return nullptr; }
   auto bad = [&](cudaError_t e, const char* what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     dial_plan_destroy(p);

@@ -11,11 +11,13 @@ from dial_mpc_b200.envs.base_env import BaseEnv, BaseEnvConfig, PipelineState, S
 from dial_mpc_b200.envs.unitree_go2_env import (UnitreeGo2Env, UnitreeGo2EnvConfig, UnitreeGo2SeqJumpEnv,
                                                 UnitreeGo2SeqJumpEnvConfig)
 from dial_mpc_b200.envs.unitree_h1_env import UnitreeH1WalkEnv, UnitreeH1WalkEnvConfig
+from dial_mpc_b200.envs.manipulation import AllegroReorientEnv, AllegroReorientEnvConfig
 
 _configs: Dict[str, Any] = {
     "unitree_h1_walk": UnitreeH1WalkEnvConfig,
     "unitree_go2_walk": UnitreeGo2EnvConfig,
     "unitree_go2_seq_jump": UnitreeGo2SeqJumpEnvConfig,
+    "allegro_reorient": AllegroReorientEnvConfig,
 }
 _envs: Dict[str, Type[BaseEnv]] = {}
 
@@ -41,3 +43,4 @@ def get_environment(env_name: str, **kwargs) -> BaseEnv:
 register_environment("unitree_go2_walk", UnitreeGo2Env)
 register_environment("unitree_go2_seq_jump", UnitreeGo2SeqJumpEnv)
 register_environment("unitree_h1_walk", UnitreeH1WalkEnv)
+register_environment("allegro_reorient", AllegroReorientEnv)

@@ -3,4 +3,5 @@ examples = [
     "unitree_h1_jog",
     "unitree_go2_trot",
     "unitree_go2_seq_jump",
+    "allegro_reorient",
 ]

@@ -102,6 +102,61 @@ def _z2quat(vec):
     return _axisangle_quat(axis, ang)
 
 
+
+# --------------------------------------------------------------------------
+# mesh / primitive inertia (bodies without an explicit <inertial>)
+# --------------------------------------------------------------------------
+def _load_stl(path: str) -> np.ndarray:
+    """Binary STL -> triangles [n, 3, 3] (fp64)."""
+    import struct
+    raw = open(path, "rb").read()
+    n = struct.unpack("<I", raw[80:84])[0]
+    if len(raw) != 84 + 50 * n:
+        raise NotImplementedError(f"{path}: only binary STL meshes are supported")
+    rec = np.frombuffer(raw, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), offset=84, count=n)
+    return rec["v"].astype(np.float64)
+
+
+def _mesh_mass_properties(tri: np.ndarray):
+    """Volume, centre of mass and inertia tensor about the COM (unit density) of a closed
+    triangle mesh by signed tetrahedra against the origin."""
+    a, b, c = tri[:, 0], tri[:, 1], tri[:, 2]
+    det = np.einsum("ni,ni->n", a, np.cross(b, c))
+    vol = det.sum() / 6.0
+    sgn = 1.0 if vol >= 0 else -1.0
+    det, vol = det * sgn, vol * sgn
+    com = (det[:, None] * (a + b + c)).sum(0) / 24.0 / vol
+    # second moments  int x_i x_j dV  over the tetrahedra (0,a,b,c)
+    S = np.zeros((3, 3))
+    for p in (a, b, c):
+        S += 2.0 * np.einsum("n,ni,nj->ij", det, p, p)
+    for p, q in ((a, b), (a, c), (b, c)):
+        S += np.einsum("n,ni,nj->ij", det, p, q) + np.einsum("n,ni,nj->ij", det, q, p)
+    S /= 120.0
+    I0 = np.trace(S) * np.eye(3) - S                       # inertia about the origin
+    I = I0 - vol * (np.dot(com, com) * np.eye(3) - np.outer(com, com))
+    return vol, com, I
+
+
+def _primitive_mass_properties(gtype: int, size: np.ndarray):
+    """Volume and inertia (about the centre, unit density) of sphere / capsule / box."""
+    if gtype == GEOM_SPHERE:
+        r = size[0]
+        v = 4.0 / 3.0 * np.pi * r ** 3
+        return v, np.eye(3) * (0.4 * v * r * r)
+    if gtype == GEOM_CAPSULE:
+        r, h = size[0], 2 * size[1]
+        vc, vs = np.pi * r * r * h, 4.0 / 3.0 * np.pi * r ** 3
+        ixx = vc * (h * h / 12 + r * r / 4) + vs * (0.4 * r * r + 0.375 * r * h + 0.25 * h * h)
+        izz = vc * r * r / 2 + vs * 0.4 * r * r
+        return vc + vs, np.diag([ixx, ixx, izz])
+    if gtype == GEOM_BOX:
+        x, y, z = 2 * size
+        v = x * y * z
+        return v, np.diag([v * (y * y + z * z) / 12, v * (x * x + z * z) / 12, v * (x * x + y * y) / 12])
+    raise NotImplementedError(f"geom-derived inertia for geom type {gtype}")
+
+
 def _floats(s: str) -> np.ndarray:
     return np.array([float(t) for t in s.replace(",", " ").split()], dtype=np.float64)
 
@@ -324,12 +379,14 @@ def compile_mjcf(path: str, name: Optional[str] = None) -> CompiledModel:
 
     # ---- compiler / option ----------------------------------------------
     degree, autolimits, eulerseq = True, True, "xyz"
+    meshdir = ""
     for c in root.findall("compiler"):
         if "angle" in c.attrib:
             degree = c.attrib["angle"] == "degree"
         if "autolimits" in c.attrib:
             autolimits = c.attrib["autolimits"] == "true"
         eulerseq = c.attrib.get("eulerseq", eulerseq)
+        meshdir = c.attrib.get("meshdir", meshdir)
     for o in root.findall("option"):
         a = o.attrib
         m.timestep = float(a.get("timestep", m.timestep))
@@ -349,6 +406,21 @@ def compile_mjcf(path: str, name: Optional[str] = None) -> CompiledModel:
         for fl in o.findall("flag"):
             if "eulerdamp" in fl.attrib:
                 m.eulerdamp = fl.attrib["eulerdamp"] == "enable"
+
+    # ---- mesh assets (only used for the inertia of bodies without <inertial>) -----------
+    mesh_files: Dict[str, str] = {}
+    for sec in root.findall("asset"):
+        for me in sec.findall("mesh"):
+            a = defaults.resolve("mesh", me, None)
+            if "file" in a:
+                nm = a.get("name", os.path.splitext(os.path.basename(a["file"]))[0])
+                mesh_files[nm] = os.path.join(os.path.dirname(os.path.abspath(path)), meshdir, a["file"])
+    mesh_cache: Dict[str, Any] = {}
+
+    def mesh_props(name: str):
+        if name not in mesh_cache:
+            mesh_cache[name] = _mesh_mass_properties(_load_stl(mesh_files[name]))
+        return mesh_cache[name]
 
     # ---- bodies (DFS, document order) ------------------------------------
     bodies: List[Dict[str, Any]] = [dict(name="world", parent=0, pos=np.zeros(3),
@@ -388,6 +460,8 @@ def compile_mjcf(path: str, name: Optional[str] = None) -> CompiledModel:
             s = _floats(a["solref"])
             solref[: len(s)] = s
         geoms.append(dict(
+            mesh=a.get("mesh"), mass_attr=(float(a["mass"]) if "mass" in a else None),
+            density=float(a.get("density", 1000.0)),
             name=a.get("name", ""), type=gtype, body=bid, pos=pos, quat=quat, size=size,
             friction=fr, condim=int(a.get("condim", 3)), contype=contype, conaffinity=conaff,
             margin=float(a.get("margin", 0.0)), gap=float(a.get("gap", 0.0)),
@@ -493,11 +567,45 @@ def compile_mjcf(path: str, name: Optional[str] = None) -> CompiledModel:
             if ch.tag == "body":
                 walk(ch, 0, cc, 1)
 
-    for b in bodies[1:]:
-        if b.get("needs_geom_inertia") and b["joints"]:
-            raise NotImplementedError(
-                f"body {b['name']!r} has joints but no <inertial>; geom/mesh-derived "
-                "inertia is not supported by this compiler")
+    # geom-derived inertia (MuJoCo inertiafromgeom="auto"): bodies without <inertial>
+    for bid, b in enumerate(bodies):
+        if bid == 0 or not b.get("needs_geom_inertia"):
+            continue
+        mass, mcom, parts = 0.0, np.zeros(3), []
+        for g in geoms:
+            if g["body"] != bid:
+                continue
+            if g["type"] == GEOM_MESH:
+                vol, c_loc, I_loc = mesh_props(g["mesh"])
+            elif g["type"] == GEOM_PLANE:
+                continue
+            else:
+                vol, I_loc = _primitive_mass_properties(g["type"], g["size"])
+                c_loc = np.zeros(3)
+            gm = g["mass_attr"] if g["mass_attr"] is not None else g["density"] * vol
+            if gm <= 0.0:
+                continue
+            scale = gm / vol
+            R = _qmat(g["quat"])
+            c_b = g["pos"] + R @ c_loc
+            parts.append((gm, c_b, R @ (I_loc * scale) @ R.T))
+            mass += gm
+            mcom += gm * c_b
+        if mass <= 0.0:
+            if b["joints"]:
+                raise NotImplementedError(f"body {b['name']!r} has a joint but neither <inertial> nor massive geoms")
+            continue
+        mcom /= mass
+        I = np.zeros((3, 3))
+        for gm, c_b, I_b in parts:
+            dvec = c_b - mcom
+            I += I_b + gm * (np.dot(dvec, dvec) * np.eye(3) - np.outer(dvec, dvec))
+        wv, V = np.linalg.eigh(I)
+        order = np.argsort(-wv)
+        wv, V = wv[order], V[:, order]
+        if np.linalg.det(V) < 0:
+            V[:, 2] = -V[:, 2]
+        b["mass"], b["ipos"], b["inertia"], b["iquat"] = mass, mcom, wv, _mat2quat(V)
 
     nbody = len(bodies)
     m.nbody = nbody

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DIAL_ABI_VERSION 1
+#define DIAL_ABI_VERSION 2
 
 /* capacities of the fixed-size device model */
 #define DIAL_MAXB 24   /* bodies incl. world            */
@@ -34,8 +34,8 @@ extern "C" {
 #define DIAL_MAXQ 29   /* generalized positions         */
 #define DIAL_MAXU 20   /* actuators                     */
 #define DIAL_MAXG 8    /* collision geoms               */
-#define DIAL_MAXP 8    /* contact pairs                 */
-#define DIAL_MAXC 8    /* contacts                      */
+#define DIAL_MAXP 16   /* contact pairs                 */
+#define DIAL_MAXC 20   /* contacts                      */
 #define DIAL_MAXS 8    /* sites                         */
 #define DIAL_MAXNODE 8 /* Hnode+1                       */
 #define DIAL_MAXH 64   /* Hsample+1                     */
@@ -46,6 +46,7 @@ enum {
   DIAL_ENV_GO2_WALK = 0,    /* UnitreeGo2Env.step         envs/unitree_go2_env.py:126-261 */
   DIAL_ENV_GO2_SEQJUMP = 1, /* UnitreeGo2SeqJumpEnv.step  envs/unitree_go2_env.py:403-521 */
   DIAL_ENV_H1_WALK = 2,     /* UnitreeH1WalkEnv.step      envs/unitree_h1_env.py:181-321  */
+  DIAL_ENV_ALLEGRO = 3,     /* AllegroReorientEnv.step    envs/manipulation.py:63-100     */
 };
 
 /* Compiled robot model: what `brax.io.mjcf.load` + `mjx.put_model` give the reference
@@ -60,6 +61,7 @@ typedef struct dial_model_desc {
   float body_pos[DIAL_MAXB][3], body_quat[DIAL_MAXB][4];
   float body_ipos[DIAL_MAXB][3], body_iquat[DIAL_MAXB][4];
   float body_mass[DIAL_MAXB], body_inertia[DIAL_MAXB][3], body_invweight0[DIAL_MAXB];
+  float body_invweight0_rot[DIAL_MAXB];
   /* joints (at most one per body) */
   int32_t jnt_type[DIAL_MAXB], jnt_qposadr[DIAL_MAXB], jnt_dofadr[DIAL_MAXB], jnt_limited[DIAL_MAXB];
   float jnt_pos[DIAL_MAXB][3], jnt_axis[DIAL_MAXB][3], jnt_range[DIAL_MAXB][2], jnt_margin[DIAL_MAXB];
@@ -72,6 +74,7 @@ typedef struct dial_model_desc {
   int32_t geom_type[DIAL_MAXG], geom_bodyid[DIAL_MAXG];
   float geom_pos[DIAL_MAXG][3], geom_quat[DIAL_MAXG][4], geom_size[DIAL_MAXG][3];
   int32_t pair_kind[DIAL_MAXP], pair_geom1[DIAL_MAXP], pair_geom2[DIAL_MAXP], pair_ncon[DIAL_MAXP];
+  int32_t pair_condim[DIAL_MAXP];
   float pair_friction[DIAL_MAXP][5], pair_margin[DIAL_MAXP], pair_gap[DIAL_MAXP];
   float pair_solref[DIAL_MAXP][2], pair_solimp[DIAL_MAXP][5];
   /* sites */
@@ -100,6 +103,7 @@ typedef struct dial_plan_desc {
   float joint_range[DIAL_MAXU][2];          /* env.joint_range (sampling range)   */
   float physical_joint_range[DIAL_MAXU][2]; /* sys.jnt_range[1:]                  */
   float joint_torque_range[DIAL_MAXU][2];   /* sys.actuator_ctrlrange (+-inf ok)  */
+  float joint_offset[DIAL_MAXU];            /* added to the joint target (Allegro: init_q[7:], manipulation.py:106) */
   float M_n2u[DIAL_MAXH][DIAL_MAXNODE];     /* node -> action spline matrix       */
   /* reward constants */
   int32_t torso_body;       /* MuJoCo body id of the torso (x index + 1)          */

@@ -298,8 +298,38 @@ class H1WalkOracle(OracleEnv):
         return rew, s.stage
 
 
+class AllegroReorientOracle(OracleEnv):
+    """AllegroReorientEnv (dial_mpc/envs/manipulation.py:23-115): position targets, 4 substeps."""
+    model_file = "wonik_allegro_scene_left.json"
+    init_key = "in_hand_reorient"
+
+    def __init__(self, **kw):
+        kw.setdefault("kp", 1.0)
+        kw.setdefault("kd", 0.1)
+        kw.setdefault("dt", 0.02)
+        kw.setdefault("timestep", 0.005)
+        kw.setdefault("leg_control", "position")
+        super().__init__(**kw)
+        self.obj = self.m.names["body"].index("object") - 1
+        self.ang_vel_tar = np.array([0.0, 0.0, 0.5])
+        self.pos_tar = np.array([0.0, 0.0, 0.13])
+
+    def act2joint(self, act):  # manipulation.py:102-115 (adds init_q, clips to the physical range)
+        an = (act * self.action_scale + 1.0) / 2.0
+        jt = self.joint_range[:, 0] + self.init_q[7:] + an * (self.joint_range[:, 1] - self.joint_range[:, 0])
+        return np.clip(jt, self.physical_joint_range[:, 0], self.physical_joint_range[:, 1])
+
+    def reward(self, s, qpos, qvel, d, ctrl):
+        v = mo.brax_views(self.m, d)
+        w = v["xd_ang"][:, self.obj] * np.pi / 180.0
+        r_ang = -np.sum((w - self.ang_vel_tar) ** 2, -1)
+        r_pos = -np.sum((v["x_pos"][:, self.obj] - self.pos_tar) ** 2, -1)
+        r_joint = -np.sum((qpos[:, 7:] - self.init_q[7:]) ** 2, -1)
+        return r_ang + 5.0 * r_pos + 0.1 * r_joint, s.stage
+
+
 def make_env(env_name: str, cfg: Optional[Dict] = None) -> OracleEnv:
     cfg = dict(cfg or {})
     cls = {"unitree_go2_walk": Go2WalkOracle, "unitree_go2_seq_jump": Go2SeqJumpOracle,
-           "unitree_h1_walk": H1WalkOracle}[env_name]
+           "unitree_h1_walk": H1WalkOracle, "allegro_reorient": AllegroReorientOracle}[env_name]
     return cls(**cfg)

@@ -31,6 +31,7 @@ import numpy as np
 
 JNT_FREE, JNT_SLIDE, JNT_HINGE = 0, 2, 3
 PAIR_PLANE_SPHERE, PAIR_PLANE_CAPSULE = 0, 1
+PAIR_SPHERE_SPHERE, PAIR_SPHERE_CAPSULE, PAIR_CAPSULE_CAPSULE = 2, 3, 4
 MINVAL = 1e-15
 MINIMP, MAXIMP = 1e-4, 0.9999
 
@@ -71,8 +72,15 @@ class OModel:
         self.body_dofmask = banc
         self.lim_jnt = np.nonzero(self.jnt_limited)[0]
         self.nlim = len(self.lim_jnt)
-        self.nefc = self.nlim + 4 * self.ncon  # pyramidal, condim 3
-        assert self.cone == 0 and np.all(self.pair_condim == 3), "oracle: pyramidal condim-3 only"
+        # rows per contact: pyramidal 2*(condim-1), elliptic condim; cones = (row0, dim, pair) per contact
+        self.con_pair = np.repeat(np.arange(self.npair), self.pair_ncon)
+        dims = self.pair_condim[self.con_pair]
+        assert np.all((dims == 3) | (dims == 6) | (dims == 1)), "oracle: condim 1/3/6 only"
+        rows = dims if self.cone == 1 else np.where(dims == 1, 1, 2 * (dims - 1))
+        self.con_row0 = self.nlim + np.concatenate([[0], np.cumsum(rows)[:-1]]).astype(int) if self.ncon else np.zeros(0, int)
+        self.con_rows = rows.astype(int)
+        self.nefc = self.nlim + int(rows.sum())
+        self.elliptic = self.cone == 1
 
 
 # ---------------------------------------------------------------------------
@@ -175,6 +183,7 @@ class Data(NamedTuple):
     efc_pos: np.ndarray
     qacc: np.ndarray
     solver_niter: np.ndarray
+    qfrc_constraint: np.ndarray
 
 
 def kinematics(m: OModel, qpos: np.ndarray):
@@ -376,9 +385,62 @@ def collision(m: OModel, xpos, xmat):
                 pos[:, c] = cc - n * (r + 0.5 * d)[:, None]
                 frame[:, c] = fr
                 c += 1
+        elif kind in (PAIR_SPHERE_SPHERE, PAIR_SPHERE_CAPSULE, PAIR_CAPSULE_CAPSULE):
+            if kind == PAIR_SPHERE_SPHERE:
+                q1, q2 = p1, p2
+            elif kind == PAIR_SPHERE_CAPSULE:
+                seg = R2[:, :, 2] * m.geom_size[g2, 1]
+                q1, q2 = p1, closest_segment_point(p2 - seg, p2 + seg, p1)
+            else:
+                s1, s2 = R1[:, :, 2] * m.geom_size[g1, 1], R2[:, :, 2] * m.geom_size[g2, 1]
+                q1, q2 = closest_segment_to_segment_points(p1 - s1, p1 + s1, p2 - s2, p2 + s2)
+            d, pp, fr = sphere_sphere(q1, m.geom_size[g1, 0], q2, m.geom_size[g2, 0])
+            dist[:, c], pos[:, c], frame[:, c] = d, pp, fr
+            c += 1
         else:
             raise NotImplementedError(kind)
     return dist, pos, frame
+
+
+def sphere_sphere(pos1, r1, pos2, r2):
+    """mjx collision_primitive._sphere_sphere."""
+    dvec = pos2 - pos1
+    dist = np.linalg.norm(dvec, axis=-1, keepdims=True)
+    n = dvec / (dist + 1e-6 * (dist == 0.0))
+    n = np.where(dist == 0.0, np.array([1.0, 0.0, 0.0]), n)
+    d = dist[:, 0] - (r1 + r2)
+    return d, pos1 + n * (r1 + d * 0.5)[:, None], make_frame(n)
+
+
+def closest_segment_point(a, b, pt):
+    ab = b - a
+    t = np.sum((pt - a) * ab, -1, keepdims=True) / (np.sum(ab * ab, -1, keepdims=True) + 1e-6)
+    return a + np.clip(t, 0.0, 1.0) * ab
+
+
+def closest_segment_to_segment_points(a0, a1, b0, b1):
+    """mjx math.closest_segment_to_segment_points."""
+    def nwn(x):
+        n = np.linalg.norm(x, axis=-1, keepdims=True)
+        return x / (n + 1e-6 * (n == 0.0)), n
+    dir_a, len_a = nwn(a1 - a0)
+    dir_b, len_b = nwn(b1 - b0)
+    ha, hb = len_a * 0.5, len_b * 0.5
+    a_mid, b_mid = a0 + dir_a * ha, b0 + dir_b * hb
+    trans = a_mid - b_mid
+    dd = np.sum(dir_a * dir_b, -1, keepdims=True)
+    dat = np.sum(dir_a * trans, -1, keepdims=True)
+    dbt = np.sum(dir_b * trans, -1, keepdims=True)
+    denom = 1 - dd * dd
+    ta = (-dat + dd * dbt) / (denom + 1e-6)
+    tb = dbt + ta * dd
+    ta, tb = np.clip(ta, -ha, ha), np.clip(tb, -hb, hb)
+    best_a, best_b = a_mid + dir_a * ta, b_mid + dir_b * tb
+    new_a = closest_segment_point(a0, a1, best_b)
+    new_b = closest_segment_point(b0, b1, best_a)
+    d1 = np.sum((new_a - best_b) ** 2, -1, keepdims=True)
+    d2 = np.sum((new_b - best_a) ** 2, -1, keepdims=True)
+    return np.where(d1 < d2, new_a, best_a), np.where(d1 < d2, best_b, new_b)
 
 
 def _kbi(m: OModel, solref, solimp, pos):
@@ -405,101 +467,183 @@ def _kbi(m: OModel, solref, solimp, pos):
 
 
 def make_constraint(m: OModel, qpos, qvel, cdof, root_com, con_dist, con_pos, con_frame):
-    """Rows: joint limits (joint order) then pyramidal contact edges (4 per contact)."""
+    """Rows: joint limits (joint order), then contacts: pyramidal edges (2(condim-1) per
+    contact) or elliptic rows (condim per contact: normal, 2 tangents[, torsion, 2 rolling])."""
     B = qpos.shape[0]
     nv = m.nv
     J = np.zeros((B, m.nefc, nv))
     pos = np.zeros((B, m.nefc))
-    invw = np.zeros((B, m.nefc))
-    solref = np.zeros((B, m.nefc, 2))
-    solimp = np.zeros((B, m.nefc, 5))
+    D = np.zeros((B, m.nefc))
+    aref = np.zeros((B, m.nefc))
     active = np.zeros((B, m.nefc), dtype=bool)
     for r, j in enumerate(m.lim_jnt):
         qa, d = int(m.jnt_qposadr[j]), int(m.jnt_dofadr[j])
         dmin = qpos[:, qa] - m.jnt_range[j, 0]
         dmax = m.jnt_range[j, 1] - qpos[:, qa]
         p = np.minimum(dmin, dmax) - m.jnt_margin[j]
-        J[:, r, d] = (dmin < dmax) * 2.0 - 1.0
-        pos[:, r] = p
-        active[:, r] = p < 0
-        invw[:, r] = m.dof_invweight0[d]
-        solref[:, r] = m.jnt_solref[j]
-        solimp[:, r] = m.jnt_solimp[j]
-    c = 0
-    row = m.nlim
-    for k in range(m.npair):
+        act = p < 0
+        sign = (dmin < dmax) * 2.0 - 1.0
+        J[:, r, d] = sign * act
+        pos[:, r] = p * act
+        active[:, r] = act
+        k_, b_, imp = _kbi(m, np.broadcast_to(m.jnt_solref[j], (B, 2)), np.broadcast_to(m.jnt_solimp[j], (B, 5)), p * act)
+        R = np.maximum(m.dof_invweight0[d] * (1 - imp) / imp, MINVAL)
+        D[:, r] = np.where(act, 1.0 / R, 0.0)
+        aref[:, r] = np.where(act, -b_ * (sign * qvel[:, d]) - k_ * imp * p, 0.0)
+    cones = []
+    for c in range(m.ncon):
+        k = int(m.con_pair[c])
         g1, g2 = int(m.pair_geom1[k]), int(m.pair_geom2[k])
         b1, b2 = int(m.geom_bodyid[g1]), int(m.geom_bodyid[g2])
-        mu = m.pair_friction[k]
+        fri = m.pair_friction[k]
+        dim = int(m.pair_condim[k])
         incl = m.pair_margin[k] - m.pair_gap[k]
         t = m.body_invweight0[b1, 0] + m.body_invweight0[b2, 0]
-        iw = (t + mu[0] * mu[0] * t) * 2 * mu[0] * mu[0] / m.impratio
-        for _ in range(int(m.pair_ncon[k])):
-            p = con_pos[:, c]
+        p = con_pos[:, c]
+        d = con_dist[:, c] - incl
+        act = d < 0
 
-            def jacp(body):
-                offset = p - root_com[:, body]
-                jp_ = cdof[..., 3:] + np.cross(cdof[..., :3], offset[:, None, :])
-                return jp_ * m.body_dofmask[body][None, :, None]
-            diff = jacp(b2) - jacp(b1)                               # [B,nv,3]
-            dcon = np.einsum("nij,nvj->niv", con_frame[:, c], diff)  # [B,3,nv]
-            d = con_dist[:, c] - incl
-            edges = [dcon[:, 0] + mu[0] * dcon[:, 1], dcon[:, 0] - mu[0] * dcon[:, 1],
-                     dcon[:, 0] + mu[1] * dcon[:, 2], dcon[:, 0] - mu[1] * dcon[:, 2]]
-            for e in edges:
-                J[:, row] = e
-                pos[:, row] = d
-                active[:, row] = d < 0
-                invw[:, row] = iw
-                solref[:, row] = m.pair_solref[k]
-                solimp[:, row] = m.pair_solimp[k]
-                row += 1
-            c += 1
-    # inactive rows are zeroed wholesale (MJX multiplies the whole row struct by `active`)
-    J = J * active[..., None]
-    pos = pos * active
-    k_, b_, imp = _kbi(m, solref, solimp, pos)
-    R = np.maximum(invw * (1 - imp) / imp, MINVAL)
-    aref = -b_ * np.einsum("nrv,nv->nr", J, qvel) - k_ * imp * pos
-    D = np.where(active, 1.0 / R, 0.0)
-    aref = np.where(active, aref, 0.0)
+        def jac(body):
+            offset = p - root_com[:, body]
+            jp_ = cdof[..., 3:] + np.cross(cdof[..., :3], offset[:, None, :])
+            mask = m.body_dofmask[body][None, :, None]
+            return jp_ * mask, cdof[..., :3] * mask
+        jp2, jr2 = jac(b2)
+        jp1, jr1 = jac(b1)
+        dp = np.einsum("nij,nvj->niv", con_frame[:, c], jp2 - jp1)   # [B,3,nv]
+        dr = np.einsum("nij,nvj->niv", con_frame[:, c], jr2 - jr1)
+        k_, b_, imp = _kbi(m, np.broadcast_to(m.pair_solref[k], (B, 2)), np.broadcast_to(m.pair_solimp[k], (B, 5)), d * act)
+        r0 = int(m.con_row0[c])
+        if not m.elliptic:
+            iw = (t + fri[0] * fri[0] * t) * 2 * fri[0] * fri[0] / m.impratio
+            R = np.maximum(iw * (1 - imp) / imp, MINVAL)
+            full = np.concatenate([dp, dr], 1)
+            edges = []
+            for i in range(1, dim):
+                edges += [full[:, 0] + fri[i - 1] * full[:, i], full[:, 0] - fri[i - 1] * full[:, i]]
+            if dim == 1:
+                edges = [full[:, 0]]
+            for e_i, e in enumerate(edges):
+                row = r0 + e_i
+                J[:, row] = e * act[:, None]
+                pos[:, row] = d * act
+                active[:, row] = act
+                D[:, row] = np.where(act, 1.0 / R, 0.0)
+                aref[:, row] = np.where(act, -b_ * np.einsum("nv,nv->n", e, qvel) - k_ * imp * d, 0.0)
+        else:
+            rows = np.concatenate([dp, dr], 1)[:, :dim]
+            Rn = np.maximum(t * (1 - imp) / imp, MINVAL)
+            for i in range(dim):
+                row = r0 + i
+                J[:, row] = rows[:, i] * act[:, None]
+                active[:, row] = act
+                if i == 0:
+                    Ri = Rn
+                    pos[:, row] = d * act
+                    aref[:, row] = np.where(act, -b_ * np.einsum("nv,nv->n", rows[:, 0], qvel) - k_ * imp * d, 0.0)
+                else:
+                    Ri = np.maximum(Rn / m.impratio * fri[0] * fri[0] / (fri[i - 1] * fri[i - 1]), MINVAL)
+                    aref[:, row] = np.where(act, -b_ * np.einsum("nv,nv->n", rows[:, i], qvel), 0.0)
+                D[:, row] = np.where(act, 1.0 / Ri, 0.0)
+            cones.append((r0, dim, fri[0] / np.sqrt(m.impratio), fri[:dim - 1].copy()))
+    m._cones = cones   # static per model: (row0, dim, mu, friction[dim-1]) of each elliptic contact
     return J, D, aref, pos, active
 
 
 # ---------------------------------------------------------------------------
-# Newton solver (MJX solver.py), batched with per-sample done masks
+# Newton solver (MJX solver.py), batched with per-sample done masks.
+# Elliptic cones follow MuJoCo's primal cone cost: with N = mu*x0, T = |fri o x_1..| the
+# zones are top (N >= mu T: zero), bottom (mu N + T <= 0: plain quadratic) and middle
+# (0.5 Dm (N - mu T)^2, Dm = D0 / (mu^2 (1 + mu^2))).
 # ---------------------------------------------------------------------------
 class _Ctx:
     pass
 
 
-def _update_constraint(ctx, J, D, qfrc_smooth, qacc_smooth):
+def _cone_state(cone, Jaref, D):
+    r0, dim, mu, fri = cone
+    x = Jaref[:, r0:r0 + dim]
+    N = mu * x[:, 0]
+    U = x[:, 1:] * fri
+    T = np.sqrt(np.sum(U * U, -1))
+    bottom = ((T <= 0) & (N < 0)) | ((T > 0) & (mu * N + T <= 0))
+    middle = (T > 0) & (N < mu * T) & (mu * N + T > 0)
+    Dm = D[:, r0] / max(mu * mu * (1 + mu * mu), MINVAL)
+    return x, N, U, T, bottom, middle, Dm
+
+
+def _row_active(m, ctx, D):
+    """Rows treated as plain quadratics: limits with Jaref<0, pyramidal edges with Jaref<0,
+    all rows of an elliptic contact that sits in the bottom zone."""
     act = ctx.Jaref < 0
-    ctx.efc_force = D * -ctx.Jaref * act
-    ctx.qfrc_constraint = np.einsum("nrv,nr->nv", J, ctx.efc_force)
+    for cone in getattr(m, "_cones", []):
+        r0, dim = cone[0], cone[1]
+        _, _, _, _, bottom, _, _ = _cone_state(cone, ctx.Jaref, D)
+        act[:, r0:r0 + dim] = bottom[:, None]
+    return act
+
+
+def _update_constraint(m, ctx, J, D, qfrc_smooth, qacc_smooth):
+    act = _row_active(m, ctx, D)
+    force = D * -ctx.Jaref * act
+    cost = 0.5 * np.sum(D * ctx.Jaref * ctx.Jaref * act, -1)
+    for cone in getattr(m, "_cones", []):
+        r0, dim, mu, fri = cone
+        x, N, U, T, bottom, middle, Dm = _cone_state(cone, ctx.Jaref, D)
+        Ts = np.where(T > 0, T, 1.0)
+        NmT = N - mu * T
+        f0 = -Dm * NmT * mu
+        force[:, r0] += np.where(middle, f0, 0.0)
+        force[:, r0 + 1:r0 + dim] += np.where(middle[:, None], -(f0 / Ts)[:, None] * U * fri, 0.0)
+        cost += np.where(middle, 0.5 * Dm * NmT * NmT, 0.0)
+    ctx.efc_force = force
+    ctx.qfrc_constraint = np.einsum("nrv,nr->nv", J, force)
     ctx.gauss = 0.5 * np.sum((ctx.Ma - qfrc_smooth) * (ctx.qacc - qacc_smooth), -1)
     ctx.prev_cost = ctx.cost
-    ctx.cost = 0.5 * np.sum(D * ctx.Jaref * ctx.Jaref * act, -1) + ctx.gauss
+    ctx.cost = cost + ctx.gauss
 
 
-def _update_gradient(ctx, M, J, D, qfrc_smooth):
+def cone_hessian(cone, Jaref, D):
+    """Analytic Hessian (w.r.t. the contact's rows of Jaref) of the middle-zone cone cost."""
+    r0, dim, mu, fri = cone
+    x, N, U, T, bottom, middle, Dm = _cone_state(cone, Jaref, D)
+    B = Jaref.shape[0]
+    Ts = np.where(T > 0, T, 1.0)
+    s = x[:, 0] - T
+    H = np.zeros((B, dim, dim))
+    sc = Dm * mu * mu
+    H[:, 0, 0] = sc
+    H[:, 0, 1:] = -sc[:, None] * fri * U / Ts[:, None]
+    H[:, 1:, 0] = H[:, 0, 1:]
+    yy = U[:, :, None] * U[:, None, :] / (Ts * Ts)[:, None, None] * (1 + s / Ts)[:, None, None]
+    dd = np.eye(dim - 1)[None] * (s / Ts)[:, None, None]
+    H[:, 1:, 1:] = sc[:, None, None] * (fri[:, None] * fri[None, :])[None] * (yy - dd)
+    return H * middle[:, None, None]
+
+
+def _update_gradient(m, ctx, M, J, D, qfrc_smooth):
     ctx.grad = ctx.Ma - qfrc_smooth - ctx.qfrc_constraint
-    act = ctx.Jaref < 0
+    act = _row_active(m, ctx, D)
     H = M + np.einsum("nrv,nr,nrw->nvw", J, D * act, J)
+    for cone in getattr(m, "_cones", []):
+        r0, dim = cone[0], cone[1]
+        Hc = cone_hessian(cone, ctx.Jaref, D)
+        Jc = J[:, r0:r0 + dim]
+        H = H + np.einsum("nrv,nrs,nsw->nvw", Jc, Hc, Jc)
     ctx.Mgrad = np.linalg.solve(H, ctx.grad[..., None])[..., 0]
     ctx.H = H
 
 
-def _ctx_create(M, J, D, aref, qfrc_smooth, qacc_smooth, qacc, grad=True):
+def _ctx_create(m, M, J, D, aref, qfrc_smooth, qacc_smooth, qacc, grad=True):
     ctx = _Ctx()
     ctx.qacc = qacc.copy()
     ctx.Jaref = np.einsum("nrv,nv->nr", J, qacc) - aref
     ctx.Ma = np.einsum("nvw,nw->nv", M, qacc)
     ctx.cost = np.full(qacc.shape[0], np.inf)
     ctx.prev_cost = np.zeros(qacc.shape[0])
-    _update_constraint(ctx, J, D, qfrc_smooth, qacc_smooth)
+    _update_constraint(m, ctx, J, D, qfrc_smooth, qacc_smooth)
     if grad:
-        _update_gradient(ctx, M, J, D, qfrc_smooth)
+        _update_gradient(m, ctx, M, J, D, qfrc_smooth)
         ctx.search = -ctx.Mgrad
     return ctx
 
@@ -516,14 +660,46 @@ def _linesearch(m: OModel, ctx, M, J, D, qfrc_smooth):
         np.sum(ctx.search * ctx.Ma, -1) - np.sum(ctx.search * qfrc_smooth, -1),
         0.5 * np.sum(ctx.search * mv, -1)], -1)                       # [B,3]
     quad = np.stack([0.5 * ctx.Jaref * ctx.Jaref, jv * ctx.Jaref, 0.5 * jv * jv], -1) * D[..., None]
+    cones = getattr(m, "_cones", [])
+    simple = np.ones(m.nefc, dtype=bool)
+    cq = []
+    for cone in cones:
+        r0, dim, mu, fri = cone
+        simple[r0:r0 + dim] = False
+        x, v = ctx.Jaref[:, r0:r0 + dim], jv[:, r0:r0 + dim]
+        cq.append(dict(U0=mu * x[:, 0], V0=mu * v[:, 0], UU=np.sum((x[:, 1:] * fri) ** 2, -1),
+                       UV=np.sum(x[:, 1:] * v[:, 1:] * fri * fri, -1), VV=np.sum((v[:, 1:] * fri) ** 2, -1),
+                       Dm=D[:, r0] / max(mu * mu * (1 + mu * mu), MINVAL), mu=mu,
+                       quad=np.sum(quad[:, r0:r0 + dim], 1)))
 
     def point(alpha):
         x = ctx.Jaref + alpha[:, None] * jv
-        act = x < 0
+        act = (x < 0) & simple[None]
         qt = quad_gauss + np.sum(quad * act[..., None], 1)
         cost = alpha * alpha * qt[:, 2] + alpha * qt[:, 1] + qt[:, 0]
         d0 = 2 * alpha * qt[:, 2] + qt[:, 1]
-        d1 = 2 * qt[:, 2] + (qt[:, 2] == 0) * MINVAL
+        d1 = 2 * qt[:, 2]
+        for q in cq:
+            mu = q["mu"]
+            N = q["U0"] + alpha * q["V0"]
+            Tsq = q["UU"] + alpha * (2 * q["UV"] + alpha * q["VV"])
+            T = np.sqrt(np.maximum(Tsq, 0.0))
+            bottom = ((Tsq <= 0) & (N < 0)) | ((Tsq > 0) & (mu * N + T <= 0))
+            middle = (Tsq > 0) & (N < mu * T) & (mu * N + T > 0)
+            qq = q["quad"]
+            cost = cost + np.where(bottom, alpha * alpha * qq[:, 2] + alpha * qq[:, 1] + qq[:, 0], 0.0)
+            d0 = d0 + np.where(bottom, 2 * alpha * qq[:, 2] + qq[:, 1], 0.0)
+            d1 = d1 + np.where(bottom, 2 * qq[:, 2], 0.0)
+            Ts = np.where(T > 0, T, 1.0)
+            Tsqs = np.where(Tsq > 0, Tsq, 1.0)
+            T1 = (q["UV"] + alpha * q["VV"]) / Ts
+            T2 = q["VV"] / Ts - (q["UV"] + alpha * q["VV"]) * T1 / Tsqs
+            NmT = N - mu * T
+            N1 = q["V0"]
+            cost = cost + np.where(middle, 0.5 * q["Dm"] * NmT * NmT, 0.0)
+            d0 = d0 + np.where(middle, q["Dm"] * NmT * (N1 - mu * T1), 0.0)
+            d1 = d1 + np.where(middle, q["Dm"] * ((N1 - mu * T1) ** 2 + NmT * (-mu * T2)), 0.0)
+        d1 = d1 + (d1 == 0) * MINVAL
         return np.stack([alpha, cost, d0, d1], -1)                    # [B,4]
 
     def sel(c, a, b):
@@ -572,10 +748,10 @@ def _linesearch(m: OModel, ctx, M, J, D, qfrc_smooth):
 def solve(m: OModel, M, J, D, aref, qfrc_smooth, qacc_smooth, qacc_warmstart):
     B = qacc_smooth.shape[0]
     scale = m.meaninertia * max(1, m.nv)
-    warm = _ctx_create(M, J, D, aref, qfrc_smooth, qacc_smooth, qacc_warmstart, grad=False)
-    smth = _ctx_create(M, J, D, aref, qfrc_smooth, qacc_smooth, qacc_smooth, grad=False)
+    warm = _ctx_create(m, M, J, D, aref, qfrc_smooth, qacc_smooth, qacc_warmstart, grad=False)
+    smth = _ctx_create(m, M, J, D, aref, qfrc_smooth, qacc_smooth, qacc_smooth, grad=False)
     qacc0 = np.where((warm.cost < smth.cost)[:, None], qacc_warmstart, qacc_smooth)
-    ctx = _ctx_create(M, J, D, aref, qfrc_smooth, qacc_smooth, qacc0)
+    ctx = _ctx_create(m, M, J, D, aref, qfrc_smooth, qacc_smooth, qacc0)
     niter = np.zeros(B, dtype=np.int64)
     fields = ("qacc", "Jaref", "Ma", "cost", "prev_cost", "gauss", "efc_force",
               "qfrc_constraint", "grad", "Mgrad", "search")
@@ -590,15 +766,15 @@ def solve(m: OModel, M, J, D, aref, qfrc_smooth, qacc_smooth, qacc_warmstart):
             break
         old = {f: getattr(ctx, f).copy() for f in fields}
         _linesearch(m, ctx, M, J, D, qfrc_smooth)
-        _update_constraint(ctx, J, D, qfrc_smooth, qacc_smooth)
-        _update_gradient(ctx, M, J, D, qfrc_smooth)
+        _update_constraint(m, ctx, J, D, qfrc_smooth, qacc_smooth)
+        _update_gradient(m, ctx, M, J, D, qfrc_smooth)
         ctx.search = -ctx.Mgrad
         for f in fields:
             new = getattr(ctx, f)
             g = go.reshape((B,) + (1,) * (new.ndim - 1))
             setattr(ctx, f, np.where(g, new, old[f]))
         niter = niter + go
-    return ctx.qacc, niter
+    return ctx.qacc, niter, ctx.qfrc_constraint
 
 
 # ---------------------------------------------------------------------------
@@ -628,12 +804,12 @@ def forward(m: OModel, qpos, qvel, ctrl, qacc_warmstart) -> Data:
     qfrc_smooth = qfrc_passive - qfrc_bias + qfrc_actuator
     qacc_smooth = np.linalg.solve(M, qfrc_smooth[..., None])[..., 0]
     if m.nefc == 0:
-        qacc, niter = qacc_smooth, np.zeros(B, dtype=np.int64)
+        qacc, niter, qfc = qacc_smooth, np.zeros(B, dtype=np.int64), np.zeros((B, m.nv))
     else:
-        qacc, niter = solve(m, M, J, D, aref, qfrc_smooth, qacc_smooth, qacc_warmstart)
+        qacc, niter, qfc = solve(m, M, J, D, aref, qfrc_smooth, qacc_smooth, qacc_warmstart)
     return Data(qpos_n, xpos, xquat, xmat, xipos, ximat, xanchor, xaxis, root_com, cinert, cdof, M,
                 cvel, cdof_dot, qfrc_bias, qfrc_passive, qfrc_actuator, qfrc_smooth, qacc_smooth,
-                site_xpos, con_dist, con_pos, con_frame, J, D, aref, epos, qacc, niter)
+                site_xpos, con_dist, con_pos, con_frame, J, D, aref, epos, qacc, niter, qfc)
 
 
 def integrate_pos(m: OModel, qpos, qvel, dt):
@@ -659,8 +835,7 @@ def step(m: OModel, qpos, qvel, ctrl, qacc_warmstart):
     qacc = d.qacc
     if m.eulerdamp and np.any(m.dof_damping != 0):
         Mh = d.M + np.diag(m.timestep * m.dof_damping)[None]
-        qfrc_c = np.einsum("nvw,nw->nv", d.M, d.qacc) - d.qfrc_smooth  # = qfrc_constraint
-        qacc = np.linalg.solve(Mh, (d.qfrc_smooth + qfrc_c)[..., None])[..., 0]
+        qacc = np.linalg.solve(Mh, (d.qfrc_smooth + d.qfrc_constraint)[..., None])[..., 0]
     qvel_new = qvel + m.timestep * qacc
     qpos_new = integrate_pos(m, d.qpos, qvel_new, m.timestep)
     return qpos_new, qvel_new, d.qacc.copy(), d

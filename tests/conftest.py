@@ -31,6 +31,7 @@ ENV_CASES = {
         pose_target_sequence=[[0, 0, 0.27], [0.4, 0, 0.27], [0.8, 0, 0.27], [1.2, 0, 0.27], [1.6, 0, 0.27]],
         yaw_target_sequence=[0.0] * 5),
     "unitree_h1_walk": dict(default_vx=2.0, ramp_up_time=3.0),
+    "allegro_reorient": dict(dt=0.02, timestep=0.005, leg_control="position"),
 }
 
 
