@@ -139,6 +139,8 @@ class _Lib:
             lib.dial_key_split.restype = None
             lib.dial_launch_count.argtypes = [V]
             lib.dial_launch_count.restype = C.c_int64
+            lib.dial_debug_counters.argtypes = [V, C.POINTER(C.c_float)]
+            lib.dial_debug_counters.restype = C.c_int
             for fn in ("dial_rollout", "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout",
                        "dial_reverse_update", "dial_reverse_trajbar"):
                 getattr(lib, fn).restype = C.c_int
@@ -162,4 +164,4 @@ def check(rc: int) -> None:
 
 EXPORTS = ["dial_abi_version", "dial_last_error", "dial_sizeof", "dial_plan_create", "dial_plan_destroy", "dial_rollout",
            "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout", "dial_reverse_update",
-           "dial_reverse_trajbar", "dial_key_split", "dial_launch_count"]
+           "dial_reverse_trajbar", "dial_key_split", "dial_launch_count", "dial_debug_counters"]

@@ -270,6 +270,7 @@ struct WarpCtx {
   int mylevel;         // elimination level of the dof (leaves = 0), -1 for non-dof lanes
   int parent;          // parent dof or -1
   int midsync;         // lock-step CTAs: extra CTA barrier before the Newton loop
+  float* dbg;          // optional counters (tests / tuning): [0] physics steps, [1] Newton iterations
   int chain[DIAL_MAXCHAIN];
 };
 
@@ -1247,12 +1248,18 @@ DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float
       float gradient = sqrtf(S.gradnorm2) / scale;
       if (m.iterations != 1) done = done || (improvement < m.tolerance) || (gradient < m.tolerance);
     }
+    // a diverged sample (NaN / inf cost) can never satisfy the convergence tests: stop instead of
+    // burning iterations x ls_iterations on it (its result is garbage either way, weight 0 later)
+    if (!(fabsf(S.cost) <= 3.0e38f)) done = true;
     if (done) break;
     dense_build_H(w, S, C);
     S.search = -dense_factor_solve(w, S.grad);
     dense_linesearch(w, S, C);
     ++it;
   }
+#ifndef DIAL_HOST_EMUL
+  if (w.dbg && lane == 0) { atomicAdd(w.dbg, 1.f); atomicAdd(w.dbg + 1, (float)it); }
+#endif
   return S.qacc;
 }
 
@@ -1883,6 +1890,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
   WarpCtx w;
   w.M = Mp; w.P = Pp; w.s = slab; w.lane = lane;
   w.midsync = A.lockstep >= 2;
+  w.dbg = A.dbg;
   const DevModel& M = *Mp;
   const dial_model_desc& m = M.m;
   const dial_plan_desc& c = Pp->c;

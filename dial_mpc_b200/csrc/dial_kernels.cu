@@ -258,6 +258,7 @@ struct dial_plan {
   float* zeros = nullptr;                                          // [nv]
   int ybar_grid = 0;
   int64_t launches = 0;
+  float* dbg = nullptr;  // optional device counters (DIAL_DEBUG_COUNTERS=1)
 };
 
 extern "C" int dial_abi_version(void) { return DIAL_ABI_VERSION; }
@@ -308,7 +309,9 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
     for (int o = 0; o < 6; ++o)
       if (opts[o] <= wpc && fixed + opts[o] * slab <= 227 * 1024) { wpc = opts[o]; break; }
   }
-  A.lockstep = (wpc >= 2 && !getenv("DIAL_NO_LOCKSTEP")) ? 1 : 0;
+  // lock-step pays off when the warps of a CTA do similar work; the dense (elliptic) path has a
+  // heavy-tailed iteration count per sample, so its warps run free (measured 172 vs 221 ms)
+  A.lockstep = (wpc >= 2 && !p->hM.dense && !getenv("DIAL_NO_LOCKSTEP")) ? 1 : 0;
   if (A.lockstep && !getenv("DIAL_NO_MIDSYNC")) A.lockstep = 2;  // second barrier before the Newton loop (+1-3 %)
   switch (wpc) {
     case 1: return launch_rollout<1>(p, A, st);
@@ -365,6 +368,10 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
   if ((e = cudaMalloc(&p->tb_partial, (size_t)TB_CHUNKS * H * (m.nq + m.nv + 3 * (m.nbody - 1)) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(tb_partial)");
   if ((e = cudaMalloc(&p->counter, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMalloc(counter)");
   if ((e = cudaMemset(p->counter, 0, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMemset(counter)");
+  if (getenv("DIAL_DEBUG_COUNTERS")) {
+    if ((e = cudaMalloc(&p->dbg, 8 * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(dbg)");
+    cudaMemset(p->dbg, 0, 8 * sizeof(float));
+  }
   if ((e = cudaMalloc(&p->zeros, DIAL_MAXV * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(zeros)");
   if ((e = cudaMemset(p->zeros, 0, DIAL_MAXV * sizeof(float))) != cudaSuccess) return bad(e, "cudaMemset(zeros)");
   return p;
@@ -373,7 +380,7 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
 extern "C" void dial_plan_destroy(dial_plan* p) {
   if (!p) return;
   cudaFree(p->dM); cudaFree(p->dP); cudaFree(p->traj_q); cudaFree(p->traj_qd); cudaFree(p->traj_x);
-  cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->tb_partial); cudaFree(p->counter); cudaFree(p->zeros);
+  cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->tb_partial); cudaFree(p->counter); cudaFree(p->zeros); cudaFree(p->dbg);
   delete p;
 }
 
@@ -424,6 +431,7 @@ extern "C" int dial_reverse_rollout(dial_plan* p, const dial_state* s, const flo
   A.eps = eps; A.Ybar = Ybar; A.noise = noise_scale;
   if (key) { A.key0 = key[0]; A.key1 = key[1]; }
   A.rews = rews_local; A.q = p->traj_q; A.qd = p->traj_qd; A.xpos = p->traj_x;
+  A.dbg = p->dbg;
   CUDA_OK(launch_rollout_any(p, A, (cudaStream_t)stream));
   return 0;
 }
@@ -482,3 +490,10 @@ extern "C" void dial_key_split(const uint32_t key[2], uint32_t out0[2], uint32_t
 }
 
 extern "C" int64_t dial_launch_count(const dial_plan* p) { return p ? p->launches : 0; }
+
+extern "C" int dial_debug_counters(dial_plan* p, float out[8]) {
+  if (!p || !p->dbg) return fail("debug counters are off (set DIAL_DEBUG_COUNTERS=1 before dial_plan_create)");
+  CUDA_OK(cudaMemcpy(out, p->dbg, 8 * sizeof(float), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemset(p->dbg, 0, 8 * sizeof(float)));
+  return 0;
+}

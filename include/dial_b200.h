@@ -190,6 +190,10 @@ int dial_reverse_trajbar(dial_plan* plan, const float* weights, int rank,
  * host-side Threefry-2x32; out[0] is the new rng, out[1] the sampling key. */
 void dial_key_split(const uint32_t key[2], uint32_t out0[2], uint32_t out1[2]);
 
+/* tuning aid: with DIAL_DEBUG_COUNTERS=1 in the environment at plan creation the dense solver
+ * path counts [0] physics steps and [1] Newton iterations; reads and resets the counters. */
+int dial_debug_counters(dial_plan* plan, float out[8]);
+
 /* kernel launches issued by this plan since creation (bench bookkeeping) */
 int64_t dial_launch_count(const dial_plan* plan);
 

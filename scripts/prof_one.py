@@ -11,6 +11,8 @@ if name == 'unitree_go2_walk':
     ecfg = E.UnitreeGo2EnvConfig(default_vx=0.8, ramp_up_time=1.0)
 elif name == 'unitree_go2_seq_jump':
     ecfg = E.UnitreeGo2SeqJumpEnvConfig(pose_target_sequence=np.array([[0,0,0.27],[0.4,0,0.27],[0.8,0,0.27],[1.2,0,0.27],[1.6,0,0.27]]), yaw_target_sequence=np.zeros(5))
+elif name == 'allegro_reorient':
+    ecfg = E.AllegroReorientEnvConfig(dt=0.02, timestep=0.005, leg_control='position')
 else:
     ecfg = E.UnitreeH1WalkEnvConfig(default_vx=2.0, ramp_up_time=3.0)
 env = E.get_environment(name, config=ecfg)

@@ -20,7 +20,8 @@ from oracle.planner_oracle import PlannerOracle  # noqa: E402
 from tests.conftest import ENV_CASES  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
-CASES = {"unitree_go2_walk": (16, 4, 32), "unitree_go2_seq_jump": (25, 5, 32), "unitree_h1_walk": (30, 5, 16)}
+CASES = {"unitree_go2_walk": (16, 4, 32), "unitree_go2_seq_jump": (25, 5, 32), "unitree_h1_walk": (30, 5, 16),
+         "allegro_reorient": (8, 4, 16)}
 
 
 def main():
@@ -28,12 +29,18 @@ def main():
         env = make_env(name, ENV_CASES[name])
         s = env.reset()
         # settle 10 env steps with zero action (BASELINE.md §3 fixture state)
-        for _ in range(10):
-            s, _, _ = env.step(s, np.zeros((1, env.nu)))
+        if name == "allegro_reorient":   # hold the initial grasp for 3 env steps (zero action would open the hand)
+            jr = env.joint_range
+            hold = np.clip(((-jr[:, 0]) / (jr[:, 1] - jr[:, 0])) * 2 - 1, -1, 1)[None]
+            for _ in range(3):
+                s, _, _ = env.step(s, hold)
+        else:
+            for _ in range(10):
+                s, _, _ = env.step(s, np.zeros((1, env.nu)))
         rng = np.random.default_rng(20260922)
         eps = rng.standard_normal((N, Hn + 1, env.nu)).astype(np.float32).astype(np.float64)
         pl = PlannerOracle(env, N, Hs, Hn, 0.05, 0.9 if "go2" in name else 1.0, 0.5)
-        Ybar0 = np.clip(rng.standard_normal((Hn + 1, env.nu)) * 0.2, -1, 1).astype(np.float32).astype(np.float64)
+        Ybar0 = np.clip(rng.standard_normal((Hn + 1, env.nu)) * 0.2 + (hold if name == "allegro_reorient" else 0.0), -1, 1).astype(np.float32).astype(np.float64)
         Ybar, info = pl.reverse_once(s, eps, Ybar0, pl.sigma_control)
         np.savez_compressed(
             os.path.join(OUT, f"{name}.npz"),

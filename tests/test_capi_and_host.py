@@ -68,7 +68,7 @@ def test_registry_and_yaml_loading():
         env = E.get_environment(dc.env_name, config=ec)
         assert env.action_size == env.sys.nu and abs(env.dt - 0.02) < 1e-12
         d = env.plan_desc(Nsample=8, Hsample=dc.Hsample, Hnode=dc.Hnode)
-        assert d.env_id == _capi.ENV_IDS[dc.env_name] and d.n_frames == 1
+        assert d.env_id == _capi.ENV_IDS[dc.env_name] and d.n_frames == int(round(cfg["dt"] / cfg["timestep"]))
     E.register_config("custom", E.UnitreeGo2EnvConfig)
     assert E.get_config("custom") is E.UnitreeGo2EnvConfig
 
