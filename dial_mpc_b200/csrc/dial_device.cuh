@@ -112,6 +112,7 @@ struct RolloutArgs {
   float* qvel_out;
   float* warm_out;
   float* ctrl_out;
+  unsigned int* row_counter;  // non-null: persistent warps pull rows from this counter (dense path)
   float* dbg;           // optional debug dump (tests)
 };
 
@@ -873,45 +874,49 @@ DEV void dense_update_constraint(WarpCtx& w, Solver& S, const ConeLane& C) {
   S.gradnorm2 = g2;
 }
 
-// dense Cholesky H = L L^T in SM(Ld) (lane = row) and solve; g / x on the dof lanes
-DEV float dense_factor_solve(WarpCtx& w, float g) {
-  const int nv = w.M->m.nv, lane = w.lane;
-  float* L = SM(Ld);
-  for (int k = 0; k < nv; ++k) {
-    syncwarp();
-    const float d = sqrtf(fmaxf(L[k * nv + k], DIAL_MINVAL));
-    const float inv = 1.f / d;
-    syncwarp();
-    if (lane == k) L[k * nv + k] = d;
-    if (lane > k && lane < nv) L[lane * nv + k] *= inv;
-    syncwarp();
-    if (lane > k && lane < nv) {
-      const float lik = L[lane * nv + k];
-      for (int j = k + 1; j <= lane; ++j) L[lane * nv + j] -= lik * L[j * nv + k];
+// dense Cholesky H = L L^T with row `lane` of H / L in registers (NVD = nv at compile time, fully
+// unrolled): column k of the factor needs row k broadcast from lane k (shuffles), no shared memory
+// and no barriers.  Hrow[j], j <= lane: lower triangle of H on entry, of L on return.
+template <int NVD>
+DEV float dense_factor_solve(WarpCtx& w, float* Hrow, float g) {
+  const int lane = w.lane;
+#pragma unroll
+  for (int k = 0; k < NVD; ++k) {
+    // row k is final once columns < k are done: lane k holds L[k][0..k-1] and the pivot
+    float piv = Hrow[k];
+#pragma unroll
+    for (int p = 0; p < k; ++p) {
+      const float lkp = shfl(Hrow[p], k);       // L[k][p]
+      if (lane >= k) piv -= Hrow[p] * lkp;      // lanes > k: L[i][p] * L[k][p]; lane k: L[k][p]^2
     }
+    // lane k: piv = H[k][k] - sum L[k][p]^2 ; lanes > k: piv = H[i][k] - sum L[i][p] L[k][p]
+    const float dk = sqrtf(fmaxf(shfl(piv, k), DIAL_MINVAL));
+    Hrow[k] = (lane == k) ? dk : piv / dk;
   }
-  syncwarp();
   float y = g;
-  for (int k = 0; k < nv; ++k) {       // L y = g
-    float yk = shfl(y, k) / L[k * nv + k];
+#pragma unroll
+  for (int k = 0; k < NVD; ++k) {        // L y = g
+    const float yk = shfl(y, k) / shfl(Hrow[k], k);
     if (lane == k) y = yk;
-    if (lane > k && lane < nv) y -= L[lane * nv + k] * yk;
+    if (lane > k) y -= Hrow[k] * yk;
   }
-  for (int k = nv - 1; k >= 0; --k) {  // L^T x = y
-    float xk = shfl(y, k) / L[k * nv + k];
+#pragma unroll
+  for (int k = NVD - 1; k >= 0; --k) {   // L^T x = y :  x_k = (y_k - sum_{i>k} L[i][k] x_i) / L[k][k]
+    float t = (lane > k && lane < NVD) ? Hrow[k] * y : 0.f;
+    t = warp_sum(t);
+    const float xk = (shfl(y, k) - t) / shfl(Hrow[k], k);
     if (lane == k) y = xk;
-    if (lane < k) y -= L[k * nv + lane] * xk;
   }
   return y;
 }
 
 // H = Md + J^T G with G = D o J (bottom-zone contacts) or Hc J_c (middle-zone cone Hessian)
-DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C) {
+template <int NVD>
+DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C, float* Hrow) {
   const DevModel& M = *w.M;
   const int nv = M.m.nv, lane = w.lane;
   const float* Jd = SM(Jd);
   float* Gd = SM(Gd);
-  float* L = SM(Ld);
   const float* Md = SM(Md);
   int* cact = reinterpret_cast<int*>(SM(cact));
   syncwarp();
@@ -963,20 +968,25 @@ DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C) {
     }
   }
   syncwarp();
+#pragma unroll
+  for (int j = 0; j < NVD; ++j) Hrow[j] = 0.f;
   if (lane < nv) {
-    for (int j = 0; j <= lane; ++j) L[lane * nv + j] = Md[lane * nv + j];
-    L[lane * nv + lane] += (S.l_Jaref < 0.f) ? S.l_D : 0.f;
+#pragma unroll
+    for (int j = 0; j < NVD; ++j) Hrow[j] = (j <= lane) ? Md[lane * nv + j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < NVD; ++j)
+      if (j == lane) Hrow[j] += (S.l_Jaref < 0.f) ? S.l_D : 0.f;
     for (int c = 0; c < M.m.ncon; ++c) {
       if (cact[c] != 2) continue;
       const int r0 = M.con_row0[c], dim = M.con_dim[c];
       for (int i = 0; i < dim; ++i) {
         const float a = Jd[(r0 + i) * nv + lane];
         const float* Gr = Gd + (r0 + i) * nv;
-        for (int j = 0; j <= lane; ++j) L[lane * nv + j] += a * Gr[j];
+#pragma unroll
+        for (int j = 0; j < NVD; ++j) Hrow[j] += a * Gr[j];
       }
     }
   }
-  syncwarp();
 }
 
 // dense M x (lane = dof)
@@ -1038,8 +1048,9 @@ DEV void dense_ls_points(const Solver& S, const ConeLane& C, float l_jv, const f
       if (bottom) {
         s[3 * i] += a * a * Q2 + a * Q1 + Q0; s[3 * i + 1] += 2.f * a * Q2 + Q1; s[3 * i + 2] += 2.f * Q2;
       } else if (middle) {
-        const float T1 = (UV + a * VV) / T;
-        const float T2 = VV / T - (UV + a * VV) * T1 / Tsq;
+        const float iT = 1.f / T;
+        const float T1 = (UV + a * VV) * iT;
+        const float T2 = (VV - T1 * T1) * iT;   // VV/T - (UV + a VV) T1 / T^2
         const float NmT = N - C.mu * T, dN = V0 - C.mu * T1;
         s[3 * i] += 0.5f * C.Dm * NmT * NmT;
         s[3 * i + 1] += C.Dm * NmT * dN;
@@ -1112,6 +1123,7 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
 }
 
 // sections 8-9 of the physics step for the dense path; returns qacc, leaves S.qfc
+template <int NVD>
 DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float myqvel) {
   const DevModel& M = *w.M;
   const dial_model_desc& m = M.m;
@@ -1119,7 +1131,6 @@ DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float
   const bool isdof = d < nv;
   float* Jd = SM(Jd);
   float* Md = SM(Md);
-  float* L = SM(Ld);
   const float* cdof = SM(cdof);
   const float* rcom = SM(rcom);
   const float* cdist = SM(cdist);
@@ -1213,9 +1224,10 @@ DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float
   const float scale = m.meaninertia * (float)(nv > 1 ? nv : 1);
   const float mywarm = isdof ? SM(warm)[d] : 0.f;
   syncwarp();
-  if (isdof)
-    for (int j = 0; j <= d; ++j) L[d * nv + j] = Md[d * nv + j];
-  S.qas = dense_factor_solve(w, S.qfs);
+  float Hrow[NVD];
+#pragma unroll
+  for (int j = 0; j < NVD; ++j) Hrow[j] = (isdof && j <= d) ? Md[d * nv + j] : (j == d ? 1.f : 0.f);
+  S.qas = dense_factor_solve<NVD>(w, Hrow, S.qfs);
   {
     float xw[6], xs[6], cw, cs, f[6], N, T;
     float Maw = dense_mul_M(w, mywarm);
@@ -1252,8 +1264,8 @@ DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float
     // burning iterations x ls_iterations on it (its result is garbage either way, weight 0 later)
     if (!(fabsf(S.cost) <= 3.0e38f)) done = true;
     if (done) break;
-    dense_build_H(w, S, C);
-    S.search = -dense_factor_solve(w, S.grad);
+    dense_build_H<NVD>(w, S, C, Hrow);
+    S.search = -dense_factor_solve<NVD>(w, Hrow, S.grad);
     dense_linesearch(w, S, C);
     ++it;
   }
@@ -1616,17 +1628,17 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
 
   float qacc, qacc_int;
   if constexpr (NL < 0) {
-    qacc = dense_constraint_solve(w, S, Mrow, myqvel);
+    qacc = dense_constraint_solve<NR>(w, S, Mrow, myqvel);
     qacc_int = qacc;
     if (m.eulerdamp) {   // implicit joint damping: (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
-      float* Ld_ = SM(Ld);
       const float* Md_ = SM(Md);
-      syncwarp();
-      if (isdof) {
-        for (int j = 0; j <= d; ++j) Ld_[d * nv + j] = Md_[d * nv + j];
-        Ld_[d * nv + d] += m.timestep * m.dof_damping[d];
-      }
-      qacc_int = dense_factor_solve(w, S.qfs + S.qfc);
+      float Hd[NR > 0 ? NR : 1];
+#pragma unroll
+      for (int j = 0; j < NR; ++j) Hd[j] = (isdof && j <= d) ? Md_[d * nv + j] : 0.f;
+#pragma unroll
+      for (int j = 0; j < NR; ++j)
+        if (j == d) Hd[j] += isdof ? m.timestep * m.dof_damping[d] : 1.f;
+      qacc_int = dense_factor_solve<NR>(w, Hd, S.qfs + S.qfc);
     }
   } else {
   // ---- 8. constraint rows ----------------------------------------------------------------

@@ -186,7 +186,7 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   D.o_vec = take(32); D.o_frow = take(32); D.o_cpos = take(3 * m.ncon); D.o_cframe = take(9 * m.ncon);
   D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = take(nv * DIAL_MAXCHAIN); D.o_crb = take(10 * nb); D.o_cfs = take(6 * nb);
   if (D.dense) {
-    D.o_Md = take(nv * nv); D.o_Ld = take(nv * nv); D.o_Jd = take(D.nrow_c * nv); D.o_Gd = take(D.nrow_c * nv);
+    D.o_Md = take(nv * nv); D.o_Ld = 0; D.o_Jd = take(D.nrow_c * nv); D.o_Gd = take(D.nrow_c * nv);
     D.o_frow2 = take(D.nrow_c); D.o_cact = take(DIAL_MAXC);
   }
   D.warp_floats = o;
@@ -195,7 +195,7 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
 
 // which solver instantiation fits the model: 1 = star<3,6>, 2 = star<5,7>, 0 = generic tree
 static inline int star_variant(const DevModel& D) {
-  if (D.dense) return 3;
+  if (D.dense) return D.m.nv == 22 ? 3 : -1;   // dense path is instantiated for nv = 22 (Allegro)
   if (D.star_nchain >= 1 && D.star_nchain <= 4) {
     int maxchain = 0;
     for (int i = 0; i < D.m.nv; ++i) maxchain = D.dof_nchain[i] > maxchain ? D.dof_nchain[i] : maxchain;

@@ -63,12 +63,24 @@ __global__ void __launch_bounds__(WPC * 32, (WPC > 8 ? 1 : 16 / WPC)) rollout_ke
   __syncthreads();
   mbar_wait(&bar, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* slab = slabs + (size_t)warp * sM->warp_floats;
+  if (A.row_counter) {
+    // persistent warps + dynamic row assignment: the dense path has a heavy-tailed cost per row
+    for (;;) {
+      int row = 0;
+      if (lane == 0) row = (int)atomicAdd(A.row_counter, 1u);
+      row = __shfl_sync(0xffffffffu, row, 0);
+      if (row >= A.nrows) return;
+      rollout_warp<NL, NR>(sM, sP, slab, A, row, lane);
+      __syncwarp();
+    }
+  }
   int row = blockIdx.x * WPC + warp;
   if (row >= A.nrows) {
     if (!A.lockstep) return;
     row = A.nrows - 1;  // lock-step CTAs need every warp at the barriers: duplicate the last row (benign)
   }
-  rollout_warp<NL, NR>(sM, sP, slabs + (size_t)warp * sM->warp_floats, A, row, lane);
+  rollout_warp<NL, NR>(sM, sP, slab, A, row, lane);
 }
 
 // ---------------------------------------------------------------------------------
@@ -255,6 +267,7 @@ struct dial_plan {
   float* partial = nullptr;
   float* tb_partial = nullptr;
   unsigned int* counter = nullptr;
+  unsigned int* row_counter = nullptr;
   float* zeros = nullptr;                                          // [nv]
   int ybar_grid = 0;
   int64_t launches = 0;
@@ -277,6 +290,12 @@ static cudaError_t launch_rollout_t(dial_plan* p, const RolloutArgs& A, cudaStre
     configured = smem;
   }
   int grid = (A.nrows + WPC - 1) / WPC;
+  if (A.row_counter) {
+    const int resident = p->num_sms * (WPC > 8 ? 1 : 16 / WPC);
+    grid = grid < resident ? grid : resident;
+    cudaError_t e = cudaMemsetAsync(A.row_counter, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+  }
   rollout_kernel<WPC, NL, NR><<<grid, WPC * 32, smem, st>>>(p->dM, p->dP, A);
   p->launches++;
   return cudaGetLastError();
@@ -288,7 +307,7 @@ static cudaError_t launch_rollout(dial_plan* p, const RolloutArgs& A, cudaStream
   switch (p->variant) {
     case 1: return launch_rollout_t<WPC, 3, 6>(p, A, st);
     case 2: return launch_rollout_t<WPC, 5, 7>(p, A, st);
-    case 3: return launch_rollout_t<WPC, -1, 0>(p, A, st);
+    case 3: return launch_rollout_t<WPC, -1, 22>(p, A, st);
     default: return launch_rollout_t<WPC, 0, 0>(p, A, st);
   }
 }
@@ -312,6 +331,7 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
   // lock-step pays off when the warps of a CTA do similar work; the dense (elliptic) path has a
   // heavy-tailed iteration count per sample, so its warps run free (measured 172 vs 221 ms)
   A.lockstep = (wpc >= 2 && !p->hM.dense && !getenv("DIAL_NO_LOCKSTEP")) ? 1 : 0;
+  if (p->hM.dense && A.nrows > wpc * p->num_sms && !getenv("DIAL_NO_DYNAMIC_ROWS")) A.row_counter = p->row_counter;
   if (A.lockstep && !getenv("DIAL_NO_MIDSYNC")) A.lockstep = 2;  // second barrier before the Newton loop (+1-3 %)
   switch (wpc) {
     case 1: return launch_rollout<1>(p, A, st);
@@ -334,7 +354,8 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
       p->num_sms = sms;
   }
-  p->variant = getenv("DIAL_FORCE_GENERIC_TREE") ? 0 : star_variant(p->hM);
+  p->variant = (getenv("DIAL_FORCE_GENERIC_TREE") && !p->hM.dense) ? 0 : star_variant(p->hM);
+  if (p->variant < 0) { g_err = "the dense (elliptic) solver path is instantiated for nv = 22 only"; delete p; return nullptr; }
   memset(&p->hP, 0, sizeof(DevPlan));
   p->hP.c = *cfg;
   const dial_plan_desc& c = *cfg;
@@ -368,6 +389,7 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
   if ((e = cudaMalloc(&p->tb_partial, (size_t)TB_CHUNKS * H * (m.nq + m.nv + 3 * (m.nbody - 1)) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(tb_partial)");
   if ((e = cudaMalloc(&p->counter, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMalloc(counter)");
   if ((e = cudaMemset(p->counter, 0, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMemset(counter)");
+  if ((e = cudaMalloc(&p->row_counter, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMalloc(row_counter)");
   if (getenv("DIAL_DEBUG_COUNTERS")) {
     if ((e = cudaMalloc(&p->dbg, 8 * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(dbg)");
     cudaMemset(p->dbg, 0, 8 * sizeof(float));
@@ -380,7 +402,7 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
 extern "C" void dial_plan_destroy(dial_plan* p) {
   if (!p) return;
   cudaFree(p->dM); cudaFree(p->dP); cudaFree(p->traj_q); cudaFree(p->traj_qd); cudaFree(p->traj_x);
-  cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->tb_partial); cudaFree(p->counter); cudaFree(p->zeros); cudaFree(p->dbg);
+  cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->tb_partial); cudaFree(p->counter); cudaFree(p->row_counter); cudaFree(p->zeros); cudaFree(p->dbg);
   delete p;
 }
 
