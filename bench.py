@@ -75,7 +75,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    rows = 256
+    rows = 128
     for _ in range(args.warmup and 1):
         oracle_throughput(rows, 1, cores)
     vals, t_all = [], 0.0
