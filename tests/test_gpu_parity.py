@@ -236,3 +236,33 @@ print("GENERIC_OK")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
     assert "GENERIC_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_deploy_planner_cycle_over_shared_memory(built):
+    """the async planner (deploy/dial_plan.py) attached to the reference's six shm
+    segments: one planning cycle publishes finite joint targets / torques / refs and time-shifts."""
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.deploy.dial_plan import MBDPublisher
+    import dial_mpc_b200.envs as E
+    cfg = DialConfig(env_name="unitree_go2_walk", Nsample=256, Hsample=16, Hnode=4, Ndiffuse=1, Ndiffuse_init=2,
+                     temp_sample=0.05)
+    ecfg = E.UnitreeGo2EnvConfig(default_vx=0.8, ramp_up_time=1.0)
+    env = E.get_environment(cfg.env_name, config=ecfg)
+    pub = MBDPublisher(env, ecfg, cfg, create_shm=True)      # the test plays the simulator's role
+    try:
+        assert pub.acts_shared.shape == (17, 12) and pub.refs_shared.shape == (17, 12, 3)
+        assert pub._shm["state_shm"].size >= 37 * 32
+        out = pub.plan_once()
+        assert np.isfinite(pub.acts_shared).all() and np.isfinite(pub.tau_shared).all()
+        assert np.isfinite(pub.refs_shared).all() and pub.plan_time_shared[0] == 0.0
+        lo, hi = env.physical_joint_range[:, 0], env.physical_joint_range[:, 1]
+        assert (pub.acts_shared >= lo - 1e-5).all() and (pub.acts_shared <= hi + 1e-5).all()
+        Y_before = pub.Y.clone()
+        pub.time_shared[0] = 0.0205                              # the sim advanced (int(t / dt) truncates like the reference)
+        out2 = pub.plan_once()
+        assert pub.plan_time_shared[0] == np.float32(0.0205) and pub._state.info["step"] == 1
+        # shifting by one node period moves node k+1 onto node k (interpolating spline)
+        sh = pub.shift(Y_before, pub.mbdpi.node_dt)
+        assert torch.allclose(sh[:-1], Y_before[1:], atol=1e-5)
+    finally:
+        pub.close(unlink=True)
