@@ -66,7 +66,7 @@ dial_model_desc = _mk("dial_model_desc")
 dial_plan_desc = _mk("dial_plan_desc")
 dial_state = _mk("dial_state")
 
-ENV_IDS = {"unitree_go2_walk": 0, "unitree_go2_seq_jump": 1, "unitree_h1_walk": 2, "allegro_reorient": 3}
+ENV_IDS = {"unitree_go2_walk": 0, "unitree_go2_seq_jump": 1, "unitree_h1_walk": 2, "allegro_reorient": 3, "unitree_h1_loco": 4}
 
 
 def _set(field, value):

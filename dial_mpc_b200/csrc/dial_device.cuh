@@ -1835,7 +1835,7 @@ DEV float reward_lane0(WarpCtx& w, int step, int& stage) {
     for (int a = 0; a < m.nu; ++a) { float e = SM(qpos)[7 + a] - c.joint_offset[a]; rj -= e * e; }
     return -dot(dw, dw) - 5.f * dot(dp, dp) + 0.1f * rj;
   }
-  if (c.env_id == DIAL_ENV_GO2_WALK || c.env_id == DIAL_ENV_H1_WALK) {
+  if (c.env_id == DIAL_ENV_GO2_WALK || c.env_id == DIAL_ENV_H1_WALK || c.env_id == DIAL_ENV_H1_LOCO) {
     float ramp = stepf * c.dt / c.ramp_up_time;
     float vtx = fminf(c.vel_cmd[0] * ramp, c.vel_cmd[0]), vty = fminf(c.vel_cmd[1] * ramp, c.vel_cmd[1]);
     float atz = fminf(c.ang_cmd[2] * ramp, c.ang_cmd[2]);
@@ -1849,8 +1849,11 @@ DEV float reward_lane0(WarpCtx& w, int step, int& stage) {
         z = SM(xpos)[3 * sb + 2] + X[6] * m.site_pos[sid][0] + X[7] * m.site_pos[sid][1] + X[8] * m.site_pos[sid][2];
         float e = (zt - z) / 0.05f;
         r_gaits -= e * e;
-      } else {
+      } else if (c.env_id == DIAL_ENV_H1_WALK) {
         z = fminf(SM(cdist)[2 * f], SM(cdist)[2 * f + 1]);
+        r_gaits -= (zt - z) * (zt - z);
+      } else {   // H1 loco: two capsules (4 contacts) per foot
+        z = fminf(fminf(SM(cdist)[4 * f], SM(cdist)[4 * f + 1]), fminf(SM(cdist)[4 * f + 2], SM(cdist)[4 * f + 3]));
         r_gaits -= (zt - z) * (zt - z);
       }
     }
@@ -1863,6 +1866,18 @@ DEV float reward_lane0(WarpCtx& w, int step, int& stage) {
     float r_h = -(bk.pos.z - c.pos_tar[2]) * (bk.pos.z - c.pos_tar[2]);
     if (c.env_id == DIAL_ENV_GO2_WALK) {
       rew = 0.1f * r_gaits + 0.5f * r_upright + 0.3f * r_yaw + r_vel + r_ang + r_h;
+    } else if (c.env_id == DIAL_ENV_H1_LOCO) {
+      // unitree_h1_env.py:774-800: all three body-rate components, foot-level and energy terms
+      float atx = fminf(c.ang_cmd[0] * ramp, c.ang_cmd[0]), aty = fminf(c.ang_cmd[1] * ramp, c.ang_cmd[1]);
+      float r_ang3 = -((bk.ab.x - atx) * (bk.ab.x - atx) + (bk.ab.y - aty) * (bk.ab.y - aty) + (bk.ab.z - atz) * (bk.ab.z - atz));
+      float r_level = 0.f;
+      for (int f = 0; f < c.nfeet; ++f) {
+        const float* X = SM(xmat) + 9 * m.site_bodyid[c.feet_site[f]];
+        r_level -= X[2] * X[2] + X[5] * X[5] + (X[8] - 1.f) * (X[8] - 1.f);
+      }
+      float r_energy = 0.f;
+      for (int a = 0; a < m.nu; ++a) { float e = SM(ctrl)[a] / c.joint_torque_range[a][1] * SM(qvel)[6 + a] / 160.f; r_energy -= e * e; }
+      rew = 10.f * r_gaits + 0.5f * r_upright + 0.5f * r_yaw + r_vel + r_ang3 + 0.5f * r_h + 0.02f * r_level + 0.01f * r_energy;
     } else {
       float r_energy = 0.f;
       for (int a = 0; a < m.nu; ++a) { float e = SM(ctrl)[a] / c.joint_torque_range[a][1]; r_energy -= e * e; }

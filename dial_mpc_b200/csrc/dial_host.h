@@ -201,6 +201,7 @@ static inline int star_variant(const DevModel& D) {
     for (int i = 0; i < D.m.nv; ++i) maxchain = D.dof_nchain[i] > maxchain ? D.dof_nchain[i] : maxchain;
     if (D.star_nroot == 6 && D.star_maxlen <= 3 && maxchain <= 9) return 1;
     if (D.star_nroot == 7 && D.star_maxlen <= 5) return 2;
+    if (D.star_nroot == 6 && D.star_maxlen <= 5) return 4;
   }
   return 0;
 }

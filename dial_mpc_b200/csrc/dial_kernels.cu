@@ -308,6 +308,7 @@ static cudaError_t launch_rollout(dial_plan* p, const RolloutArgs& A, cudaStream
     case 1: return launch_rollout_t<WPC, 3, 6>(p, A, st);
     case 2: return launch_rollout_t<WPC, 5, 7>(p, A, st);
     case 3: return launch_rollout_t<WPC, -1, 22>(p, A, st);
+    case 4: return launch_rollout_t<WPC, 5, 6>(p, A, st);
     default: return launch_rollout_t<WPC, 0, 0>(p, A, st);
   }
 }
@@ -365,7 +366,7 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
     delete p;
     return nullptr;
   }
-  if (c.env_id < DIAL_ENV_GO2_WALK || c.env_id > DIAL_ENV_ALLEGRO) { g_err = "unknown env_id"; delete p; return nullptr; }
+  if (c.env_id < DIAL_ENV_GO2_WALK || c.env_id > DIAL_ENV_H1_LOCO) { g_err = "unknown env_id"; delete p; return nullptr; }
   auto bad = [&](cudaError_t e, const char* what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     dial_plan_destroy(p);

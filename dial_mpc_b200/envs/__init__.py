@@ -10,7 +10,8 @@ from typing import Any, Dict, Type
 from dial_mpc_b200.envs.base_env import BaseEnv, BaseEnvConfig, PipelineState, State, System  # noqa: F401
 from dial_mpc_b200.envs.unitree_go2_env import (UnitreeGo2Env, UnitreeGo2EnvConfig, UnitreeGo2SeqJumpEnv,
                                                 UnitreeGo2SeqJumpEnvConfig)
-from dial_mpc_b200.envs.unitree_h1_env import UnitreeH1WalkEnv, UnitreeH1WalkEnvConfig
+from dial_mpc_b200.envs.unitree_h1_env import (UnitreeH1LocoEnv, UnitreeH1LocoEnvConfig, UnitreeH1WalkEnv,
+                                               UnitreeH1WalkEnvConfig)
 from dial_mpc_b200.envs.manipulation import AllegroReorientEnv, AllegroReorientEnvConfig
 
 _configs: Dict[str, Any] = {
@@ -18,6 +19,7 @@ _configs: Dict[str, Any] = {
     "unitree_go2_walk": UnitreeGo2EnvConfig,
     "unitree_go2_seq_jump": UnitreeGo2SeqJumpEnvConfig,
     "allegro_reorient": AllegroReorientEnvConfig,
+    "unitree_h1_loco": UnitreeH1LocoEnvConfig,
 }
 _envs: Dict[str, Type[BaseEnv]] = {}
 
@@ -44,3 +46,4 @@ register_environment("unitree_go2_walk", UnitreeGo2Env)
 register_environment("unitree_go2_seq_jump", UnitreeGo2SeqJumpEnv)
 register_environment("unitree_h1_walk", UnitreeH1WalkEnv)
 register_environment("allegro_reorient", AllegroReorientEnv)
+register_environment("unitree_h1_loco", UnitreeH1LocoEnv)

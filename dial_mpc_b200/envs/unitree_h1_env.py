@@ -82,3 +82,41 @@ class UnitreeH1WalkEnv(BaseEnv):
         _capi._set(d.pos_tar, self._pos_tar)
         d.n_stage = 1
         d.jump_dt = 1.0
+
+
+def _h1_loco_kp():
+    return np.array([200.0, 200.0, 200.0, 200.0, 60.0] * 2 + [200.0])
+
+
+def _h1_loco_kd():
+    return np.array([5.0, 5.0, 5.0, 5.0, 1.5] * 2 + [5.0])
+
+
+@dataclass
+class UnitreeH1LocoEnvConfig(BaseEnvConfig):
+    kp: Union[float, Any] = field(default_factory=_h1_loco_kp)
+    kd: Union[float, Any] = field(default_factory=_h1_loco_kd)
+    default_vx: float = 1.0
+    default_vy: float = 0.0
+    default_vyaw: float = 0.0
+    ramp_up_time: float = 2.0
+    gait: str = "jog"
+
+
+class UnitreeH1LocoEnv(UnitreeH1WalkEnv):
+    """``UnitreeH1LocoEnv`` (dial_mpc/envs/unitree_h1_env.py:609-902): legs + torso
+    actuated, arms welded, two capsules per foot, one Newton / line-search iteration."""
+    env_id = _capi.ENV_IDS["unitree_h1_loco"]
+
+    def __init__(self, config: UnitreeH1LocoEnvConfig):
+        super().__init__(config)
+        self._gait_params = {  # ratio, cadence, amplitude
+            "stand": np.array([1.0, 1.0, 0.0]), "slow_walk": np.array([0.6, 0.8, 0.15]),
+            "walk": np.array([0.5, 1.5, 0.10]), "jog": np.array([0.3, 2.0, 0.2])}
+        self.joint_range = np.array(
+            [[-0.2, 0.2], [-0.2, 0.2], [-0.6, 0.6], [0.0, 1.5], [-0.6, 0.4]] * 2 + [[-0.5, 0.5]])
+
+    def make_system(self, config) -> System:
+        model_path = get_model_path("unitree_h1", "mjx_scene_h1_loco.xml")
+        sys = System(CompiledModel.load(model_path))
+        return sys.tree_replace({"opt.timestep": config.timestep})

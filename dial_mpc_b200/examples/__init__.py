@@ -4,4 +4,5 @@ examples = [
     "unitree_go2_trot",
     "unitree_go2_seq_jump",
     "allegro_reorient",
+    "unitree_h1_loco",
 ]

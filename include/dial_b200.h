@@ -47,6 +47,7 @@ enum {
   DIAL_ENV_GO2_SEQJUMP = 1, /* UnitreeGo2SeqJumpEnv.step  envs/unitree_go2_env.py:403-521 */
   DIAL_ENV_H1_WALK = 2,     /* UnitreeH1WalkEnv.step      envs/unitree_h1_env.py:181-321  */
   DIAL_ENV_ALLEGRO = 3,     /* AllegroReorientEnv.step    envs/manipulation.py:63-100     */
+  DIAL_ENV_H1_LOCO = 4,     /* UnitreeH1LocoEnv.step      envs/unitree_h1_env.py:686-830  */
 };
 
 /* Compiled robot model: what `brax.io.mjcf.load` + `mjx.put_model` give the reference

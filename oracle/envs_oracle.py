@@ -298,6 +298,54 @@ class H1WalkOracle(OracleEnv):
         return rew, s.stage
 
 
+class H1LocoOracle(H1WalkOracle):
+    """UnitreeH1LocoEnv.step (dial_mpc/envs/unitree_h1_env.py:686-830): 11 actuated joints (arms
+    welded), two capsules per foot (8 contacts), iterations = ls_iterations = 1."""
+    model_file = "unitree_h1_mjx_scene_h1_loco.json"
+    GAIT_PARAMS = {"stand": (1.0, 1.0, 0.0), "slow_walk": (0.6, 0.8, 0.15), "walk": (0.5, 1.5, 0.10),
+                   "jog": (0.3, 2.0, 0.2)}
+    KP = [200.0, 200.0, 200.0, 200.0, 60.0] * 2 + [200.0]
+    KD = [5.0, 5.0, 5.0, 5.0, 1.5] * 2 + [5.0]
+
+    def __init__(self, **kw):
+        kw.setdefault("kp", self.KP)
+        kw.setdefault("kd", self.KD)
+        super().__init__(**kw)
+        self.joint_range = np.array([[-0.2, 0.2], [-0.2, 0.2], [-0.6, 0.6], [0.0, 1.5], [-0.6, 0.4]] * 2 + [[-0.5, 0.5]])
+        self.feet_site = [self.m.names["site"].index(n) for n in ("left_foot", "right_foot")]
+
+    def reward(self, s, qpos, qvel, d, ctrl):
+        v = mo.brax_views(self.m, d)
+        stepf = s.step.astype(np.float64)
+        ramp = stepf[:, None] * self.dt / self.ramp_up_time
+        vel_tar = np.minimum(self.vel_cmd * ramp, self.vel_cmd)
+        ang_tar = np.minimum(self.ang_cmd * ramp, self.ang_cmd)
+        duty, cad, amp = self.GAIT_PARAMS[self.gait]
+        z_tar = get_foot_step(duty, cad, amp, self.GAIT_PHASE[self.gait], stepf * self.dt)
+        z_feet = np.stack([d.con_dist[:, 0:4].min(-1), d.con_dist[:, 4:8].min(-1)], -1)
+        r_gaits = -np.sum((z_tar - z_feet) ** 2, -1)
+        up = np.array([0.0, 0.0, 1.0])
+        r_upright = -np.sum((rotate(up, v["x_rot"][:, 0]) - up) ** 2, -1)
+        rot_b = v["x_rot"][:, self.torso]
+        yaw_tar = 0.0 + ang_tar[:, 2] * self.dt * stepf
+        dyaw = quat_to_euler(rot_b)[:, 2] - yaw_tar
+        r_yaw = -np.arctan2(np.sin(dyaw), np.cos(dyaw)) ** 2
+        vb = inv_rotate(v["xd_vel"][:, self.torso], rot_b)
+        ab = inv_rotate(v["xd_ang"][:, self.torso] * np.pi / 180.0, rot_b)
+        r_vel = -np.sum((vb[:, :2] - vel_tar[:, :2]) ** 2, -1)
+        r_angvel = -np.sum((ab - ang_tar) ** 2, -1)
+        r_height = -(v["x_pos"][:, self.torso, 2] - self.pos_tar[2]) ** 2
+        r_level = 0.0
+        for sid in self.feet_site:
+            zc = d.xmat[:, self.m.site_bodyid[sid], :, 2]        # site frame = body frame (no site quat)
+            r_level = r_level - np.sum((zc - up) ** 2, -1)
+        nj = len(self.joint_range)
+        r_energy = -np.sum((ctrl / self.joint_torque_range[:, 1] * qvel[:, 6:6 + nj] / 160.0) ** 2, -1)
+        rew = (10.0 * r_gaits + 0.5 * r_upright + 0.5 * r_yaw + r_vel + r_angvel + 0.5 * r_height
+               + 0.02 * r_level + 0.01 * r_energy)
+        return rew, s.stage
+
+
 class AllegroReorientOracle(OracleEnv):
     """AllegroReorientEnv (dial_mpc/envs/manipulation.py:23-115): position targets, 4 substeps."""
     model_file = "wonik_allegro_scene_left.json"
@@ -331,5 +379,5 @@ class AllegroReorientOracle(OracleEnv):
 def make_env(env_name: str, cfg: Optional[Dict] = None) -> OracleEnv:
     cfg = dict(cfg or {})
     cls = {"unitree_go2_walk": Go2WalkOracle, "unitree_go2_seq_jump": Go2SeqJumpOracle,
-           "unitree_h1_walk": H1WalkOracle, "allegro_reorient": AllegroReorientOracle}[env_name]
+           "unitree_h1_walk": H1WalkOracle, "allegro_reorient": AllegroReorientOracle, "unitree_h1_loco": H1LocoOracle}[env_name]
     return cls(**cfg)

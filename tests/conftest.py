@@ -32,6 +32,7 @@ ENV_CASES = {
         yaw_target_sequence=[0.0] * 5),
     "unitree_h1_walk": dict(default_vx=2.0, ramp_up_time=3.0),
     "allegro_reorient": dict(dt=0.02, timestep=0.005, leg_control="position"),
+    "unitree_h1_loco": dict(default_vx=0.6, ramp_up_time=3.0, gait="walk"),
 }
 
 

@@ -21,7 +21,7 @@ from tests.conftest import ENV_CASES  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 CASES = {"unitree_go2_walk": (16, 4, 32), "unitree_go2_seq_jump": (25, 5, 32), "unitree_h1_walk": (30, 5, 16),
-         "allegro_reorient": (8, 4, 16)}
+         "allegro_reorient": (8, 4, 16), "unitree_h1_loco": (20, 5, 16)}
 
 
 def main():

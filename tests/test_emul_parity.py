@@ -8,7 +8,8 @@ from tests.conftest import ENV_CASES, make_pair
 from tests.emul import emul
 
 
-@pytest.mark.parametrize("name,H", [("unitree_go2_walk", 12), ("unitree_go2_seq_jump", 12), ("unitree_h1_walk", 10)])
+@pytest.mark.parametrize("name,H", [("unitree_go2_walk", 12), ("unitree_go2_seq_jump", 12), ("unitree_h1_walk", 10),
+                                    ("unitree_h1_loco", 10)])
 def test_emulated_rollout_matches_oracle(name, H):
     env, o = make_pair(name)
     s = o.reset()

@@ -24,7 +24,7 @@ def _state_from(env, qpos, qvel, warm, step=0, stage=0):
 
 
 @pytest.mark.parametrize("name,H", [("unitree_go2_walk", 17), ("unitree_go2_seq_jump", 26), ("unitree_h1_walk", 31),
-                                    ("allegro_reorient", 6)])
+                                    ("allegro_reorient", 6), ("unitree_h1_loco", 21)])
 def test_rollout_matches_oracle(built, name, H):
     from dial_mpc_b200 import random as drandom
     env, o = make_pair(name)
