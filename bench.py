@@ -282,9 +282,18 @@ def run_own(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / t_kernel / 1e9
-    traffic = None
+    traffic, fp32 = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "rollout_traffic.json")))["dram_bytes_per_launch"]
+        prof = json.load(open(os.path.join(ROOT, "profiles", "rollout_traffic.json")))
+        traffic = prof["dram_bytes_per_launch"]
+        # compute-side view (the binding resource): flop per physics step counted by ncu (committed
+        # capture) x physics steps per second measured live, against the nominal fp32 peak
+        fpp = prof["fp32"]["flop_per_physics_step"]
+        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        peak_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        ach_tf = fpp * rows * H / t_kernel / 1e12
+        fp32 = dict(flop_per_physics_step=fpp, achieved_tflops=ach_tf, peak_tflops=peak_tf, frac=ach_tf / peak_tf,
+                    peak_source="nominal 148 SM x 128 FFMA/clk x 2 x sm_max_mhz", flop_source="ncu capture profiles/rollout_traffic.json")
     except Exception:
         pass
     roofline = dict(bound="hbm", kernel="rollout_kernel", achieved=achieved, peak=peak, unit="GB/s",
@@ -293,7 +302,7 @@ def run_own(args):
                     kernel_share_of_step=cfg.Ndiffuse * t_kernel / (t_dev / args.steps),
                     note=("the path is fp32-issue/latency bound (~140 flop/B, SURVEY.md 8d): the HBM fraction is "
                           "reported as required but cannot approach 1; see DESIGN.md"),
-                    physics_steps_per_s=rows * H / t_kernel)
+                    physics_steps_per_s=rows * H / t_kernel, fp32=fp32)
 
     if rank != 0:
         if world > 1:
