@@ -92,6 +92,9 @@ class MBDPI:
         self._weights = torch.empty(N + 1, dtype=torch.float32, device=dev)
         m = env.sys
         self._bars = torch.empty(Hs1 * (m.nq + m.nv + 3 * (m.nbody - 1)), dtype=torch.float32, device=dev)
+        # the info-only bars (+ their allreduce) run on a side stream and overlap the next rollout
+        self._side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._bar_events = []
 
     # -- spline maps (dial_core.py:82-101) -------------------------------------------------------
     def node2u(self, nodes):
@@ -122,7 +125,7 @@ class MBDPI:
         return rewss, (q, qd, x)
 
     # -- the hot path (dial_core.py:103-145) ----------------------------------------------------------
-    def reverse_once(self, state, rng, Ybar_i, noise_scale, eps=None):
+    def reverse_once(self, state, rng, Ybar_i, noise_scale, eps=None, _sync_bars=True):
         """One annealing iteration.  ``eps`` (optional, [Nsample,Hnode+1,nu]) injects the noise;
         otherwise it is drawn in-kernel from the Threefry stream keyed by ``split(rng)[1]``."""
         rng, Y0s_rng = drandom.split(rng)
@@ -132,6 +135,9 @@ class MBDPI:
             eps = self.plan.f32(eps, (self.args.Nsample, self.args.Hnode + 1, self.nu))
         key = None if eps is not None else Y0s_rng
         N, Nl = self.args.Nsample, self.Nlocal
+        if self._side is not None and len(self._bar_events) >= 2:
+            # the trajectory buffer about to be overwritten was read by the bars two iterations ago
+            torch.cuda.current_stream().wait_event(self._bar_events.pop(0))
         self.plan.reverse_rollout(state, eps, key, Ybar_i, noise_scale, self._rews_local)
         if self.world_size > 1:
             import torch.distributed as dist
@@ -141,18 +147,35 @@ class MBDPI:
         else:
             rews_all = self._rews_local
         Ybar = torch.empty_like(Ybar_i)
-        self.plan.reverse_update(eps, key, Ybar_i, noise_scale, rews_all, Ybar, self._weights)
-        info: Dict[str, Any] = {"rews": rews_all.clone(), "new_noise_scale": noise_scale, "weights": self._weights}
+        weights = torch.empty_like(self._weights)
+        self.plan.reverse_update(eps, key, Ybar_i, noise_scale, rews_all, Ybar, weights)
+        info: Dict[str, Any] = {"rews": rews_all.clone(), "new_noise_scale": noise_scale, "weights": weights}
         if self.compute_bars:
             m = self.env.sys
             Hs1 = self.args.Hsample + 1
             n1, n2 = Hs1 * m.nq, Hs1 * m.nv
             bars = torch.empty_like(self._bars)
             qbar, qdbar, xbar = bars[:n1], bars[n1:n1 + n2], bars[n1 + n2:]
-            self.plan.reverse_trajbar(self._weights, self.rank, qbar, qdbar, xbar)
-            if self.world_size > 1:
-                import torch.distributed as dist
-                dist.all_reduce(bars, group=self.pg)
+            main = torch.cuda.current_stream() if self._side is not None else None
+            if self._side is not None:
+                self._side.wait_stream(main)
+                ctx = torch.cuda.stream(self._side)
+            else:
+                import contextlib
+                ctx = contextlib.nullcontext()
+            with ctx:
+                self.plan.reverse_trajbar(weights, self.rank, qbar, qdbar, xbar)
+                if self.world_size > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(bars, group=self.pg)
+                if self._side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(self._side)
+                    self._bar_events.append(ev)
+                    for t in (bars, weights):
+                        t.record_stream(self._side)
+            if self._side is not None and _sync_bars:
+                main.wait_stream(self._side)
             info["qbar"] = qbar.view(Hs1, m.nq)
             info["qdbar"] = qdbar.view(Hs1, m.nv)
             info["xbar"] = xbar.view(Hs1, m.nbody - 1, 3)
@@ -161,8 +184,9 @@ class MBDPI:
     def reverse_scan(self, state, rng, Y0, factors):
         """``lax.scan(reverse_scan, (rng, Y0, state), factors)`` of dial_core.py:177-180,262-264."""
         info = None
-        for i in range(factors.shape[0]):
-            rng, Y0, info = self.reverse_once(state, rng, Y0, factors[i])
+        n = factors.shape[0]
+        for i in range(n):
+            rng, Y0, info = self.reverse_once(state, rng, Y0, factors[i], _sync_bars=(i == n - 1))
         return rng, Y0, info
 
     def schedule(self, n_diffuse: int) -> torch.Tensor:

@@ -28,15 +28,11 @@
 #else
 #define HD __host__ __device__ __forceinline__
 #define DEV __device__ __forceinline__
-#define DEVNI __device__ __noinline__
 DEV void syncwarp() { __syncwarp(); }
 DEV float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEV int shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 DEV void cta_sync() { __syncthreads(); }
-#endif
-#ifndef DEVNI
-#define DEVNI inline
 #endif
 
 #define DIAL_MAXCHAIN 12   // longest dof ancestor chain (H1: 6 + 5 = 11)
@@ -113,7 +109,7 @@ struct RolloutArgs {
   float* warm_out;
   float* ctrl_out;
   unsigned int* row_counter;  // non-null: persistent warps pull rows from this counter (dense path)
-  float* dbg;           // optional debug dump (tests)
+  float* dbg;           // optional device counters (DIAL_DEBUG_COUNTERS, see dial_debug_counters)
 };
 
 // ---------------------------------------------------------------------------------

@@ -262,7 +262,10 @@ struct dial_plan {
   int num_sms = 148;
   size_t smem_bytes = 0;
   // workspaces
-  float *traj_q = nullptr, *traj_qd = nullptr, *traj_x = nullptr;  // [Nsample+1, Hs+1, *]
+  // trajectory workspaces [Nsample+1, Hs+1, *], double-buffered so that the bars of iteration i
+  // (side stream) can overlap the rollout of iteration i+1
+  float *traj_q[2] = {nullptr, nullptr}, *traj_qd[2] = {nullptr, nullptr}, *traj_x[2] = {nullptr, nullptr};
+  int cur = 0;
   float* weights = nullptr;                                        // [Ntotal+1]
   float* partial = nullptr;
   float* tb_partial = nullptr;
@@ -379,9 +382,11 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
   if ((e = cudaMemcpy(p->dP, &p->hP, sizeof(DevPlan), cudaMemcpyHostToDevice)) != cudaSuccess) return bad(e, "cudaMemcpy(plan)");
   const size_t rows = (size_t)c.Nsample + 1, H = (size_t)c.Hsample + 1;
   const dial_model_desc& m = *model;
-  if ((e = cudaMalloc(&p->traj_q, rows * H * m.nq * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(traj_q)");
-  if ((e = cudaMalloc(&p->traj_qd, rows * H * m.nv * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(traj_qd)");
-  if ((e = cudaMalloc(&p->traj_x, rows * H * 3 * (m.nbody - 1) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(traj_x)");
+  for (int b = 0; b < 2; ++b) {
+    if ((e = cudaMalloc(&p->traj_q[b], rows * H * m.nq * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(traj_q)");
+    if ((e = cudaMalloc(&p->traj_qd[b], rows * H * m.nv * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(traj_qd)");
+    if ((e = cudaMalloc(&p->traj_x[b], rows * H * 3 * (m.nbody - 1) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(traj_x)");
+  }
   if ((e = cudaMalloc(&p->weights, ((size_t)c.Ntotal + 1) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(weights)");
   const int ne = (c.Hnode + 1) * m.nu, slots = YBAR_THREADS / ne;
   int g = (c.Ntotal + 1 + slots - 1) / slots;
@@ -402,7 +407,8 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
 
 extern "C" void dial_plan_destroy(dial_plan* p) {
   if (!p) return;
-  cudaFree(p->dM); cudaFree(p->dP); cudaFree(p->traj_q); cudaFree(p->traj_qd); cudaFree(p->traj_x);
+  cudaFree(p->dM); cudaFree(p->dP);
+  for (int b = 0; b < 2; ++b) { cudaFree(p->traj_q[b]); cudaFree(p->traj_qd[b]); cudaFree(p->traj_x[b]); }
   cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->tb_partial); cudaFree(p->counter); cudaFree(p->row_counter); cudaFree(p->zeros); cudaFree(p->dbg);
   delete p;
 }
@@ -453,7 +459,8 @@ extern "C" int dial_reverse_rollout(dial_plan* p, const dial_state* s, const flo
   A.nrows = c.Nsample + 1; A.H = c.Hsample + 1; A.mode = 1;
   A.eps = eps; A.Ybar = Ybar; A.noise = noise_scale;
   if (key) { A.key0 = key[0]; A.key1 = key[1]; }
-  A.rews = rews_local; A.q = p->traj_q; A.qd = p->traj_qd; A.xpos = p->traj_x;
+  p->cur ^= 1;
+  A.rews = rews_local; A.q = p->traj_q[p->cur]; A.qd = p->traj_qd[p->cur]; A.xpos = p->traj_x[p->cur];
   A.dbg = p->dbg;
   CUDA_OK(launch_rollout_any(p, A, (cudaStream_t)stream));
   return 0;
@@ -488,7 +495,7 @@ extern "C" int dial_reverse_trajbar(dial_plan* p, const float* weights, int rank
   const float* w = weights ? weights : p->weights;
   const int H = c.Hsample + 1, rows = c.Nsample + 1;
   TrajArgs T;
-  T.traj[0] = p->traj_q; T.traj[1] = p->traj_qd; T.traj[2] = p->traj_x;
+  T.traj[0] = p->traj_q[p->cur]; T.traj[1] = p->traj_qd[p->cur]; T.traj[2] = p->traj_x[p->cur];
   T.out[0] = qbar; T.out[1] = qdbar; T.out[2] = xbar;
   T.ncol[0] = m.nq; T.ncol[1] = m.nv; T.ncol[2] = 3 * (m.nbody - 1);
   T.coloff[0] = 0; T.coloff[1] = m.nq; T.coloff[2] = m.nq + m.nv;

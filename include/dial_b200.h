@@ -165,7 +165,10 @@ int dial_pipeline_init(dial_plan* plan, const float* qpos, const float* qvel,
  * `key`), pin node 0, append the mean row, clip, spline to actions, roll out
  * this rank's shard + the mean sample and write per-sample mean rewards
  * rews_local [dev][Nsample+1] (mean sample last).  Trajectories
- * (q/qd/xpos [Nsample+1,Hs+1,*]) are kept in the plan's workspace. */
+ * (q/qd/xpos [Nsample+1,Hs+1,*]) are kept in the plan's workspace, which is double-buffered:
+ * dial_reverse_trajbar enqueued (on any stream, after the matching update) before the NEXT
+ * dial_reverse_rollout reads the buffer of this rollout, so it may overlap the next rollout;
+ * the buffer is reused by the rollout after next. */
 int dial_reverse_rollout(dial_plan* plan, const dial_state* s, const float* eps,
                          const uint32_t key[2], const float* Ybar /*[dev][Hn+1,nu]*/,
                          const float* noise_scale /*[dev][Hn+1]*/, float* rews_local,
