@@ -130,3 +130,20 @@ def test_mbdpi_host_math_without_gpu():
     assert mb.ctrl_dt == 0.02 and abs(mb.node_dt - 0.08) < 1e-12 and mb.nu == 12
     sh = mb.shift_Y_from_u(torch.ones(17, 12), 2)
     assert sh.shape == (5, 12) and abs(float(sh[-1, 0])) < 1e-5
+
+
+def test_deploy_shm_layout_and_time_shift():
+    """deploy/dial_plan.py: segment sizes follow the reference (x32 over-allocation),
+    and the plan time-shift is the node spline evaluated at shifted node times."""
+    from dial_mpc_b200.deploy.dial_plan import shm_layout
+    from dial_mpc_b200.utils.spline import interp_matrix
+    lay = shm_layout(n_acts=17, nx=37, nu=12)
+    assert lay["acts_shm"] == ((17, 12), 17 * 12 * 32) and lay["refs_shm"] == ((17, 12, 3), 17 * 12 * 3 * 32)
+    assert lay["state_shm"] == ((37,), 37 * 32) and lay["time_shm"][1] == 32 and lay["plan_time_shm"][1] == 32
+    nodes = np.linspace(0, 0.32, 5)
+    M = interp_matrix(nodes, nodes + 0.08)               # one node period: node k+1 moves onto node k
+    assert np.abs(M[:4] - np.eye(5)[1:]).max() < 1e-12
+    y = np.random.default_rng(0).standard_normal(5)
+    from scipy.interpolate import InterpolatedUnivariateSpline
+    for dt in (0.013, 0.02, 0.055):
+        assert np.abs(interp_matrix(nodes, nodes + dt) @ y - InterpolatedUnivariateSpline(nodes, y, k=2)(nodes + dt)).max() < 1e-12
