@@ -33,6 +33,8 @@ DEV float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEV int shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 DEV void cta_sync() { __syncthreads(); }
+DEV void fast_sincos(float x, float& s, float& c) { __sincosf(x, &s, &c); }
+DEV float fast_cos(float x) { return __cosf(x); }
 #endif
 
 #define DIAL_MAXCHAIN 12   // longest dof ancestor chain (H1: 6 + 5 = 11)
@@ -155,7 +157,8 @@ DEV void qmat(Q4 q, float* m) {  // row-major 3x3
   m[6] = 2.f * (x * z - w * y); m[7] = 2.f * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
 }
 DEV Q4 axisangle(V3 axis, float angle) {
-  float s = sinf(0.5f * angle), c = cosf(0.5f * angle);
+  float s, c;
+  fast_sincos(0.5f * angle, s, c);   // |angle/2| < pi: SFU sin/cos (abs err ~4e-7), same code in every instantiation
   Q4 q; q.w = c; q.x = axis.x * s; q.y = axis.y * s; q.z = axis.z * s; return q;
 }
 
@@ -1785,7 +1788,7 @@ DEV float foot_step(float duty, float cadence, float amplitude, float phase, flo
   float angle = a - floorf(a / TWO_PI) * TWO_PI - PI;
   if (duty < 1.f) angle *= 0.5f / (1.f - duty);
   float cl = fminf(fmaxf(angle, -0.5f * PI), 0.5f * PI);
-  float value = duty < 1.f ? cosf(cl) : 0.f;
+  float value = duty < 1.f ? fast_cos(cl) : 0.f;   // |cl| <= pi/2
   float fin = fabsf(value) >= 1e-6f ? fabsf(value) : 0.f;
   return amplitude * fin;
 }
@@ -1855,7 +1858,8 @@ DEV float reward_lane0(WarpCtx& w, int step, int& stage) {
     }
     float yaw_tar = 0.f + atz * c.dt * stepf;
     float dyaw = quat_yaw(bk.rot) - yaw_tar;
-    float wy = atan2f(sinf(dyaw), cosf(dyaw));
+    // atan2(sin d, cos d) == d wrapped to (-pi, pi]
+    float wy = dyaw - 6.28318530717959f * rintf(dyaw * 0.159154943091895f);
     float r_yaw = -wy * wy;
     float r_vel = -((bk.vb.x - vtx) * (bk.vb.x - vtx) + (bk.vb.y - vty) * (bk.vb.y - vty));
     float r_ang = -(bk.ab.z - atz) * (bk.ab.z - atz);
