@@ -66,7 +66,8 @@ dial_model_desc = _mk("dial_model_desc")
 dial_plan_desc = _mk("dial_plan_desc")
 dial_state = _mk("dial_state")
 
-ENV_IDS = {"unitree_go2_walk": 0, "unitree_go2_seq_jump": 1, "unitree_h1_walk": 2, "allegro_reorient": 3, "unitree_h1_loco": 4}
+ENV_IDS = {"unitree_go2_walk": 0, "unitree_go2_seq_jump": 1, "unitree_h1_walk": 2, "allegro_reorient": 3, "unitree_h1_loco": 4,
+           "custom": 5}
 
 
 def _set(field, value):
@@ -108,53 +109,58 @@ def fill_model_desc(cm) -> dial_model_desc:
     return d
 
 
-class _Lib:
-    _lib: Optional[C.CDLL] = None
-
-    @classmethod
-    def get(cls) -> C.CDLL:
-        if cls._lib is None:
-            if not os.path.exists(LIB_PATH):
-                raise RuntimeError(
-                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`."
-                    " There is no CPU fallback for the DIAL-MPC sampling core.")
-            lib = C.CDLL(LIB_PATH)
-            lib.dial_abi_version.restype = C.c_int
-            lib.dial_last_error.restype = C.c_char_p
-            lib.dial_sizeof.restype = C.c_size_t
-            lib.dial_sizeof.argtypes = [C.c_int]
-            lib.dial_plan_create.restype = C.c_void_p
-            lib.dial_plan_create.argtypes = [C.POINTER(dial_model_desc), C.POINTER(dial_plan_desc)]
-            lib.dial_plan_destroy.argtypes = [C.c_void_p]
-            lib.dial_plan_destroy.restype = None
-            P, I, V = C.c_void_p, C.c_int, C.c_void_p
-            lib.dial_rollout.argtypes = [V, C.POINTER(dial_state), P, I, I, P, P, P, P, V]
-            lib.dial_env_step.argtypes = [V, C.POINTER(dial_state), P, P, P, P, P, P, V]
-            lib.dial_pipeline_init.argtypes = [V, P, P, P, P, V]
-            U2 = C.POINTER(C.c_uint32)
-            lib.dial_reverse_rollout.argtypes = [V, C.POINTER(dial_state), P, U2, P, P, P, V]
-            lib.dial_reverse_update.argtypes = [V, P, U2, P, P, P, P, P, V]
-            lib.dial_reverse_trajbar.argtypes = [V, P, I, P, P, P, V]
-            lib.dial_key_split.argtypes = [U2, U2, U2]
-            lib.dial_key_split.restype = None
-            lib.dial_launch_count.argtypes = [V]
-            lib.dial_launch_count.restype = C.c_int64
-            lib.dial_debug_counters.argtypes = [V, C.POINTER(C.c_float)]
-            lib.dial_debug_counters.restype = C.c_int
-            for fn in ("dial_rollout", "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout",
-                       "dial_reverse_update", "dial_reverse_trajbar"):
-                getattr(lib, fn).restype = C.c_int
-            if lib.dial_abi_version() != DEFINES["DIAL_ABI_VERSION"]:
-                raise RuntimeError("libdial_b200.so ABI version does not match include/dial_b200.h")
-            for i, t in enumerate((dial_model_desc, dial_plan_desc, dial_state)):
-                if lib.dial_sizeof(i) != C.sizeof(t):
-                    raise RuntimeError(f"struct layout mismatch for {t.__name__}: C {lib.dial_sizeof(i)} vs ctypes {C.sizeof(t)}")
-            cls._lib = lib
-        return cls._lib
+def _bind(path: str) -> C.CDLL:
+    """dlopen one build of the library and declare its prototypes; checks ABI + struct layout."""
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`."
+            " There is no CPU fallback for the DIAL-MPC sampling core.")
+    lib = C.CDLL(path)
+    lib.dial_abi_version.restype = C.c_int
+    lib.dial_last_error.restype = C.c_char_p
+    lib.dial_sizeof.restype = C.c_size_t
+    lib.dial_sizeof.argtypes = [C.c_int]
+    lib.dial_plan_create.restype = C.c_void_p
+    lib.dial_plan_create.argtypes = [C.POINTER(dial_model_desc), C.POINTER(dial_plan_desc)]
+    lib.dial_plan_destroy.argtypes = [C.c_void_p]
+    lib.dial_plan_destroy.restype = None
+    P, I, V = C.c_void_p, C.c_int, C.c_void_p
+    lib.dial_rollout.argtypes = [V, C.POINTER(dial_state), P, I, I, P, P, P, P, V]
+    lib.dial_env_step.argtypes = [V, C.POINTER(dial_state), P, P, P, P, P, P, V]
+    lib.dial_pipeline_init.argtypes = [V, P, P, P, P, V]
+    U2 = C.POINTER(C.c_uint32)
+    lib.dial_reverse_rollout.argtypes = [V, C.POINTER(dial_state), P, U2, P, P, P, V]
+    lib.dial_reverse_update.argtypes = [V, P, U2, P, P, P, P, P, V]
+    lib.dial_reverse_trajbar.argtypes = [V, P, I, P, P, P, V]
+    lib.dial_key_split.argtypes = [U2, U2, U2]
+    lib.dial_key_split.restype = None
+    lib.dial_launch_count.argtypes = [V]
+    lib.dial_launch_count.restype = C.c_int64
+    lib.dial_debug_counters.argtypes = [V, C.POINTER(C.c_float)]
+    lib.dial_debug_counters.restype = C.c_int
+    lib.dial_solver_variant.argtypes = [C.POINTER(dial_model_desc)]
+    lib.dial_solver_variant.restype = C.c_int
+    lib.dial_custom_reward_id.restype = C.c_char_p
+    for fn in ("dial_rollout", "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout",
+               "dial_reverse_update", "dial_reverse_trajbar"):
+        getattr(lib, fn).restype = C.c_int
+    if lib.dial_abi_version() != DEFINES["DIAL_ABI_VERSION"]:
+        raise RuntimeError(f"{os.path.basename(path)} ABI version does not match include/dial_b200.h")
+    for i, t in enumerate((dial_model_desc, dial_plan_desc, dial_state)):
+        if lib.dial_sizeof(i) != C.sizeof(t):
+            raise RuntimeError(f"struct layout mismatch for {t.__name__}: C {lib.dial_sizeof(i)} vs ctypes {C.sizeof(t)}")
+    return lib
 
 
-def lib() -> C.CDLL:
-    return _Lib.get()
+_LIBS: Dict[str, C.CDLL] = {}
+
+
+def lib(path: Optional[str] = None) -> C.CDLL:
+    """The stock library (default) or a custom-reward build (``dial_mpc_b200.custom``)."""
+    path = os.path.abspath(path or LIB_PATH)
+    if path not in _LIBS:
+        _LIBS[path] = _bind(path)
+    return _LIBS[path]
 
 
 def check(rc: int) -> None:
@@ -164,4 +170,5 @@ def check(rc: int) -> None:
 
 EXPORTS = ["dial_abi_version", "dial_last_error", "dial_sizeof", "dial_plan_create", "dial_plan_destroy", "dial_rollout",
            "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout", "dial_reverse_update",
-           "dial_reverse_trajbar", "dial_key_split", "dial_launch_count", "dial_debug_counters"]
+           "dial_reverse_trajbar", "dial_key_split", "dial_launch_count", "dial_debug_counters",
+           "dial_solver_variant", "dial_custom_reward_id"]

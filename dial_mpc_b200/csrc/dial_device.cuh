@@ -1814,12 +1814,32 @@ DEV BaseKin base_kin(WarpCtx& w, int bid) {
   return r;
 }
 
+#ifdef DIAL_CUSTOM_REWARD_FILE
+// user reward of a custom build (include/dial_custom_reward.h)
+#include "../../include/dial_custom_reward.h"
+#include DIAL_CUSTOM_REWARD_FILE
+#endif
+
 DEV float reward_lane0(WarpCtx& w, int step, int& stage) {
   const DevModel& M = *w.M;
   const dial_plan_desc& c = w.P->c;
   const dial_model_desc& m = M.m;
   const float stepf = (float)step;
   float rew = 0.f;
+#ifdef DIAL_CUSTOM_REWARD_FILE
+  if (c.env_id == DIAL_ENV_CUSTOM) {
+    dial_reward_ctx x;
+    x.step = step; x.dt = c.dt;
+    x.nq = m.nq; x.nv = m.nv; x.nu = m.nu; x.nbody = m.nbody; x.ncon = m.ncon; x.nsite = m.nsite; x.n_user = c.n_user;
+    x.qpos = SM(qpos); x.qvel = SM(qvel); x.ctrl = SM(ctrl);
+    x.xpos = SM(xpos); x.xquat = SM(xquat); x.xmat = SM(xmat); x.cvel = SM(cvel);
+    x.subtree_com = SM(rcom); x.body_rootidx = M.body_rootidx;
+    x.contact_dist = SM(cdist); x.contact_pos = SM(cpos);
+    x.site_bodyid = m.site_bodyid; x.site_pos = &m.site_pos[0][0];
+    x.user = c.user;
+    return dial_custom_reward(&x);
+  }
+#endif
   Q4 rot0 = ldq(SM(xquat) + 4);  // x.rot[0]
   V3 up = qrot(rot0, v3(0, 0, 1));
   float r_upright = -(up.x * up.x + up.y * up.y + (up.z - 1.f) * (up.z - 1.f));

@@ -307,12 +307,29 @@ static cudaError_t launch_rollout_t(dial_plan* p, const RolloutArgs& A, cudaStre
 // solver instantiation by tree shape: star<3,6> (quadruped), star<5,7> (humanoid), generic tree
 template <int WPC>
 static cudaError_t launch_rollout(dial_plan* p, const RolloutArgs& A, cudaStream_t st) {
+  // custom-reward builds compile only the instantiation their model needs (-DDIAL_ONLY_VARIANT=v)
+#ifdef DIAL_ONLY_VARIANT
+#define DIAL_HAS_VARIANT(v) ((v) == DIAL_ONLY_VARIANT)
+#else
+#define DIAL_HAS_VARIANT(v) 1
+#endif
   switch (p->variant) {
+#if DIAL_HAS_VARIANT(1)
     case 1: return launch_rollout_t<WPC, 3, 6>(p, A, st);
+#endif
+#if DIAL_HAS_VARIANT(2)
     case 2: return launch_rollout_t<WPC, 5, 7>(p, A, st);
+#endif
+#if DIAL_HAS_VARIANT(3)
     case 3: return launch_rollout_t<WPC, -1, 22>(p, A, st);
+#endif
+#if DIAL_HAS_VARIANT(4)
     case 4: return launch_rollout_t<WPC, 5, 6>(p, A, st);
-    default: return launch_rollout_t<WPC, 0, 0>(p, A, st);
+#endif
+#if DIAL_HAS_VARIANT(0)
+    case 0: return launch_rollout_t<WPC, 0, 0>(p, A, st);
+#endif
+    default: return cudaErrorInvalidDeviceFunction;
   }
 }
 
@@ -369,7 +386,20 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
     delete p;
     return nullptr;
   }
-  if (c.env_id < DIAL_ENV_GO2_WALK || c.env_id > DIAL_ENV_H1_LOCO) { g_err = "unknown env_id"; delete p; return nullptr; }
+  if (c.env_id < DIAL_ENV_GO2_WALK || c.env_id > DIAL_ENV_CUSTOM) { g_err = "unknown env_id"; delete p; return nullptr; }
+#ifndef DIAL_CUSTOM_REWARD_FILE
+  if (c.env_id == DIAL_ENV_CUSTOM) {
+    g_err = "env_id DIAL_ENV_CUSTOM needs a library built with a reward source (dial_mpc_b200.custom.build_library); this is the stock build";
+    delete p; return nullptr;
+  }
+#endif
+#ifdef DIAL_ONLY_VARIANT
+  if (p->variant != DIAL_ONLY_VARIANT) {
+    g_err = "this custom build holds solver variant " + std::to_string(DIAL_ONLY_VARIANT) + " only, the model needs " + std::to_string(p->variant);
+    delete p; return nullptr;
+  }
+#endif
+  if (c.n_user < 0 || c.n_user > DIAL_MAXUSER) { g_err = "n_user out of range"; delete p; return nullptr; }
   auto bad = [&](cudaError_t e, const char* what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     dial_plan_destroy(p);
@@ -517,6 +547,30 @@ extern "C" void dial_key_split(const uint32_t key[2], uint32_t out0[2], uint32_t
   threefry2x32(key[0], key[1], a0, b0);
   threefry2x32(key[0], key[1], a1, b1);
   out0[0] = a0; out0[1] = a1; out1[0] = b0; out1[1] = b1;
+}
+
+extern "C" int dial_solver_variant(const dial_model_desc* model) {
+  if (!model) return fail("null descriptor");
+  DevModel* D = new (std::nothrow) DevModel();
+  if (!D) return fail("out of memory");
+  std::string err;
+  int v = -1;
+  if (!derive_model(*model, *D, err)) g_err = err;
+  else if ((v = star_variant(*D)) < 0) g_err = "the dense (elliptic) solver path is instantiated for nv = 22 only";
+  delete D;
+  return v;
+}
+
+#define DIAL_STR2(x) #x
+#define DIAL_STR(x) DIAL_STR2(x)
+extern "C" const char* dial_custom_reward_id(void) {
+#if defined(DIAL_CUSTOM_REWARD_FILE) && defined(DIAL_CUSTOM_REWARD_ID)
+  return DIAL_STR(DIAL_CUSTOM_REWARD_ID);
+#elif defined(DIAL_CUSTOM_REWARD_FILE)
+  return "custom";
+#else
+  return "";
+#endif
 }
 
 extern "C" int64_t dial_launch_count(const dial_plan* p) { return p ? p->launches : 0; }

@@ -1,0 +1,89 @@
+"""Custom-reward builds of the sampling core.
+
+The reference lets users write their own env in JAX (README.md:223-312, ``--custom-env`` at
+dial_mpc/core/dial_core.py:202-204).  Here ``step``'s physics is the fused rollout kernel, so a
+custom env supplies (1) an MJCF model, compiled by ``dial_mpc_b200.modelc``, and (2) its reward
+as ONE CUDA device function (contract: ``include/dial_custom_reward.h``).  ``build_library``
+compiles a dedicated build of ``libdial_b200`` with that function fused into the rollout
+kernel — sm_100a, same flags as the stock library, only the solver instantiation the model
+needs — and caches it in-tree under ``dial_mpc_b200/_custom/`` keyed by the content hash of
+every source that goes into it.  There is no interpreter / CPU fallback for the reward.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+from typing import Optional
+
+from dial_mpc_b200 import _capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+CACHE_DIR = os.path.join(_HERE, "_custom")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-use_fast_math", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+
+def _sources(reward_path: str):
+    return [os.path.join(CSRC, f) for f in ("dial_kernels.cu", "dial_device.cuh", "dial_host.h")] + \
+        [os.path.join(_ROOT, "include", "dial_b200.h"), os.path.join(_ROOT, "include", "dial_custom_reward.h"),
+         reward_path]
+
+
+def reward_id(reward_path: str, variant: int) -> str:
+    h = hashlib.sha256()
+    for s in _sources(reward_path):
+        h.update(open(s, "rb").read())
+    h.update((" ".join(NVCC_FLAGS) + f" variant={variant}").encode())
+    return h.hexdigest()[:16]
+
+
+def library_path(reward_path: str, variant: int) -> str:
+    stem = os.path.splitext(os.path.basename(reward_path))[0]
+    return os.path.join(CACHE_DIR, f"libdial_b200_{stem}_v{variant}_{reward_id(reward_path, variant)}.so")
+
+
+def solver_variant(model) -> int:
+    """Solver instantiation a compiled model maps to (host logic of the stock library)."""
+    md = _capi.fill_model_desc(model)
+    v = _capi.lib().dial_solver_variant(md)
+    if v < 0:
+        raise RuntimeError(f"model not supported: {_capi.lib().dial_last_error().decode()}")
+    return v
+
+
+def build_library(reward_path: str, model=None, variant: Optional[int] = None, force: bool = False,
+                  verbose: bool = False) -> str:
+    """Compile (or reuse) the library with ``reward_path`` fused in; returns the ``.so`` path."""
+    reward_path = os.path.abspath(reward_path)
+    if not os.path.exists(reward_path):
+        raise FileNotFoundError(reward_path)
+    if variant is None:
+        if model is None:
+            raise ValueError("pass the compiled model (or the solver variant) the library is for")
+        variant = solver_variant(model)
+    out = library_path(reward_path, variant)
+    if os.path.exists(out) and not force:
+        return out
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: custom rewards are compiled CUDA, there is no fallback")
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    tmp = out + f".tmp{os.getpid()}"
+    cmd = [nvcc] + NVCC_FLAGS + [f'-DDIAL_CUSTOM_REWARD_FILE="{reward_path}"',
+                                 f"-DDIAL_CUSTOM_REWARD_ID={reward_id(reward_path, variant)}",
+                                 f"-DDIAL_ONLY_VARIANT={variant}", "-o", tmp,
+                                 os.path.join(CSRC, "dial_kernels.cu")]
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise RuntimeError(f"nvcc failed for {reward_path}:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, out)  # atomic: concurrent ranks may build the same library
+    return out

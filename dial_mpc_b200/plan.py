@@ -35,7 +35,8 @@ class Plan:
     def __init__(self, env, desc: "_capi.dial_plan_desc", device: Optional[torch.device] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("dial_mpc_b200 needs a CUDA device (B200); there is no CPU fallback")
-        self.lib = _capi.lib()
+        # custom-reward envs carry their own build of the library (dial_mpc_b200.custom)
+        self.lib = _capi.lib(getattr(env, "library_path", None))
         self.env = env
         self.desc = desc
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -48,6 +49,10 @@ class Plan:
         self.nq, self.nv, self.nu, self.nbody = m.nq, m.nv, m.nu, m.nbody
         self.N, self.Ntotal = desc.Nsample, desc.Ntotal
         self.Hs, self.Hn = desc.Hsample, desc.Hnode
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise RuntimeError(f"dial_b200: {self.lib.dial_last_error().decode()} (rc={rc})")
 
     def __del__(self):
         try:
@@ -89,7 +94,7 @@ class Plan:
         q = self.f32(qpos, (self.nq,))
         qv = torch.zeros(self.nv, dtype=torch.float32, device=self.device)
         qo, wo = self.empty(self.nq), self.empty(self.nv)
-        _capi.check(self.lib.dial_pipeline_init(self.handle, _ptr(q), _ptr(qv), _ptr(qo), _ptr(wo), _stream()))
+        self._check(self.lib.dial_pipeline_init(self.handle, _ptr(q), _ptr(qv), _ptr(qo), _ptr(wo), _stream()))
         return PipelineState(qo, qv, wo, torch.zeros(self.nu, dtype=torch.float32, device=self.device))
 
     def env_step(self, state, action):
@@ -97,7 +102,7 @@ class Plan:
         s, keep = self._state(state)
         a = self.f32(action, (self.nu,))
         qo, vo, wo, r, c = self.empty(self.nq), self.empty(self.nv), self.empty(self.nv), self.empty(1), self.empty(self.nu)
-        _capi.check(self.lib.dial_env_step(self.handle, C.byref(s), _ptr(a), _ptr(qo), _ptr(vo), _ptr(wo), _ptr(r),
+        self._check(self.lib.dial_env_step(self.handle, C.byref(s), _ptr(a), _ptr(qo), _ptr(vo), _ptr(wo), _ptr(r),
                                            _ptr(c), _stream()))
         return PipelineState(qo, vo, wo, c), r[0]
 
@@ -110,19 +115,19 @@ class Plan:
         q = self.empty(B, H, self.nq) if want_traj else None
         qd = self.empty(B, H, self.nv) if want_traj else None
         x = self.empty(B, H, self.nbody - 1, 3) if want_traj else None
-        _capi.check(self.lib.dial_rollout(self.handle, C.byref(s), _ptr(us), B, H, _ptr(rewss), _ptr(q), _ptr(qd),
+        self._check(self.lib.dial_rollout(self.handle, C.byref(s), _ptr(us), B, H, _ptr(rewss), _ptr(q), _ptr(qd),
                                           _ptr(x), _stream()))
         return rewss, q, qd, x
 
     def reverse_rollout(self, state, eps, key, Ybar, noise_scale, rews_local):
         s, keep = self._state(state)
-        _capi.check(self.lib.dial_reverse_rollout(self.handle, C.byref(s), _ptr(eps), _key(key), _ptr(Ybar),
+        self._check(self.lib.dial_reverse_rollout(self.handle, C.byref(s), _ptr(eps), _key(key), _ptr(Ybar),
                                                   _ptr(noise_scale), _ptr(rews_local), _stream()))
 
     def reverse_update(self, eps, key, Ybar, noise_scale, rews_all, Ybar_out, weights=None):
-        _capi.check(self.lib.dial_reverse_update(self.handle, _ptr(eps), _key(key), _ptr(Ybar), _ptr(noise_scale),
+        self._check(self.lib.dial_reverse_update(self.handle, _ptr(eps), _key(key), _ptr(Ybar), _ptr(noise_scale),
                                                  _ptr(rews_all), _ptr(Ybar_out), _ptr(weights), _stream()))
 
     def reverse_trajbar(self, weights, rank, qbar, qdbar, xbar):
-        _capi.check(self.lib.dial_reverse_trajbar(self.handle, _ptr(weights), int(rank), _ptr(qbar), _ptr(qdbar),
+        self._check(self.lib.dial_reverse_trajbar(self.handle, _ptr(weights), int(rank), _ptr(qbar), _ptr(qdbar),
                                                   _ptr(xbar), _stream()))

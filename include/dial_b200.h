@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DIAL_ABI_VERSION 2
+#define DIAL_ABI_VERSION 3
 
 /* capacities of the fixed-size device model */
 #define DIAL_MAXB 24   /* bodies incl. world            */
@@ -40,6 +40,7 @@ extern "C" {
 #define DIAL_MAXNODE 8 /* Hnode+1                       */
 #define DIAL_MAXH 64   /* Hsample+1                     */
 #define DIAL_MAXSTAGE 8
+#define DIAL_MAXUSER 64 /* user constants of a custom reward */
 
 /* environments (reward functors fused into the rollout kernel) */
 enum {
@@ -48,6 +49,9 @@ enum {
   DIAL_ENV_H1_WALK = 2,     /* UnitreeH1WalkEnv.step      envs/unitree_h1_env.py:181-321  */
   DIAL_ENV_ALLEGRO = 3,     /* AllegroReorientEnv.step    envs/manipulation.py:63-100     */
   DIAL_ENV_H1_LOCO = 4,     /* UnitreeH1LocoEnv.step      envs/unitree_h1_env.py:686-830  */
+  DIAL_ENV_CUSTOM = 5,      /* user reward (README.md:223-312 "Writing Custom Environment"):
+                               a device functor compiled into a dedicated build of this library,
+                               see include/dial_custom_reward.h                              */
 };
 
 /* Compiled robot model: what `brax.io.mjcf.load` + `mjx.put_model` give the reference
@@ -117,6 +121,9 @@ typedef struct dial_plan_desc {
   float jump_dt;
   float pose_seq[DIAL_MAXSTAGE][3], yaw_seq[DIAL_MAXSTAGE];
   float contact_targets[DIAL_MAXSTAGE][4][3], contact_radius[DIAL_MAXSTAGE][4];
+  /* DIAL_ENV_CUSTOM: constants handed to dial_custom_reward() (ctx->user) */
+  int32_t n_user;
+  float user[DIAL_MAXUSER];
 } dial_plan_desc;
 
 /* State handed to the planner: Brax `State.pipeline_state` (qpos, qvel,
@@ -197,6 +204,15 @@ void dial_key_split(const uint32_t key[2], uint32_t out0[2], uint32_t out1[2]);
 /* tuning aid: with DIAL_DEBUG_COUNTERS=1 in the environment at plan creation the dense solver
  * path counts [0] physics steps and [1] Newton iterations; reads and resets the counters. */
 int dial_debug_counters(dial_plan* plan, float out[8]);
+
+/* Which solver instantiation `model` maps to (1 star<3,6>, 2 star<5,7>, 3 dense nv=22,
+ * 4 star<5,6>, 0 generic tree, <0 unsupported): custom-reward builds compile only this one
+ * (-DDIAL_ONLY_VARIANT=v). */
+int dial_solver_variant(const dial_model_desc* model);
+
+/* "" for the stock library; the identifier (-DDIAL_CUSTOM_REWARD_ID) of the reward source a
+ * custom build was compiled with.  Only such a build accepts env_id == DIAL_ENV_CUSTOM. */
+const char* dial_custom_reward_id(void);
 
 /* kernel launches issued by this plan since creation (bench bookkeeping) */
 int64_t dial_launch_count(const dial_plan* plan);

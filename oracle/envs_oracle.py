@@ -87,8 +87,8 @@ class OracleEnv:
     init_key = "home"
 
     def __init__(self, dt=0.02, timestep=0.02, kp=30.0, kd=0.0, action_scale=1.0,
-                 leg_control="torque"):
-        self.m = mo.OModel(os.path.join(_MODELS, self.model_file), timestep=timestep)
+                 leg_control="torque", model_path=None):
+        self.m = mo.OModel(model_path or os.path.join(_MODELS, self.model_file), timestep=timestep)
         self.dt, self.timestep = dt, timestep
         self.n_frames = int(dt / timestep)
         self.kp, self.kd = np.asarray(kp, dtype=np.float64), np.asarray(kd, dtype=np.float64)
@@ -374,6 +374,33 @@ class AllegroReorientOracle(OracleEnv):
         r_pos = -np.sum((v["x_pos"][:, self.obj] - self.pos_tar) ** 2, -1)
         r_joint = -np.sum((qpos[:, 7:] - self.init_q[7:]) ** 2, -1)
         return r_ang + 5.0 * r_pos + 0.1 * r_joint, s.stage
+
+
+class CustomRewardOracle(OracleEnv):
+    """Checker for user-written envs (the reference's README.md:223-312 recipe): the physics of
+    ``step`` is the common ``OracleEnv`` path, the reward a Python callable
+    ``reward_fn(ctx) -> [B]`` over the batched fp64 counterparts of ``dial_reward_ctx``
+    (include/dial_custom_reward.h): step, dt, qpos, qvel, ctrl, xpos, xquat, xmat, xd_vel,
+    xd_ang (indexed by MuJoCo body id), contact_dist, contact_pos, site_xpos, user."""
+
+    def __init__(self, model_path, reward_fn, user=(), joint_range=None, init_q=None, **kw):
+        super().__init__(model_path=model_path, **kw)
+        self.reward_fn = reward_fn
+        self.user = np.asarray(user, dtype=np.float64)
+        if joint_range is not None:
+            self.joint_range = np.asarray(joint_range, dtype=np.float64)
+        if init_q is not None:
+            self.init_q = np.asarray(init_q, dtype=np.float64)
+
+    def reward(self, s, qpos, qvel, d, ctrl):
+        v = mo.brax_views(self.m, d)
+        B = qpos.shape[0]
+        pad = lambda a: np.concatenate([np.zeros((B, 1) + a.shape[2:]), a], 1)  # body 0 = world
+        ctx = dict(step=s.step, dt=self.dt, qpos=qpos, qvel=qvel, ctrl=ctrl, xpos=d.xpos, xquat=d.xquat,
+                   xmat=d.xmat, xd_vel=pad(v["xd_vel"]), xd_ang=pad(v["xd_ang"]),
+                   contact_dist=d.con_dist, contact_pos=d.con_pos, site_xpos=d.site_xpos,
+                   user=self.user)
+        return np.asarray(self.reward_fn(ctx), dtype=np.float64), s.stage
 
 
 def make_env(env_name: str, cfg: Optional[Dict] = None) -> OracleEnv:

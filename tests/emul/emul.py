@@ -11,15 +11,30 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_DIR, "libdial_emul.so")
 
 
-def build(force=False):
+def build(force=False, reward_source=None):
+    """g++ build of the device code for the lock-step warp emulator.  ``reward_source``: a custom
+    reward file (include/dial_custom_reward.h) compiled in, as dial_mpc_b200.custom does with nvcc."""
     srcs = [os.path.join(_DIR, "emul_main.cpp"), os.path.join(_DIR, "warp_emul.h"),
             os.path.join(_DIR, "..", "..", "dial_mpc_b200", "csrc", "dial_device.cuh"),
             os.path.join(_DIR, "..", "..", "dial_mpc_b200", "csrc", "dial_host.h"),
             os.path.join(_DIR, "..", "..", "include", "dial_b200.h")]
-    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", _DIR, "-shared", "-fPIC", "-o", _SO,
-                               os.path.join(_DIR, "emul_main.cpp")])
-    return C.CDLL(_SO)
+    so, extra = _SO, []
+    if reward_source is not None:
+        import hashlib
+        reward_source = os.path.abspath(reward_source)
+        tag = hashlib.sha256(open(reward_source, "rb").read()).hexdigest()[:12]
+        so = os.path.join(_DIR, f"libdial_emul_custom_{tag}.so")
+        extra = [f'-DDIAL_CUSTOM_REWARD_FILE="{reward_source}"']
+        srcs += [reward_source, os.path.join(_DIR, "..", "..", "include", "dial_custom_reward.h")]
+    if so not in _LIBS or force:
+        if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", _DIR, "-shared", "-fPIC"] + extra +
+                                  ["-o", so, os.path.join(_DIR, "emul_main.cpp")])
+        _LIBS[so] = C.CDLL(so)
+    return _LIBS[so]
+
+
+_LIBS = {}
 
 
 def _p(a):
@@ -28,7 +43,7 @@ def _p(a):
 
 def rollout(env, plan_desc, qpos, qvel, warm, step0=0, stage0=0, us=None, eps=None, Ybar=None,
             noise=None, key=(0, 0), mode=0, nrows=None, H=None, want_traj=True):
-    lib = build()
+    lib = build(reward_source=getattr(env, "reward_source", None) or None)
     md = _capi.fill_model_desc(env.sys.model)
     nq, nv, nu, nb = md.nq, md.nv, md.nu, md.nbody
     f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)

@@ -37,7 +37,6 @@ def test_key_split_matches_oracle(built):
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_capi, "LIB_PATH", str(tmp_path / "nope.so"))
-    monkeypatch.setattr(_capi._Lib, "_lib", None)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _capi.lib()
 

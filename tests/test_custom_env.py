@@ -1,0 +1,145 @@
+"""Custom-environment path (reference README.md:223-312 "Writing Custom
+Environment", ``--custom-env`` dial_mpc/core/dial_core.py:202-204): a user model compiled from
+MJCF + a user reward written as a CUDA device function, fused into a dedicated library build.
+
+CPU: the reward + device code run in the warp emulator against the oracle with the same
+reward written in NumPy; the nvcc cross-compile of the custom library is checked for its
+exports.  GPU: the real custom build against the oracle."""
+import importlib
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT
+
+EX = os.path.join(ROOT, "dial_mpc_b200", "examples", "custom_env")
+
+
+def _reward_np(c):
+    """NumPy twin of examples/custom_env/quadpod_reward.cuh (the oracle's side of the check)."""
+    u = c["user"]
+    t = c["step"].astype(np.float64) * c["dt"]
+    vx_tar = np.minimum(u[0] * t / u[1], u[0])
+    v, w = c["xd_vel"][:, 1], c["xd_ang"][:, 1]
+    r_vel = -((v[:, 0] - vx_tar) ** 2 + v[:, 1] ** 2)
+    r_yaw = -w[:, 2] ** 2
+    dz = c["xpos"][:, 1, 2] - u[2]
+    q = c["xquat"][:, 1]
+    upz = 1.0 - 2.0 * (q[:, 1] ** 2 + q[:, 2] ** 2)
+    r_up = -(1.0 - upz)
+    r_energy = -np.sum((c["ctrl"] / u[5]) ** 2, -1)
+    r_feet = -np.sum(c["contact_dist"] ** 2, -1)
+    r_head = -(c["site_xpos"][:, 0, 2] - (u[2] + 0.02)) ** 2
+    return r_vel + 0.1 * r_yaw - 10.0 * dz * dz + 0.5 * r_up + u[3] * r_energy + u[4] * r_feet + r_head
+
+
+@pytest.fixture(scope="module")
+def pair():
+    if EX not in sys.path:
+        sys.path.insert(0, EX)
+    qe = importlib.import_module("quadpod_env")
+    import dial_mpc_b200.envs as E
+    from oracle.envs_oracle import CustomRewardOracle
+    cfg = qe.QuadpodEnvConfig()
+    env = E.get_environment("quadpod_walk", config=cfg)
+    tmp = tempfile.NamedTemporaryFile(suffix=".json", delete=False)
+    tmp.close()
+    env.sys.model.save(tmp.name)
+    o = CustomRewardOracle(tmp.name, _reward_np, user=env.user_params(), joint_range=env.joint_range,
+                           kp=cfg.kp, kd=cfg.kd, dt=cfg.dt, timestep=cfg.timestep)
+    yield env, o
+    os.unlink(tmp.name)
+
+
+def test_custom_env_descriptor_and_registry(pair):
+    env, o = pair
+    from dial_mpc_b200 import _capi
+    d = env.plan_desc(Nsample=8, Hsample=10, Hnode=4)
+    assert d.env_id == _capi.ENV_IDS["custom"] == _capi.DEFINES.get("DIAL_ENV_CUSTOM", 5)
+    assert d.n_user == 6 and abs(d.user[0] - 0.5) < 1e-7 and d.user[5] == 12.0
+    assert env.action_size == 8 and env.sys.nv == 14
+    np.testing.assert_allclose(env._init_q, o.init_q)
+    import dial_mpc_b200.envs as E
+    assert E.get_config("quadpod_walk").__name__ == "QuadpodEnvConfig"
+
+
+def test_custom_reward_in_emulator_matches_oracle(pair):
+    from tests.emul import emul
+    env, o = pair
+    s = o.reset()
+    s.step[:] = 20
+    rng = np.random.default_rng(3)
+    H = 12
+    us = np.clip(rng.normal(size=(3, H, env.action_size)) * 0.6, -1, 1)
+    rew, q, qd, x = o.rollout(s, us)
+    out = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us, step0=20)
+    assert np.abs(out["q"] - q).max() < 1e-4
+    assert np.abs(out["qd"] - qd).max() < 5e-3
+    assert np.abs(out["xpos"] - x).max() < 1e-4
+    assert np.abs(out["rewss"] - rew).max() < 1e-3 * (1 + np.abs(rew).max())
+    assert np.abs(rew).max() > 1e-3   # the reward is not trivially zero
+
+
+def test_stock_library_rejects_custom_env(pair, built):
+    """The product path fails loudly: the stock build has no reward for DIAL_ENV_CUSTOM."""
+    import ctypes as C
+    from dial_mpc_b200 import _capi
+    env, _ = pair
+    lib = _capi.lib()
+    assert lib.dial_custom_reward_id() == b""
+    md = _capi.fill_model_desc(env.sys.model)
+    assert lib.dial_solver_variant(md) == 1     # 4 hanging 2-dof legs fit the star<3,6> instantiation
+    h = lib.dial_plan_create(C.byref(md), C.byref(env.plan_desc()))
+    assert not h and b"DIAL_ENV_CUSTOM" in lib.dial_last_error()
+
+
+def test_custom_library_builds_and_exports(pair, built):
+    """nvcc cross-compiles the custom build without a GPU; it carries the same C ABI."""
+    from dial_mpc_b200 import _capi, custom
+    env, _ = pair
+    path = env.library_path
+    assert os.path.exists(path) and path.startswith(custom.CACHE_DIR)
+    lib = _capi.lib(path)
+    assert lib.dial_custom_reward_id().decode() == custom.reward_id(env.reward_source, 1)
+    for sym in _capi.EXPORTS:
+        assert hasattr(lib, sym)
+    assert custom.build_library(env.reward_source, model=env.sys.model) == path   # cached
+
+
+@pytest.mark.gpu
+def test_gpu_custom_env_matches_oracle(pair, built):
+    import torch
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import MBDPI
+    from dial_mpc_b200 import random as drandom
+    from oracle.planner_oracle import PlannerOracle, jax_normal_legacy
+    env, o = pair
+    # rollout_us_vmap through the custom library
+    s = o.reset()
+    state = env.reset(drandom.PRNGKey(0))
+    np.testing.assert_allclose(state.pipeline_state.qpos.cpu().numpy(), s.qpos[0], atol=1e-6)
+    rng = np.random.default_rng(5)
+    N, Hs, Hn = 64, 12, 4
+    args = DialConfig(env_name="quadpod_walk", Nsample=N, Hsample=Hs, Hnode=Hn, Ndiffuse=1, temp_sample=0.05,
+                      horizon_diffuse_factor=0.9, traj_diffuse_factor=0.5)
+    mb = MBDPI(args, env)
+    us = np.clip(rng.normal(size=(5, Hs + 1, env.action_size)) * 0.6, -1, 1).astype(np.float32)
+    rewss, ps = mb.rollout_us_vmap(state, us)
+    rew, q, qd, x = o.rollout(s, us.astype(np.float64))
+    assert np.abs(rewss.cpu().numpy() - rew).max() < 1e-3 * (1 + np.abs(rew).max())
+    # one reverse_once with injected-equivalent native RNG
+    pl = PlannerOracle(o, N, Hs, Hn, 0.05, 0.9, 0.5)
+    key = drandom.PRNGKey(7)
+    _, k2 = drandom.split(key)
+    eps = jax_normal_legacy(tuple(int(v) for v in k2), (N, Hn + 1, env.action_size))
+    Ybar = np.zeros((Hn + 1, env.action_size))
+    Yo, info_o = pl.reverse_once(s, eps, Ybar, pl.sigma_control)
+    _, Y, info = mb.reverse_once(state, key, torch.zeros(Hn + 1, env.action_size, device="cuda"),
+                                 torch.as_tensor(pl.sigma_control, dtype=torch.float32, device="cuda"))
+    r = info["rews"].cpu().numpy()
+    ok = np.abs(r - info_o["rews"]) < 2e-3 * (1 + np.abs(info_o["rews"]))
+    assert ok.mean() > 0.97, (ok.mean(), np.abs(r - info_o["rews"]).max())
+    assert np.abs(Y.cpu().numpy() - Yo).max() < 5e-3
