@@ -65,6 +65,7 @@ def _mk(name):
 dial_model_desc = _mk("dial_model_desc")
 dial_plan_desc = _mk("dial_plan_desc")
 dial_state = _mk("dial_state")
+dial_mpc_buffers = _mk("dial_mpc_buffers")
 
 ENV_IDS = {"unitree_go2_walk": 0, "unitree_go2_seq_jump": 1, "unitree_h1_walk": 2, "allegro_reorient": 3, "unitree_h1_loco": 4,
            "custom": 5}
@@ -141,12 +142,16 @@ def _bind(path: str) -> C.CDLL:
     lib.dial_solver_variant.argtypes = [C.POINTER(dial_model_desc)]
     lib.dial_solver_variant.restype = C.c_int
     lib.dial_custom_reward_id.restype = C.c_char_p
+    lib.dial_mpc_bind.argtypes = [V, C.POINTER(dial_mpc_buffers), P]
+    lib.dial_mpc_bind.restype = C.c_int
+    lib.dial_mpc_step.argtypes = [V, I, I, V]
+    lib.dial_mpc_step.restype = C.c_int
     for fn in ("dial_rollout", "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout",
                "dial_reverse_update", "dial_reverse_trajbar"):
         getattr(lib, fn).restype = C.c_int
     if lib.dial_abi_version() != DEFINES["DIAL_ABI_VERSION"]:
         raise RuntimeError(f"{os.path.basename(path)} ABI version does not match include/dial_b200.h")
-    for i, t in enumerate((dial_model_desc, dial_plan_desc, dial_state)):
+    for i, t in enumerate((dial_model_desc, dial_plan_desc, dial_state, dial_mpc_buffers)):
         if lib.dial_sizeof(i) != C.sizeof(t):
             raise RuntimeError(f"struct layout mismatch for {t.__name__}: C {lib.dial_sizeof(i)} vs ctypes {C.sizeof(t)}")
     return lib
@@ -171,4 +176,4 @@ def check(rc: int) -> None:
 EXPORTS = ["dial_abi_version", "dial_last_error", "dial_sizeof", "dial_plan_create", "dial_plan_destroy", "dial_rollout",
            "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout", "dial_reverse_update",
            "dial_reverse_trajbar", "dial_key_split", "dial_launch_count", "dial_debug_counters",
-           "dial_solver_variant", "dial_custom_reward_id"]
+           "dial_solver_variant", "dial_custom_reward_id", "dial_mpc_bind", "dial_mpc_step"]

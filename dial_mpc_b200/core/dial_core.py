@@ -205,6 +205,92 @@ class MBDPI:
         return self.u2node_vmap(u)
 
 
+class DeviceLoop:
+    """Device-resident synchronous MPC loop: the reference's per-step sequence
+    (dial_core.py:242-268) — ``state = step_env(state, Y0[0]); Y0 = shift(Y0); Y0 = reverse_scan(...)``
+    — replayed as ONE CUDA graph per control step (C ABI ``dial_mpc_bind`` / ``dial_mpc_step``).
+    State, step counters, rng and control knots live in device tensors owned by this object; the
+    host only launches the graph and reads back what it needs (e.g. ``action``).  Equals the
+    eager ``env.step`` + ``MBDPI.shift`` + ``MBDPI.reverse_scan`` sequence (tests/test_gpu_parity.py).
+    Single-GPU plans."""
+
+    def __init__(self, mbdpi: "MBDPI", state, rng, Y0=None, n_diffuse_max: Optional[int] = None,
+                 compute_bars: bool = True):
+        if mbdpi.world_size != 1:
+            raise RuntimeError("DeviceLoop is single-GPU; sharded runs use MBDPI.reverse_once")
+        self.mbdpi, self.plan = mbdpi, mbdpi.plan
+        a, pl, dev = mbdpi.args, mbdpi.plan, mbdpi.device
+        nmax = int(n_diffuse_max or max(a.Ndiffuse, a.Ndiffuse_init))
+        ps = state.pipeline_state
+        f, e = pl.f32, pl.empty
+        Hs1 = a.Hsample + 1
+        m = mbdpi.env.sys
+        key = np.ascontiguousarray(rng, dtype=np.uint32).view(np.int32)
+        self.info0 = dict(state.info)
+        self.buf = dict(
+            qpos=f(ps.qpos).clone(), qvel=f(ps.qvel).clone(), qacc_warmstart=f(ps.qacc_warmstart).clone(),
+            counters=torch.tensor([int(state.info.get("step", 0)), int(state.info.get("contact_stage", 0))],
+                                  dtype=torch.int32, device=dev),
+            rng=torch.as_tensor(key.copy(), device=dev),
+            Y=(torch.zeros(a.Hnode + 1, mbdpi.nu, device=dev) if Y0 is None else f(Y0).clone()),
+            ctrl=torch.zeros(mbdpi.nu, device=dev), reward=torch.zeros(1, device=dev),
+            rews=torch.zeros(a.Nsample + 1, device=dev),
+            qbar=e(Hs1, m.nq) if compute_bars else None, qdbar=e(Hs1, m.nv) if compute_bars else None,
+            xbar=e(Hs1, m.nbody - 1, 3) if compute_bars else None,
+            noise=mbdpi.schedule(nmax).contiguous())
+        self.n_diffuse_max = nmax
+        pl.mpc_bind(self.buf, mbdpi.M_shift.cpu().numpy())
+
+    def step(self, n_diffuse: Optional[int] = None, env_step: bool = True) -> None:
+        """One control step (asynchronous on the current stream)."""
+        n = self.mbdpi.args.Ndiffuse if n_diffuse is None else int(n_diffuse)
+        if n > self.n_diffuse_max:
+            raise ValueError("n_diffuse exceeds the bound noise schedule")
+        self.plan.mpc_step(n, env_step)
+
+    def set_state(self, qpos, qvel, qacc_warmstart=None, step: Optional[int] = None) -> None:
+        """Overwrite the planning state (deploy: the state comes from the robot / simulator)."""
+        self.buf["qpos"].copy_(self.plan.f32(qpos))
+        self.buf["qvel"].copy_(self.plan.f32(qvel))
+        if qacc_warmstart is not None:
+            self.buf["qacc_warmstart"].copy_(self.plan.f32(qacc_warmstart))
+        if step is not None:
+            self.buf["counters"][0] = int(step)
+
+    @property
+    def action(self) -> torch.Tensor:
+        """``Y0[0]``: the action the next env step applies (device view)."""
+        return self.buf["Y"][0]
+
+    @property
+    def Y(self) -> torch.Tensor:
+        return self.buf["Y"]
+
+    @property
+    def reward(self) -> torch.Tensor:
+        return self.buf["reward"][0]
+
+    def info(self) -> Dict[str, Any]:
+        b = self.buf
+        d = {"rews": b["rews"]}
+        if b["qbar"] is not None:
+            d.update(qbar=b["qbar"], qdbar=b["qdbar"], xbar=b["xbar"])
+        return d
+
+    def state(self):
+        """Materialise the env ``State`` (synchronises: reads the counters)."""
+        from dial_mpc_b200.envs.base_env import PipelineState, State
+        b = self.buf
+        c = b["counters"].cpu().numpy()
+        info = dict(self.info0)
+        info["step"] = int(c[0])
+        if "contact_stage" in info:
+            info["contact_stage"] = int(c[1])
+        info["rng"] = b["rng"].cpu().numpy().view(np.uint32).copy()
+        ps = PipelineState(b["qpos"].clone(), b["qvel"].clone(), b["qacc_warmstart"].clone(), b["ctrl"].clone())
+        return State(ps, None, b["reward"][0].clone(), 0.0, {}, info)
+
+
 def main():
     """Synchronous MPC loop — dial_core.py:175-268 without the rendering / flask tail."""
     parser = argparse.ArgumentParser()
@@ -214,6 +300,8 @@ def main():
     g.add_argument("--list-examples", action="store_true")
     parser.add_argument("--custom-env", type=str, default=None, help="Custom environment to import dynamically")
     parser.add_argument("--n-steps", type=int, default=None)
+    parser.add_argument("--eager", action="store_true",
+                        help="per-call launches (env.step / reverse_scan) instead of the CUDA-graph loop")
     args = parser.parse_args()
     from dial_mpc_b200.examples import examples
     if args.list_examples:
@@ -240,20 +328,35 @@ def main():
     rng_exp, rng = drandom.split(rng)
     Nstep = args.n_steps or dial_config.n_steps
     rews, rollout, infos = [], [], []
-    for t in range(Nstep):
-        state = env.step(state, Y0[0])
-        ps = state.pipeline_state
-        rollout.append(torch.cat([torch.tensor([float(t)], device=mbdpi.device), ps.qpos, ps.qvel, ps.ctrl]))
-        rews.append(state.reward)
-        Y0 = mbdpi.shift(Y0)
-        n_diffuse = dial_config.Ndiffuse_init if t == 0 else dial_config.Ndiffuse
-        t0 = time.time()
-        rng, Y0, info = mbdpi.reverse_scan(state, rng, Y0, mbdpi.schedule(n_diffuse))
-        torch.cuda.synchronize()
-        freq = 1 / (time.time() - t0)
-        infos.append(info["xbar"][-1])
-        if t % 10 == 0:
-            print(f"step {t}: rew={float(state.reward):.3e} freq={freq:.1f} Hz")
+    if mbdpi.world_size == 1 and not args.eager:
+        # one CUDA graph per control step; the host launches it and logs
+        loop = DeviceLoop(mbdpi, state, rng, Y0)
+        b = loop.buf
+        t0, tlast = time.time(), -1
+        for t in range(Nstep):
+            loop.step(dial_config.Ndiffuse_init if t == 0 else dial_config.Ndiffuse)
+            rollout.append(torch.cat([torch.tensor([float(t)], device=mbdpi.device), b["qpos"], b["qvel"], b["ctrl"]]))
+            rews.append(b["reward"][0].clone())
+            infos.append(b["xbar"][-1].clone())
+            if t % 10 == 0:
+                r = float(rews[-1])  # synchronises: the rate below is whole control steps per second
+                print(f"step {t}: rew={r:.3e} freq={(t - tlast) / (time.time() - t0):.1f} Hz")
+                t0, tlast = time.time(), t
+    else:
+        for t in range(Nstep):
+            state = env.step(state, Y0[0])
+            ps = state.pipeline_state
+            rollout.append(torch.cat([torch.tensor([float(t)], device=mbdpi.device), ps.qpos, ps.qvel, ps.ctrl]))
+            rews.append(state.reward)
+            Y0 = mbdpi.shift(Y0)
+            n_diffuse = dial_config.Ndiffuse_init if t == 0 else dial_config.Ndiffuse
+            t0 = time.time()
+            rng, Y0, info = mbdpi.reverse_scan(state, rng, Y0, mbdpi.schedule(n_diffuse))
+            torch.cuda.synchronize()
+            freq = 1 / (time.time() - t0)
+            infos.append(info["xbar"][-1])
+            if t % 10 == 0:
+                print(f"step {t}: rew={float(state.reward):.3e} freq={freq:.1f} Hz")
     rew = torch.stack([torch.as_tensor(r) for r in rews]).mean()
     print(f"mean reward = {float(rew):.2e}")
     os.makedirs(dial_config.output_dir, exist_ok=True)

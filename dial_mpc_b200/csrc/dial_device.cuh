@@ -110,6 +110,11 @@ struct RolloutArgs {
   float* qvel_out;
   float* warm_out;
   float* ctrl_out;
+  // device-resident MPC loop (dial_mpc_step): counters / key live in HBM so that a captured CUDA
+  // graph can be replayed without patching kernel arguments
+  const int32_t* counters_in;   // non-null: {step0, stage0} read from here
+  int32_t* counters_out;        // non-null: row 0 writes {step, stage} after its H steps
+  const uint32_t* key_dev;      // non-null: sampling key read from here
   unsigned int* row_counter;  // non-null: persistent warps pull rows from this counter (dense path)
   float* dbg;           // optional device counters (DIAL_DEBUG_COUNTERS, see dial_debug_counters)
 };
@@ -1979,6 +1984,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     const bool is_mean = row == c.Nsample;
     const uint32_t gidx = (uint32_t)(c.shard_offset + row);
     const uint32_t ntot = (uint32_t)c.Ntotal * (uint32_t)Hn1 * (uint32_t)nu;
+    const uint32_t key0 = A.key_dev ? A.key_dev[0] : A.key0, key1 = A.key_dev ? A.key_dev[1] : A.key1;
 #pragma unroll
     for (int k = 0; k < DIAL_MAXNODE; ++k) {
       if (k < Hn1) {
@@ -1986,7 +1992,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
         float y = yb;
         if (!is_mean && k > 0) {
           uint32_t idx = (gidx * (uint32_t)Hn1 + (uint32_t)k) * (uint32_t)nu + (uint32_t)lane;
-          float e = A.eps ? A.eps[idx] : jax_normal_legacy(A.key0, A.key1, idx, ntot);
+          float e = A.eps ? A.eps[idx] : jax_normal_legacy(key0, key1, idx, ntot);
           y = e * A.noise[k] + yb;
         }
         Y[k] = fminf(fmaxf(y, -1.f), 1.f);
@@ -1994,7 +2000,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     }
   }
 
-  int step = A.step0, stage = A.stage0;
+  int step = A.counters_in ? A.counters_in[0] : A.step0, stage = A.counters_in ? A.counters_in[1] : A.stage0;
   float rsum = 0.f;
   const bool fwd_only = A.mode == 2;  // pipeline_init: mjx.forward only, zero ctrl
   const int H = fwd_only ? 1 : A.H;
@@ -2044,5 +2050,6 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     if (A.qvel_out) for (int i = lane; i < nv; i += 32) A.qvel_out[i] = SM(qvel)[i];
     if (A.warm_out) for (int i = lane; i < nv; i += 32) A.warm_out[i] = SM(warm)[i];
     if (A.ctrl_out) for (int i = lane; i < nu; i += 32) A.ctrl_out[i] = SM(ctrl)[i];
+    if (A.counters_out && lane == 0) { A.counters_out[0] = step; A.counters_out[1] = stage; }
   }
 }

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string>
+#include <vector>
 #include <new>
 #include "dial_host.h"
 
@@ -148,7 +149,9 @@ __global__ void __launch_bounds__(YBAR_THREADS) ybar_kernel(const float* __restr
                                                              uint32_t key0, uint32_t key1, const float* __restrict__ Ybar,
                                                              const float* __restrict__ noise, int Ntotal, int Hn1, int nu,
                                                              float* __restrict__ partial, unsigned int* __restrict__ counter,
-                                                             float* __restrict__ Ybar_out) {
+                                                             float* __restrict__ Ybar_out,
+                                                             const uint32_t* __restrict__ key_dev) {
+  if (key_dev) { key0 = key_dev[0]; key1 = key_dev[1]; }
   // thread -> (sample slot, output element); elements = Hn1*nu <= 160
   const int ne = Hn1 * nu;
   __shared__ float acc[YBAR_THREADS];
@@ -189,6 +192,35 @@ __global__ void __launch_bounds__(YBAR_THREADS) ybar_kernel(const float* __restr
       Ybar_out[threadIdx.x] = s;
     }
     if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// glue of the device-resident MPC loop (dial_mpc_step): everything the reference's Python loop
+// does between kernels (core/dial_core.py:242-268) as tiny kernels, so that one MPC step is one
+// CUDA graph with no host work inside
+// ---------------------------------------------------------------------------------
+// rng, key = jax.random.split(rng)   (dial_core.py:106), legacy layout as dial_key_split
+__global__ void mpc_split_kernel(uint32_t* __restrict__ rng, uint32_t* __restrict__ key) {
+  if (threadIdx.x == 0) {
+    const uint32_t k0 = rng[0], k1 = rng[1];
+    uint32_t a0 = 0, b0 = 2, a1 = 1, b1 = 3;
+    threefry2x32(k0, k1, a0, b0);
+    threefry2x32(k0, k1, a1, b1);
+    rng[0] = a0; rng[1] = a1; key[0] = b0; key[1] = b1;
+  }
+}
+
+// Y <- shift(Y) = u2node(roll(node2u(Y), -1), last row 0)  (dial_core.py:160-165) as one constant
+// (Hn+1)x(Hn+1) matrix; one thread per output element
+__global__ void mpc_shift_kernel(const float* __restrict__ Msh, const float* __restrict__ Yin,
+                                 float* __restrict__ Yout, int n1, int nu) {
+  const int i = threadIdx.x;
+  if (i < n1 * nu) {
+    const int k = i / nu, a = i - k * nu;
+    float s = 0.f;
+    for (int j = 0; j < n1; ++j) s += Msh[k * n1 + j] * Yin[j * nu + a];
+    Yout[i] = s;
   }
 }
 
@@ -275,12 +307,21 @@ struct dial_plan {
   int ybar_grid = 0;
   int64_t launches = 0;
   float* dbg = nullptr;  // optional device counters (DIAL_DEBUG_COUNTERS=1)
+  // device-resident MPC loop
+  dial_mpc_buffers mpc{};       // caller-owned state block (dial_mpc_bind)
+  bool mpc_bound = false;
+  float* mpc_Msh = nullptr;     // [Hn+1][Hn+1] shift matrix
+  float* mpc_Y1 = nullptr;      // ping-pong partner of mpc.Y
+  uint32_t* mpc_key = nullptr;  // sampling key of the current reverse_once
+  struct MpcGraph { int n_diffuse, env_step, seen; cudaGraphExec_t exec; int64_t launches; };
+  std::vector<MpcGraph> mpc_graphs;
 };
 
 extern "C" int dial_abi_version(void) { return DIAL_ABI_VERSION; }
 extern "C" const char* dial_last_error(void) { return g_err.c_str(); }
 extern "C" size_t dial_sizeof(int which) {
-  return which == 0 ? sizeof(dial_model_desc) : which == 1 ? sizeof(dial_plan_desc) : which == 2 ? sizeof(dial_state) : 0;
+  return which == 0 ? sizeof(dial_model_desc) : which == 1 ? sizeof(dial_plan_desc) : which == 2 ? sizeof(dial_state)
+       : which == 3 ? sizeof(dial_mpc_buffers) : 0;
 }
 
 template <int WPC, int NL, int NR>
@@ -439,6 +480,8 @@ extern "C" void dial_plan_destroy(dial_plan* p) {
   if (!p) return;
   cudaFree(p->dM); cudaFree(p->dP);
   for (int b = 0; b < 2; ++b) { cudaFree(p->traj_q[b]); cudaFree(p->traj_qd[b]); cudaFree(p->traj_x[b]); }
+  for (auto& g : p->mpc_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  cudaFree(p->mpc_Msh); cudaFree(p->mpc_Y1); cudaFree(p->mpc_key);
   cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->tb_partial); cudaFree(p->counter); cudaFree(p->row_counter); cudaFree(p->zeros); cudaFree(p->dbg);
   delete p;
 }
@@ -508,7 +551,7 @@ extern "C" int dial_reverse_update(dial_plan* p, const float* eps, const uint32_
   p->launches++;
   CUDA_OK(cudaGetLastError());
   ybar_kernel<<<p->ybar_grid, YBAR_THREADS, 0, st>>>(w, eps, key ? key[0] : 0u, key ? key[1] : 0u, Ybar, noise_scale,
-                                                     c.Ntotal, c.Hnode + 1, p->hM.m.nu, p->partial, p->counter, Ybar_out);
+                                                     c.Ntotal, c.Hnode + 1, p->hM.m.nu, p->partial, p->counter, Ybar_out, nullptr);
   p->launches++;
   CUDA_OK(cudaGetLastError());
   if (weights && weights != p->weights)
@@ -538,6 +581,116 @@ extern "C" int dial_reverse_trajbar(dial_plan* p, const float* weights, int rank
   trajbar_final_kernel<<<H, 128, 0, st>>>(T);
   p->launches++;
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- device-resident synchronous MPC loop ---------------------------------------------------
+extern "C" int dial_mpc_bind(dial_plan* p, const dial_mpc_buffers* b, const float* M_shift) {
+  if (!p || !b || !M_shift) return fail("dial_mpc_bind: null argument");
+  if (!b->qpos || !b->qvel || !b->qacc_warmstart || !b->counters || !b->rng || !b->Y || !b->ctrl || !b->reward ||
+      !b->rews || !b->noise)
+    return fail("dial_mpc_bind: only qbar/qdbar/xbar may be null");
+  const dial_plan_desc& c = p->hP.c;
+  if (c.Ntotal != c.Nsample) return fail("dial_mpc_bind: the device-resident loop is single-GPU (sharded plans use reverse_once)");
+  const int n1 = c.Hnode + 1, nu = p->hM.m.nu;
+  for (auto& g : p->mpc_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  p->mpc_graphs.clear();
+  if (!p->mpc_Msh) CUDA_OK(cudaMalloc(&p->mpc_Msh, DIAL_MAXNODE * DIAL_MAXNODE * sizeof(float)));
+  if (!p->mpc_Y1) CUDA_OK(cudaMalloc(&p->mpc_Y1, DIAL_MAXNODE * DIAL_MAXU * sizeof(float)));
+  if (!p->mpc_key) CUDA_OK(cudaMalloc(&p->mpc_key, 2 * sizeof(uint32_t)));
+  CUDA_OK(cudaMemcpy(p->mpc_Msh, M_shift, (size_t)n1 * n1 * sizeof(float), cudaMemcpyHostToDevice));
+  (void)nu;
+  p->mpc = *b;
+  p->mpc_bound = true;
+  return 0;
+}
+
+// enqueue one MPC step on `st` (eagerly or into a capture)
+static int mpc_enqueue(dial_plan* p, int n_diffuse, int env_step, cudaStream_t st) {
+  const dial_plan_desc& c = p->hP.c;
+  const dial_mpc_buffers& B = p->mpc;
+  const int n1 = c.Hnode + 1, nu = p->hM.m.nu;
+  float* Y[2] = {B.Y, p->mpc_Y1};
+  int cur = 0;
+  if (env_step) {
+    // state = step_env(state, Y0[0])  (dial_core.py:245): in place, counters advanced by the kernel
+    RolloutArgs A; memset(&A, 0, sizeof(A));
+    A.qpos0 = B.qpos; A.qvel0 = B.qvel; A.warm0 = B.qacc_warmstart;
+    A.counters_in = B.counters; A.counters_out = B.counters;
+    A.nrows = 1; A.H = 1; A.mode = 0; A.us = Y[cur]; A.rewss = B.reward;
+    A.qpos_out = B.qpos; A.qvel_out = B.qvel; A.warm_out = B.qacc_warmstart; A.ctrl_out = B.ctrl;
+    CUDA_OK(launch_rollout<1>(p, A, st));
+    // Y0 = shift(Y0)  (dial_core.py:252)
+    mpc_shift_kernel<<<1, DIAL_MAXNODE * DIAL_MAXU, 0, st>>>(p->mpc_Msh, Y[cur], Y[cur ^ 1], n1, nu);
+    p->launches++;
+    CUDA_OK(cudaGetLastError());
+    cur ^= 1;
+  }
+  for (int i = 0; i < n_diffuse; ++i) {
+    const float* noise = B.noise + (size_t)i * n1;
+    mpc_split_kernel<<<1, 32, 0, st>>>(B.rng, p->mpc_key);
+    p->launches++;
+    CUDA_OK(cudaGetLastError());
+    RolloutArgs A; memset(&A, 0, sizeof(A));
+    A.qpos0 = B.qpos; A.qvel0 = B.qvel; A.warm0 = B.qacc_warmstart; A.counters_in = B.counters;
+    A.nrows = c.Nsample + 1; A.H = c.Hsample + 1; A.mode = 1;
+    A.Ybar = Y[cur]; A.noise = noise; A.key_dev = p->mpc_key;
+    p->cur ^= 1;
+    A.rews = B.rews; A.q = p->traj_q[p->cur]; A.qd = p->traj_qd[p->cur]; A.xpos = p->traj_x[p->cur];
+    A.dbg = p->dbg;
+    CUDA_OK(launch_rollout_any(p, A, st));
+    weights_kernel<<<1, 1024, 0, st>>>(B.rews, c.Ntotal + 1, c.temp_sample, p->weights);
+    p->launches++;
+    CUDA_OK(cudaGetLastError());
+    ybar_kernel<<<p->ybar_grid, YBAR_THREADS, 0, st>>>(p->weights, nullptr, 0u, 0u, Y[cur], noise, c.Ntotal, n1, nu,
+                                                       p->partial, p->counter, Y[cur ^ 1], p->mpc_key);
+    p->launches++;
+    CUDA_OK(cudaGetLastError());
+    cur ^= 1;
+  }
+  if (cur != 0) CUDA_OK(cudaMemcpyAsync(Y[0], Y[1], (size_t)n1 * nu * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // the info-only bars of the LAST reverse_once (the one the reference's scan returns)
+  if (n_diffuse > 0 && B.qbar && B.qdbar && B.xbar) {
+    int rc = dial_reverse_trajbar(p, nullptr, 0, B.qbar, B.qdbar, B.xbar, (void*)st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int dial_mpc_step(dial_plan* p, int n_diffuse, int env_step, void* stream) {
+  if (!p) return fail("dial_mpc_step: null plan");
+  if (!p->mpc_bound) return fail("dial_mpc_step: call dial_mpc_bind first");
+  if (n_diffuse < 0 || n_diffuse > 64) return fail("dial_mpc_step: n_diffuse out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  dial_plan::MpcGraph* g = nullptr;
+  for (auto& e : p->mpc_graphs) if (e.n_diffuse == n_diffuse && e.env_step == env_step) g = &e;
+  if (!g) {
+    // first use of this shape: run it eagerly (also configures the kernels' shared-memory limits)
+    p->mpc_graphs.push_back({n_diffuse, env_step, 1, nullptr, 0});
+    return mpc_enqueue(p, n_diffuse, env_step, st);
+  }
+  if (!g->exec) {
+    if (getenv("DIAL_NO_GRAPH")) return mpc_enqueue(p, n_diffuse, env_step, st);
+    // second use: capture the same sequence into a graph, then replay it from now on
+    cudaStream_t cs;
+    CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    const int64_t l0 = p->launches;
+    cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaStreamDestroy(cs); CUDA_OK(e); }
+    int rc = mpc_enqueue(p, n_diffuse, env_step, cs);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(cs, &graph);
+    cudaStreamDestroy(cs);
+    g->launches = p->launches - l0;
+    p->launches = l0;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    CUDA_OK(e);
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_OK(e);
+  }
+  CUDA_OK(cudaGraphLaunch(g->exec, st));
+  p->launches += g->launches;
   return 0;
 }
 

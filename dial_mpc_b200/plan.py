@@ -131,3 +131,24 @@ class Plan:
     def reverse_trajbar(self, weights, rank, qbar, qdbar, xbar):
         self._check(self.lib.dial_reverse_trajbar(self.handle, _ptr(weights), int(rank), _ptr(qbar), _ptr(qdbar),
                                                   _ptr(xbar), _stream()))
+
+    # -- device-resident MPC loop (one CUDA graph per control step) ---------------------------------
+    def mpc_bind(self, bufs: dict, M_shift) -> None:
+        """``bufs``: name -> CUDA tensor for every field of ``dial_mpc_buffers`` (qbar/qdbar/xbar may be
+        None).  The tensors must stay alive and in place while bound (kept on ``self``)."""
+        b = _capi.dial_mpc_buffers()
+        want = {"counters": torch.int32, "rng": torch.int32}
+        for name, _ in _capi.dial_mpc_buffers._fields_:
+            t = bufs.get(name)
+            if t is None:
+                setattr(b, name, None)
+                continue
+            assert t.is_cuda and t.is_contiguous() and t.dtype == want.get(name, torch.float32), name
+            setattr(b, name, t.data_ptr())
+        M = np.ascontiguousarray(M_shift, dtype=np.float32)
+        assert M.shape == (self.Hn + 1, self.Hn + 1)
+        self._mpc_keep = (dict(bufs), b, M)
+        self._check(self.lib.dial_mpc_bind(self.handle, C.byref(b), M.ctypes.data_as(C.c_void_p)))
+
+    def mpc_step(self, n_diffuse: int, env_step: bool = True) -> None:
+        self._check(self.lib.dial_mpc_step(self.handle, int(n_diffuse), int(bool(env_step)), _stream()))

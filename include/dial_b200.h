@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DIAL_ABI_VERSION 3
+#define DIAL_ABI_VERSION 4
 
 /* capacities of the fixed-size device model */
 #define DIAL_MAXB 24   /* bodies incl. world            */
@@ -142,7 +142,7 @@ typedef struct dial_plan dial_plan;
 int dial_abi_version(void);
 const char* dial_last_error(void);
 /* sizeof() of the descriptor structs as compiled into the library: which = 0 model, 1 plan,
- * 2 state (lets foreign-language bindings verify their struct layout). */
+ * 2 state, 3 mpc buffers (lets foreign-language bindings verify their struct layout). */
 size_t dial_sizeof(int which);
 
 /* Create / destroy a plan (uploads model + config, allocates all workspaces). */
@@ -196,6 +196,41 @@ int dial_reverse_update(dial_plan* plan, const float* eps, const uint32_t key[2]
  * qbar [Hs+1,nq], qdbar [Hs+1,nv], xbar [Hs+1,nbody-1,3]. */
 int dial_reverse_trajbar(dial_plan* plan, const float* weights, int rank,
                          float* qbar, float* qdbar, float* xbar, void* stream);
+
+/* ---- Device-resident synchronous MPC loop -------------------------------------------------
+ * The reference's main loop (core/dial_core.py:242-268) is, per control step,
+ *     state = step_env(state, Y0[0]); Y0 = shift(Y0);
+ *     for i < n_diffuse: rng, Y0, info = reverse_once(state, rng, Y0, noise[i])
+ * with one jitted XLA program per piece.  Here the whole step is ONE CUDA graph: state, step
+ * counters, rng and control knots stay in HBM (caller-owned `dial_mpc_buffers`), the key
+ * splitting / shift / counter bookkeeping between kernels runs as tiny glue kernels, and
+ * `dial_mpc_step` only replays the graph (captured on the second use of an
+ * (n_diffuse, env_step) shape; the first use runs eagerly).  Results equal the eager
+ * `dial_env_step` + `dial_reverse_*` sequence.  Single-GPU plans only (Ntotal == Nsample). */
+typedef struct dial_mpc_buffers { /* all [dev], caller-owned, fixed while bound */
+  float* qpos;            /* [nq]  state, advanced in place by the env step                  */
+  float* qvel;            /* [nv]                                                            */
+  float* qacc_warmstart;  /* [nv]                                                            */
+  int32_t* counters;      /* [2]   info["step"], info["contact_stage"]; advanced in place    */
+  uint32_t* rng;          /* [2]   planner rng; each reverse_once splits it                  */
+  float* Y;               /* [Hn+1,nu] control knots, in/out                                 */
+  float* ctrl;            /* [nu]  out: control applied by the env step                      */
+  float* reward;          /* [1]   out: reward of the env step                               */
+  float* rews;            /* [Nsample+1] out: sample rewards of the last reverse_once        */
+  float* qbar;            /* [Hs+1,nq]        nullable (all three or none): bars of the last  */
+  float* qdbar;           /* [Hs+1,nv]        reverse_once                                    */
+  float* xbar;            /* [Hs+1,nbody-1,3]                                                 */
+  const float* noise;     /* [>= n_diffuse][Hn+1] annealing schedule (dial_core.py:259-261)  */
+} dial_mpc_buffers;
+
+/* Bind the state block; M_shift [host][Hn+1][Hn+1] = u2node . roll(-1, last row 0) . node2u
+ * (MBDPI.shift, core/dial_core.py:160-165).  Drops previously captured graphs. */
+int dial_mpc_bind(dial_plan* plan, const dial_mpc_buffers* buffers, const float* M_shift);
+
+/* One control step on `stream`: [env_step: state <- env.step(state, Y[0]); Y <- shift(Y)] then
+ * n_diffuse x reverse_once with noise rows 0..n_diffuse-1.  env_step = 0 plans from the bound
+ * state as it is (deploy/dial_plan.py: the state comes from the robot). */
+int dial_mpc_step(dial_plan* plan, int n_diffuse, int env_step, void* stream);
 
 /* jax.random.split(rng) / the planner's key threading (core/dial_core.py:106,145):
  * host-side Threefry-2x32; out[0] is the new rng, out[1] the sampling key. */

@@ -277,3 +277,55 @@ def test_deploy_planner_cycle_over_shared_memory(built):
         assert torch.allclose(sh[:-1], Y_before[1:], atol=1e-5)
     finally:
         pub.close(unlink=True)
+
+
+@pytest.mark.parametrize("name", ["unitree_go2_seq_jump", "unitree_h1_walk"])
+def test_device_loop_graph_equals_eager_loop(built, name):
+    """The CUDA-graph control step (dial_mpc_step: env.step + shift + Ndiffuse x reverse_once with
+    device-side key splitting / counters) reproduces the eager call sequence of the reference's
+    main loop (core/dial_core.py:242-268): same keys (exact), same rewards and control knots."""
+    from dial_mpc_b200 import random as drandom
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import DeviceLoop, MBDPI
+    env, _ = make_pair(name)
+    args = DialConfig(env_name=name, Nsample=256, Hsample=12, Hnode=4, Ndiffuse=3, Ndiffuse_init=5,
+                      temp_sample=0.05, horizon_diffuse_factor=0.9, traj_diffuse_factor=0.5)
+    mb = MBDPI(args, env)
+    rng = drandom.PRNGKey(3)
+    rng, r0 = drandom.split(rng)
+    state = env.reset(r0)
+    state.info["step"] = 48          # seq-jump: crosses into the second stage during the run
+    if "contact_stage" in state.info:
+        state.info["contact_stage"] = 0
+    Y0 = torch.zeros(args.Hnode + 1, mb.nu, device="cuda")
+    loop = DeviceLoop(mb, state, rng, Y0)
+    nsteps = 4                        # step 0 eager (Ndiffuse_init), 1 eager (Ndiffuse), 2.. graph replays
+    st, Y, r = state, Y0, rng
+    for t in range(nsteps):
+        nd = args.Ndiffuse_init if t == 0 else args.Ndiffuse
+        st = env.step(st, Y[0])
+        Y = mb.shift(Y)
+        r, Y, info = mb.reverse_scan(st, r, Y, mb.schedule(nd))
+        loop.step(nd)
+        torch.cuda.synchronize()
+        s2 = loop.state()
+        # rng chain and counters are integer-exact
+        assert np.array_equal(np.asarray(r, dtype=np.uint32), s2.info["rng"])
+        assert s2.info["step"] == st.info["step"]
+        if "contact_stage" in st.info:
+            assert s2.info["contact_stage"] == st.info["contact_stage"]
+        tol = 1e-5 if t == 0 else 2e-3   # later steps inherit fp32 reordering of the 6x6 shift matmul
+        assert (s2.pipeline_state.qpos - st.pipeline_state.qpos).abs().max() < tol
+        assert abs(float(s2.reward) - float(st.reward)) < tol * (1 + abs(float(st.reward)))
+        assert (loop.Y - Y).abs().max() < 5 * tol
+        assert (loop.info()["rews"] - info["rews"]).abs().max() < 5 * tol * (1 + float(info["rews"].abs().max()))
+        assert (loop.info()["xbar"] - info["xbar"]).abs().max() < 5 * tol
+    assert mb.plan.launches > 0
+    # env_step=False: plan again from the same state (deploy mode) -> state and counters untouched
+    q_before, c_before = loop.buf["qpos"].clone(), loop.buf["counters"].clone()
+    loop.step(2, env_step=False)
+    loop.step(2, env_step=False)
+    loop.step(2, env_step=False)
+    torch.cuda.synchronize()
+    assert torch.equal(q_before, loop.buf["qpos"]) and torch.equal(c_before, loop.buf["counters"])
+    assert torch.isfinite(loop.Y).all()
