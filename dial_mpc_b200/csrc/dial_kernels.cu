@@ -384,6 +384,9 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
   if (wpc == 0) {
     const int per_sm = (A.nrows + p->num_sms - 1) / p->num_sms;
     wpc = per_sm <= 1 ? 1 : per_sm <= 2 ? 2 : per_sm <= 4 ? 4 : per_sm <= 8 ? 8 : per_sm <= 14 ? 14 : 16;
+    // more than one wave of rows (tree path): two resident 8-warp CTAs per SM overlap each other's
+    // barriers and tail (Go2 N=8192: 3.81 ms vs 3.85 / 3.93 ms for 14 / 16 warps per CTA)
+    if (per_sm > 14 && !p->hM.dense) wpc = 8;
     // respect the 227 KB shared-memory limit of one CTA
     const size_t fixed = sizeof(DevModel) + sizeof(DevPlan), slab = (size_t)p->hM.warp_floats * sizeof(float);
     const int opts[6] = {16, 14, 8, 4, 2, 1};
