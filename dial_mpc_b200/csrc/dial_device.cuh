@@ -77,7 +77,7 @@ struct alignas(16) DevModel {
   // per-warp shared-memory layout (float offsets)
   int32_t o_xpos, o_xquat, o_xmat, o_xipos, o_cinert, o_cdof, o_cdofdot, o_cvel, o_cacc,
       o_cfrc, o_Mb, o_L, o_J, o_qpos, o_qvel, o_warm, o_ctrl, o_vec, o_frow, o_cpos,
-      o_cframe, o_cdist, o_rcom, o_xch, o_crb, o_cfs, o_Md, o_Ld, o_Jd, o_Gd, o_frow2, o_cact, warp_floats;
+      o_cframe, o_cdist, o_rcom, o_xch, o_crb, o_cfs, o_Md, o_Ld, o_Jd, o_Gd, o_frow2, o_cact, o_hcs, warp_floats;
   int32_t pad_[3];
 };
 
@@ -780,22 +780,35 @@ struct ConeLane {
 };
 
 DEV void dense_mul_J(WarpCtx& w, const ConeLane& C, float xd, float* out) {
-  const int nv = w.M->m.nv, lane = w.lane;
+  // contact lane c returns J_c x (its <= 6 rows).  The instantiated contacts are few and the dofs
+  // many, so every dof lane multiplies its column and the rows are summed by xor-shuffles (all
+  // lanes busy) instead of one contact lane walking the 22 columns alone.
+  const DevModel& M = *w.M;
+  const int nv = M.m.nv, lane = w.lane;
   const float* Jd = SM(Jd);
-  float* vec = SM(vec);
-  syncwarp();
-  vec[lane] = xd;
-  syncwarp();
+  const int* cact = reinterpret_cast<const int*>(SM(cact));
 #pragma unroll
   for (int i = 0; i < 6; ++i) out[i] = 0.f;
-  if (C.inst) {
-    for (int d = 0; d < nv; ++d) {
-      const float xv = vec[d];
+  const float xv = lane < nv ? xd : 0.f;
+  const int col = lane < nv ? lane : 0;
+  for (int c = 0; c < M.m.ncon; ++c) {
+    if (!cact[c]) continue;   // warp-uniform
+    const int r0 = M.con_row0[c], dim = M.con_dim[c];
+    float p[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) p[i] = (i < dim) ? Jd[(r0 + i) * nv + col] * xv : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
       for (int i = 0; i < 6; ++i)
-        if (i < C.dim) out[i] += Jd[(C.r0 + i) * nv + d] * xv;
+        if (i < dim) p[i] += shfl_xor(p[i], o);
+    }
+    if (lane == c) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) out[i] = p[i];
     }
   }
+  (void)C;
 }
 
 // rows of G (same shape as J) times ... J^T f: contact lanes publish f, dof lanes gather
@@ -923,27 +936,24 @@ DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C, float* Hr
   float* Gd = SM(Gd);
   const float* Md = SM(Md);
   int* cact = reinterpret_cast<int*>(SM(cact));
+  float* hcs = SM(hcs);   // 6x6 cone Hessian of the contact being expanded
   syncwarp();
+  // contact lanes: zone of their cone (cact: 1 top = no curvature, 2 bottom, 3 middle) and, for
+  // the middle zone, the analytic Hessian of 0.5 Dm mu^2 (x0 - T)^2, y_i = fri_i x_i, s = x0 - T
+  float Hc[6][6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) Hc[i][j] = 0.f;
   if (lane < M.m.ncon) {
     float cc, f[6], N, T;
     const int zone = cone_eval(C, C.x, cc, f, N, T);
-    cact[lane] = C.inst ? (zone != 0 ? 2 : 1) : 0;   // 2: contributes to H
-    if (zone == 2) {
-      for (int d = 0; d < nv; ++d)
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-          if (i < C.dim) Gd[(C.r0 + i) * nv + d] = C.D[i] * Jd[(C.r0 + i) * nv + d];
-    } else if (zone == 1) {
-      // analytic Hessian of 0.5 Dm mu^2 (x0 - T)^2, y_i = fri_i x_i, s = x0 - T
-      float Hc[6][6];
+    cact[lane] = C.inst ? (zone == 2 ? 2 : zone == 1 ? 3 : 1) : 0;
+    if (C.inst && zone == 1) {
       const float sc = C.Dm * C.mu * C.mu, s = C.x[0] - T, iT = 1.f / T;
       float y[6];
 #pragma unroll
       for (int i = 1; i < 6; ++i) y[i] = (i < C.dim) ? C.x[i] * C.fri[i - 1] : 0.f;
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) Hc[i][j] = 0.f;
       Hc[0][0] = sc;
 #pragma unroll
       for (int i = 1; i < 6; ++i) {
@@ -955,21 +965,46 @@ DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C, float* Hr
               Hc[i][j] = sc * C.fri[i - 1] * C.fri[j - 1] * (y[i] * y[j] * iT * iT * (1.f + s * iT) - (i == j ? s * iT : 0.f));
         }
       }
-      for (int d = 0; d < nv; ++d) {
-        float jc[6];
+    }
+  }
+  syncwarp();
+  // G rows of the curved contacts, one dof column per lane (the contacts are few, the dofs many)
+  for (int c = 0; c < M.m.ncon; ++c) {
+    const int z = cact[c];   // warp-uniform
+    if (z < 2) continue;
+    const int r0 = M.con_row0[c], dim = M.con_dim[c];
+    if (z == 3) {
+      if (lane == c) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) jc[i] = (i < C.dim) ? Jd[(C.r0 + i) * nv + d] : 0.f;
+        for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          if (i < C.dim) {
-            float a = 0.f;
+          for (int j = 0; j < 6; ++j) hcs[i * 6 + j] = Hc[i][j];
+      }
+      syncwarp();
+    }
+    float Dc[6];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) a += Hc[i][j] * jc[j];
-            Gd[(C.r0 + i) * nv + d] = a;
+    for (int i = 0; i < 6; ++i) Dc[i] = shfl(C.D[i], c);
+    if (lane < nv) {
+      float jc[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) jc[i] = (i < dim) ? Jd[(r0 + i) * nv + lane] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (i < dim) {
+          float a;
+          if (z == 2) {
+            a = Dc[i] * jc[i];
+          } else {
+            a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) a += hcs[i * 6 + j] * jc[j];
           }
+          Gd[(r0 + i) * nv + lane] = a;
         }
       }
     }
+    if (z == 3) syncwarp();
   }
   syncwarp();
 #pragma unroll
@@ -981,7 +1016,7 @@ DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C, float* Hr
     for (int j = 0; j < NVD; ++j)
       if (j == lane) Hrow[j] += (S.l_Jaref < 0.f) ? S.l_D : 0.f;
     for (int c = 0; c < M.m.ncon; ++c) {
-      if (cact[c] != 2) continue;
+      if (cact[c] < 2) continue;
       const int r0 = M.con_row0[c], dim = M.con_dim[c];
       for (int i = 0; i < dim; ++i) {
         const float a = Jd[(r0 + i) * nv + lane];
@@ -1007,56 +1042,74 @@ DEV float dense_mul_M(WarpCtx& w, float x) {
   return y;
 }
 
-// line-search point: cost and derivatives at up to NA alphas (limit rows + cones)
-template <int NA>
-DEV void dense_ls_points(const Solver& S, const ConeLane& C, float l_jv, const float* cv, const float* qg,
-                         const float* al, LSPoint* out) {
-  float s[3 * NA];
-#pragma unroll
-  for (int i = 0; i < 3 * NA; ++i) s[i] = 0.f;
-  {
-    const float q0 = 0.5f * S.l_Jaref * S.l_Jaref * S.l_D, q1 = l_jv * S.l_Jaref * S.l_D, q2 = 0.5f * l_jv * l_jv * S.l_D;
-#pragma unroll
-    for (int i = 0; i < NA; ++i)
-      if (S.l_Jaref + al[i] * l_jv < 0.f) {
-        s[3 * i] += al[i] * al[i] * q2 + al[i] * q1 + q0;
-        s[3 * i + 1] += 2.f * al[i] * q2 + q1;
-        s[3 * i + 2] += 2.f * q2;
-      }
-  }
+// Per-lane coefficients of the 1-D cost along the search direction; constant during one line
+// search (mjx solver._linesearch evaluates them inside every point; hoisted here).
+struct LSCoef {
+  float q0, q1, q2;                       // limit row of this dof lane: quadratic in alpha
+  float Q0, Q1, Q2, UU, UV, VV, U0, V0;   // cone of this contact lane (mjx _eval_pt_elliptic)
+};
+
+DEV LSCoef dense_ls_coef(const Solver& S, const ConeLane& C, float l_jv, const float* cv) {
+  LSCoef K;
+  K.q0 = 0.5f * S.l_Jaref * S.l_Jaref * S.l_D; K.q1 = l_jv * S.l_Jaref * S.l_D; K.q2 = 0.5f * l_jv * l_jv * S.l_D;
+  K.Q0 = K.Q1 = K.Q2 = K.UU = K.UV = K.VV = 0.f;
   if (C.inst) {
-    float Q0 = 0.f, Q1 = 0.f, Q2 = 0.f, UU = 0.f, UV = 0.f, VV = 0.f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       if (i < C.dim) {
-        Q0 += 0.5f * C.x[i] * C.x[i] * C.D[i]; Q1 += cv[i] * C.x[i] * C.D[i]; Q2 += 0.5f * cv[i] * cv[i] * C.D[i];
+        K.Q0 += 0.5f * C.x[i] * C.x[i] * C.D[i]; K.Q1 += cv[i] * C.x[i] * C.D[i]; K.Q2 += 0.5f * cv[i] * cv[i] * C.D[i];
         if (i > 0) {
           const float f2 = C.fri[i - 1] * C.fri[i - 1];
-          UU += C.x[i] * C.x[i] * f2; UV += C.x[i] * cv[i] * f2; VV += cv[i] * cv[i] * f2;
+          K.UU += C.x[i] * C.x[i] * f2; K.UV += C.x[i] * cv[i] * f2; K.VV += cv[i] * cv[i] * f2;
         }
       }
     }
-    const float U0 = C.mu * C.x[0], V0 = C.mu * cv[0];
+  }
+  K.U0 = C.mu * C.x[0]; K.V0 = C.mu * cv[0];
+  return K;
+}
+
+// line-search points: derivatives (and, with COST, the cost) at NA alphas (limit rows + cones).
+// The bracketing loop needs only d0 / d1; the costs of the surviving points are evaluated once
+// at the end (same expressions), which removes a third of the warp reductions.
+template <int NA, bool COST>
+DEV void dense_ls_points(const Solver& S, const ConeLane& C, const LSCoef& K, float l_jv, const float* cv,
+                         const float* qg, const float* al, LSPoint* out) {
+  float s[3 * NA];
+#pragma unroll
+  for (int i = 0; i < 3 * NA; ++i) s[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NA; ++i)
+    if (S.l_Jaref + al[i] * l_jv < 0.f) {
+      if (COST) s[3 * i] += al[i] * al[i] * K.q2 + al[i] * K.q1 + K.q0;
+      s[3 * i + 1] += 2.f * al[i] * K.q2 + K.q1;
+      s[3 * i + 2] += 2.f * K.q2;
+    }
+  if (C.inst) {
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
       const float a = al[i];
       if (C.dim == 1) {
-        if (C.x[0] + a * cv[0] < 0.f) { s[3 * i] += a * a * Q2 + a * Q1 + Q0; s[3 * i + 1] += 2.f * a * Q2 + Q1; s[3 * i + 2] += 2.f * Q2; }
+        if (C.x[0] + a * cv[0] < 0.f) {
+          if (COST) s[3 * i] += a * a * K.Q2 + a * K.Q1 + K.Q0;
+          s[3 * i + 1] += 2.f * a * K.Q2 + K.Q1; s[3 * i + 2] += 2.f * K.Q2;
+        }
         continue;
       }
-      const float N = U0 + a * V0;
-      const float Tsq = UU + a * (2.f * UV + a * VV);
+      const float N = K.U0 + a * K.V0;
+      const float Tsq = K.UU + a * (2.f * K.UV + a * K.VV);
       const float T = sqrtf(fmaxf(Tsq, 0.f));
       const bool bottom = (Tsq <= 0.f && N < 0.f) || (Tsq > 0.f && C.mu * N + T <= 0.f);
       const bool middle = (Tsq > 0.f) && (N < C.mu * T) && (C.mu * N + T > 0.f);
       if (bottom) {
-        s[3 * i] += a * a * Q2 + a * Q1 + Q0; s[3 * i + 1] += 2.f * a * Q2 + Q1; s[3 * i + 2] += 2.f * Q2;
+        if (COST) s[3 * i] += a * a * K.Q2 + a * K.Q1 + K.Q0;
+        s[3 * i + 1] += 2.f * a * K.Q2 + K.Q1; s[3 * i + 2] += 2.f * K.Q2;
       } else if (middle) {
         const float iT = 1.f / T;
-        const float T1 = (UV + a * VV) * iT;
-        const float T2 = (VV - T1 * T1) * iT;   // VV/T - (UV + a VV) T1 / T^2
-        const float NmT = N - C.mu * T, dN = V0 - C.mu * T1;
-        s[3 * i] += 0.5f * C.Dm * NmT * NmT;
+        const float T1 = (K.UV + a * K.VV) * iT;
+        const float T2 = (K.VV - T1 * T1) * iT;   // VV/T - (UV + a VV) T1 / T^2
+        const float NmT = N - C.mu * T, dN = K.V0 - C.mu * T1;
+        if (COST) s[3 * i] += 0.5f * C.Dm * NmT * NmT;
         s[3 * i + 1] += C.Dm * NmT * dN;
         s[3 * i + 2] += C.Dm * (dN * dN + NmT * (-C.mu * T2));
       }
@@ -1065,13 +1118,14 @@ DEV void dense_ls_points(const Solver& S, const ConeLane& C, float l_jv, const f
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int i = 0; i < 3 * NA; ++i) s[i] += shfl_xor(s[i], o);
+    for (int i = 0; i < 3 * NA; ++i)
+      if (COST || (i % 3) != 0) s[i] += shfl_xor(s[i], o);
   }
 #pragma unroll
   for (int i = 0; i < NA; ++i) {
     const float a = al[i];
     out[i].alpha = a;
-    out[i].cost = a * a * qg[2] + a * qg[1] + qg[0] + s[3 * i];
+    out[i].cost = COST ? a * a * qg[2] + a * qg[1] + qg[0] + s[3 * i] : 0.f;
     out[i].d0 = 2.f * a * qg[2] + qg[1] + s[3 * i + 1];
     const float d1 = 2.f * qg[2] + s[3 * i + 2];
     out[i].d1 = d1 + (d1 == 0.f ? DIAL_MINVAL : 0.f);
@@ -1090,11 +1144,12 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
   warp_sum3(ss, sMa, sMv);
   float gtol = M.m.tolerance * M.m.ls_tolerance * sqrtf(ss) * scale;
   float qg[3] = {S.gauss, sMa, 0.5f * sMv};
+  const LSCoef K = dense_ls_coef(S, C, l_jv, cv);
   LSPoint p0, lo, hi;
   float a1[1] = {0.f};
-  dense_ls_points<1>(S, C, l_jv, cv, qg, a1, &p0);
+  dense_ls_points<1, true>(S, C, K, l_jv, cv, qg, a1, &p0);
   a1[0] = p0.alpha - p0.d0 / p0.d1;
-  dense_ls_points<1>(S, C, l_jv, cv, qg, a1, &lo);
+  dense_ls_points<1, false>(S, C, K, l_jv, cv, qg, a1, &lo);
   if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
   bool swap = true;
   // In fp32 the bracket can rarely reach `gtol` (the derivative noise is orders of magnitude above
@@ -1112,8 +1167,7 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
     if (done) break;
     if (stop_at == M.m.ls_iterations && it > 0) {
       const bool same = swap == snap_swap && lo.alpha == snap_lo.alpha && hi.alpha == snap_hi.alpha &&
-                        lo.d0 == snap_lo.d0 && hi.d0 == snap_hi.d0 && lo.d1 == snap_lo.d1 && hi.d1 == snap_hi.d1 &&
-                        lo.cost == snap_lo.cost && hi.cost == snap_hi.cost;
+                        lo.d0 == snap_lo.d0 && hi.d0 == snap_hi.d0 && lo.d1 == snap_lo.d1 && hi.d1 == snap_hi.d1;
       if (same) {
         const int period = it - snap_it;
         stop_at = it + (M.m.ls_iterations - it) % period;
@@ -1124,7 +1178,7 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
     }
     LSPoint pt[3];
     float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
-    dense_ls_points<3>(S, C, l_jv, cv, qg, a3, pt);
+    dense_ls_points<3, false>(S, C, K, l_jv, cv, qg, a3, pt);
     const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
     bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
     if (swap_lo_next) lo = lo_next;
@@ -1135,6 +1189,13 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
     bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
     if (swap_hi_mid) hi = mid;
     swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+  }
+  // costs of the two surviving points (mjx carries them along; same expressions, evaluated once)
+  {
+    LSPoint fin[2];
+    float a2[2] = {lo.alpha, hi.alpha};
+    dense_ls_points<2, true>(S, C, K, l_jv, cv, qg, a2, fin);
+    lo.cost = fin[0].cost; hi.cost = fin[1].cost;
   }
   bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
   float alpha = (lo.cost < hi.cost) ? lo.alpha : hi.alpha;

@@ -187,7 +187,7 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = take(nv * DIAL_MAXCHAIN); D.o_crb = take(10 * nb); D.o_cfs = take(6 * nb);
   if (D.dense) {
     D.o_Md = take(nv * nv); D.o_Ld = 0; D.o_Jd = take(D.nrow_c * nv); D.o_Gd = take(D.nrow_c * nv);
-    D.o_frow2 = take(D.nrow_c); D.o_cact = take(DIAL_MAXC);
+    D.o_frow2 = take(D.nrow_c); D.o_cact = take(DIAL_MAXC); D.o_hcs = take(36);
   }
   D.warp_floats = o;
   return true;

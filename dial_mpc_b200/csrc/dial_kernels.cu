@@ -386,7 +386,16 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
     wpc = per_sm <= 1 ? 1 : per_sm <= 2 ? 2 : per_sm <= 4 ? 4 : per_sm <= 8 ? 8 : per_sm <= 14 ? 14 : 16;
     // more than one wave of rows (tree path): two resident 8-warp CTAs per SM overlap each other's
     // barriers and tail (Go2 N=8192: 3.81 ms vs 3.85 / 3.93 ms for 14 / 16 warps per CTA)
-    if (per_sm > 14 && !p->hM.dense) wpc = 8;
+    // (only when two such CTAs fit the SM's 228 KB of shared memory, 1 KB reserved per CTA)
+    {
+      const size_t cta8 = sizeof(DevModel) + sizeof(DevPlan) + 8 * (size_t)p->hM.warp_floats * sizeof(float) + 1024;
+      if (per_sm > 14 && !p->hM.dense && 2 * cta8 <= 228 * 1024) wpc = 8;
+      else if (per_sm > 16 && !p->hM.dense) {
+        // one CTA per SM: balance the waves (H1 N=8192: 4 waves of 14 beat 3.5 waves of 16, 5.57 vs 5.76 ms)
+        const int waves = (per_sm + 15) / 16;
+        wpc = (per_sm + waves - 1) / waves <= 14 ? 14 : 16;
+      }
+    }
     // respect the 227 KB shared-memory limit of one CTA
     const size_t fixed = sizeof(DevModel) + sizeof(DevPlan), slab = (size_t)p->hM.warp_floats * sizeof(float);
     const int opts[6] = {16, 14, 8, 4, 2, 1};
