@@ -933,7 +933,7 @@ DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C, float* Hr
   const DevModel& M = *w.M;
   const int nv = M.m.nv, lane = w.lane;
   const float* Jd = SM(Jd);
-  float* Gd = SM(Gd);
+  float* Gs = SM(Gd);     // G rows of ONE contact (6 x nv scratch)
   const float* Md = SM(Md);
   int* cact = reinterpret_cast<int*>(SM(cact));
   float* hcs = SM(hcs);   // 6x6 cone Hessian of the contact being expanded
@@ -968,27 +968,36 @@ DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C, float* Hr
     }
   }
   syncwarp();
-  // G rows of the curved contacts, one dof column per lane (the contacts are few, the dofs many)
+  // H rows: lane i holds H[i][0..i].  Start from M + the active limit row, then add J_c^T G_c for
+  // every curved contact: G_c (<= 6 x nv) is formed in a small scratch with one dof column per lane
+  // (the contacts are few, the dofs many) and consumed at once, so no nrow x nv copy of G exists.
+#pragma unroll
+  for (int j = 0; j < NVD; ++j) Hrow[j] = 0.f;
+  if (lane < nv) {
+#pragma unroll
+    for (int j = 0; j < NVD; ++j) Hrow[j] = (j <= lane) ? Md[lane * nv + j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < NVD; ++j)
+      if (j == lane) Hrow[j] += (S.l_Jaref < 0.f) ? S.l_D : 0.f;
+  }
   for (int c = 0; c < M.m.ncon; ++c) {
     const int z = cact[c];   // warp-uniform
     if (z < 2) continue;
     const int r0 = M.con_row0[c], dim = M.con_dim[c];
-    if (z == 3) {
-      if (lane == c) {
+    if (z == 3 && lane == c) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int j = 0; j < 6; ++j) hcs[i * 6 + j] = Hc[i][j];
-      }
-      syncwarp();
+        for (int j = 0; j < 6; ++j) hcs[i * 6 + j] = Hc[i][j];
     }
+    syncwarp();   // hcs published; previous contact's Gs fully consumed
     float Dc[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) Dc[i] = shfl(C.D[i], c);
-    if (lane < nv) {
-      float jc[6];
+    float jc[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) jc[i] = (i < dim) ? Jd[(r0 + i) * nv + lane] : 0.f;
+    for (int i = 0; i < 6; ++i) jc[i] = (i < dim && lane < nv) ? Jd[(r0 + i) * nv + lane] : 0.f;
+    if (lane < nv) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         if (i < dim) {
@@ -1000,32 +1009,21 @@ DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C, float* Hr
 #pragma unroll
             for (int j = 0; j < 6; ++j) a += hcs[i * 6 + j] * jc[j];
           }
-          Gd[(r0 + i) * nv + lane] = a;
+          Gs[i * nv + lane] = a;
         }
       }
     }
-    if (z == 3) syncwarp();
-  }
-  syncwarp();
-#pragma unroll
-  for (int j = 0; j < NVD; ++j) Hrow[j] = 0.f;
-  if (lane < nv) {
-#pragma unroll
-    for (int j = 0; j < NVD; ++j) Hrow[j] = (j <= lane) ? Md[lane * nv + j] : 0.f;
-#pragma unroll
-    for (int j = 0; j < NVD; ++j)
-      if (j == lane) Hrow[j] += (S.l_Jaref < 0.f) ? S.l_D : 0.f;
-    for (int c = 0; c < M.m.ncon; ++c) {
-      if (cact[c] < 2) continue;
-      const int r0 = M.con_row0[c], dim = M.con_dim[c];
+    syncwarp();
+    if (lane < nv) {
       for (int i = 0; i < dim; ++i) {
-        const float a = Jd[(r0 + i) * nv + lane];
-        const float* Gr = Gd + (r0 + i) * nv;
+        const float a = jc[i];
+        const float* Gr = Gs + i * nv;
 #pragma unroll
         for (int j = 0; j < NVD; ++j) Hrow[j] += a * Gr[j];
       }
     }
   }
+  syncwarp();
 }
 
 // dense M x (lane = dof)
@@ -1693,10 +1691,12 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
     for (int c = 0; c < MCU; ++c)
       if (c < w.nch) Mrow[c] = dot6(f, cdof + 6 * w.chain[c]);
     Mrow[0] += m.dof_armature[d];
-    float* Mb = SM(Mb);
+    if constexpr (NL >= 0) {   // the dense path keeps M in SM(Md) instead
+      float* Mb = SM(Mb);
 #pragma unroll
-    for (int c = 0; c < MCU; ++c)
-      if (c < w.nch) Mb[d * MC + c] = Mrow[c];
+      for (int c = 0; c < MCU; ++c)
+        if (c < w.nch) Mb[d * MC + c] = Mrow[c];
+    }
     float bias = dot6(cdof + 6 * d, SM(cfs) + 6 * bi);
     float act = 0.f;
     int a = M.dof_actuator[d];

@@ -181,13 +181,17 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   D.o_xpos = take(3 * nb); D.o_xquat = take(4 * nb); D.o_xmat = take(9 * nb); D.o_xipos = take(3 * nb);
   D.o_cinert = take(10 * nb); D.o_cdof = take(6 * nv); D.o_cdofdot = take(6 * nv);
   D.o_cvel = take(6 * nb); D.o_cacc = take(6 * nb); D.o_cfrc = take(6 * nb);
-  D.o_Mb = take(nv * DIAL_MAXCHAIN); D.o_L = take(nv * DIAL_MAXCHAIN); D.o_J = take(D.nedge * DIAL_MAXCHAIN);
+  // compact-chain M / factor / contact rows and the published solve chains: tree paths only
+  if (!D.dense) { D.o_Mb = take(nv * DIAL_MAXCHAIN); D.o_L = take(nv * DIAL_MAXCHAIN); D.o_J = take(D.nedge * DIAL_MAXCHAIN); }
+  else { D.o_Mb = D.o_L = D.o_J = 0; }
   D.o_qpos = take(m.nq); D.o_qvel = take(nv); D.o_warm = take(nv); D.o_ctrl = take(m.nu);
   D.o_vec = take(32); D.o_frow = take(32); D.o_cpos = take(3 * m.ncon); D.o_cframe = take(9 * m.ncon);
-  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = take(nv * DIAL_MAXCHAIN); D.o_crb = take(10 * nb); D.o_cfs = take(6 * nb);
+  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = D.dense ? 0 : take(nv * DIAL_MAXCHAIN); D.o_crb = take(10 * nb); D.o_cfs = take(6 * nb);
   if (D.dense) {
-    D.o_Md = take(nv * nv); D.o_Ld = 0; D.o_Jd = take(D.nrow_c * nv); D.o_Gd = take(D.nrow_c * nv);
-    D.o_frow2 = take(D.nrow_c); D.o_cact = take(DIAL_MAXC); D.o_hcs = take(36);
+    // Gd: G rows of one contact at a time (6 x nv); hcs (6x6 cone Hessian) overlays vec|frow
+    // (64 contiguous floats, idle while H is assembled).  17 KB per warp -> 12 warps per SM.
+    D.o_Md = take(nv * nv); D.o_Ld = 0; D.o_Jd = take(D.nrow_c * nv); D.o_Gd = take(6 * nv);
+    D.o_frow2 = take(D.nrow_c); D.o_cact = take(DIAL_MAXC); D.o_hcs = D.o_vec;
   }
   D.warp_floats = o;
   return true;
