@@ -67,6 +67,11 @@ struct alignas(16) DevModel {
   int32_t con_pair[DIAL_MAXC], con_sub[DIAL_MAXC];
   int32_t dense;                      // 1: dense / elliptic solver path (NL < 0)
   int32_t con_row0[DIAL_MAXC], con_dim[DIAL_MAXC], nrow_c;
+  // dense path: a contact row is non-zero only at the dofs that move exactly one of its two
+  // bodies, so J rows are stored with `jd_stride` packed columns; con_colidx[c][d] = packed
+  // column of dof d in the rows of contact c, or -1 (structural zero)
+  int32_t jd_stride;
+  int8_t con_colidx[DIAL_MAXC][DIAL_MAXV];
   int32_t con_lastdof[DIAL_MAXC];     // deepest dof moving the contact's body (geom1 must be static)
   int32_t dof_nchain[DIAL_MAXV], dof_ndesc[DIAL_MAXV], nlimited;
   int32_t chain_tab[DIAL_MAXV][DIAL_MAXCHAIN];
@@ -790,13 +795,14 @@ DEV void dense_mul_J(WarpCtx& w, const ConeLane& C, float xd, float* out) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) out[i] = 0.f;
   const float xv = lane < nv ? xd : 0.f;
-  const int col = lane < nv ? lane : 0;
+  const int col = lane < nv ? lane : 0, js = M.jd_stride;
   for (int c = 0; c < M.m.ncon; ++c) {
     if (!cact[c]) continue;   // warp-uniform
     const int r0 = M.con_row0[c], dim = M.con_dim[c];
+    const int idx = M.con_colidx[c][col];
     float p[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) p[i] = (i < dim) ? Jd[(r0 + i) * nv + col] * xv : 0.f;
+    for (int i = 0; i < 6; ++i) p[i] = (i < dim && idx >= 0) ? Jd[(r0 + i) * js + idx] * xv : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -830,7 +836,9 @@ DEV float dense_mul_JT(WarpCtx& w, const ConeLane& C, const float* f) {
     for (int c = 0; c < M.m.ncon; ++c) {
       if (!cact[c]) continue;
       const int r0 = M.con_row0[c], dim = M.con_dim[c];
-      for (int i = 0; i < dim; ++i) y += Jd[(r0 + i) * nv + lane] * fr[r0 + i];
+      const int idx = M.con_colidx[c][lane];
+      if (idx < 0) continue;
+      for (int i = 0; i < dim; ++i) y += Jd[(r0 + i) * M.jd_stride + idx] * fr[r0 + i];
     }
   }
   return y;
@@ -995,8 +1003,9 @@ DEV void dense_build_H(WarpCtx& w, const Solver& S, const ConeLane& C, float* Hr
 #pragma unroll
     for (int i = 0; i < 6; ++i) Dc[i] = shfl(C.D[i], c);
     float jc[6];
+    const int idx = lane < nv ? M.con_colidx[c][lane] : -1;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) jc[i] = (i < dim && lane < nv) ? Jd[(r0 + i) * nv + lane] : 0.f;
+    for (int i = 0; i < 6; ++i) jc[i] = (i < dim && idx >= 0) ? Jd[(r0 + i) * M.jd_stride + idx] : 0.f;
     if (lane < nv) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
@@ -1243,10 +1252,12 @@ DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float
       const int b1 = m.geom_bodyid[m.pair_geom1[k]], b2 = m.geom_bodyid[m.pair_geom2[k]];
       const float sgn = (float)((M.body_dofmask[b2] >> d) & 1u) - (float)((M.body_dofmask[b1] >> d) & 1u);
       const int r0 = M.con_row0[c], dim = M.con_dim[c];
+      const int idx = M.con_colidx[c][d];
+      if (idx < 0) continue;   // sgn == 0: dof d moves both bodies or neither
       V3 jp = (cl_ + cross(ca_, ld3(cpos + 3 * c) - rc)) * sgn, jr = ca_ * sgn;
       for (int i = 0; i < dim; ++i) {
         V3 fr = ld3(cframe + 9 * c + 3 * (i % 3));
-        Jd[(r0 + i) * nv + d] = dot(fr, i < 3 ? jp : jr);
+        Jd[(r0 + i) * M.jd_stride + idx] = dot(fr, i < 3 ? jp : jr);
       }
     }
     // joint-limit row of this dof

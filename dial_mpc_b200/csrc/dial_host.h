@@ -154,6 +154,13 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
       for (int s = 0; s < m.pair_ncon[k]; ++s) {
         D.con_pair[c] = k; D.con_sub[c] = s; D.con_lastdof[c] = 0;
         D.con_dim[c] = m.pair_condim[k]; D.con_row0[c] = D.nrow_c; D.nrow_c += m.pair_condim[k];
+        // packed columns of this contact's rows: the dofs that move exactly one of the two bodies
+        int ncol = 0;
+        for (int d = 0; d < DIAL_MAXV; ++d) {
+          const bool nz = d < nv && (((D.body_dofmask[b1] >> d) & 1u) != ((D.body_dofmask[b2] >> d) & 1u));
+          D.con_colidx[c][d] = nz ? (int8_t)ncol++ : (int8_t)-1;
+        }
+        if (ncol > D.jd_stride) D.jd_stride = ncol;
         ++c;
       }
       continue;
@@ -188,9 +195,10 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   D.o_vec = take(32); D.o_frow = take(32); D.o_cpos = take(3 * m.ncon); D.o_cframe = take(9 * m.ncon);
   D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = D.dense ? 0 : take(nv * DIAL_MAXCHAIN); D.o_crb = take(10 * nb); D.o_cfs = take(6 * nb);
   if (D.dense) {
-    // Gd: G rows of one contact at a time (6 x nv); hcs (6x6 cone Hessian) overlays vec|frow
-    // (64 contiguous floats, idle while H is assembled).  17 KB per warp -> 12 warps per SM.
-    D.o_Md = take(nv * nv); D.o_Ld = 0; D.o_Jd = take(D.nrow_c * nv); D.o_Gd = take(6 * nv);
+    // Jd: packed columns (jd_stride); Gd: G rows of one contact at a time (6 x nv); hcs (6x6 cone
+    // Hessian) overlays vec|frow (64 contiguous floats, idle while H is assembled).
+    // Allegro: 14 KB per warp -> 14 warps per SM (26.6 KB / 8 warps before).
+    D.o_Md = take(nv * nv); D.o_Ld = 0; D.o_Jd = take(D.nrow_c * D.jd_stride); D.o_Gd = take(6 * nv);
     D.o_frow2 = take(D.nrow_c); D.o_cact = take(DIAL_MAXC); D.o_hcs = D.o_vec;
   }
   D.warp_floats = o;

@@ -398,10 +398,9 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
     }
     // respect the 227 KB shared-memory limit of one CTA
     const size_t fixed = sizeof(DevModel) + sizeof(DevPlan), slab = (size_t)p->hM.warp_floats * sizeof(float);
-    // (12 warps per CTA is instantiated for the dense path only: its 17 KB slab fits 12 times)
-    const int opts[7] = {16, 14, 12, 8, 4, 2, 1};
-    for (int o = 0; o < 7; ++o)
-      if (opts[o] <= wpc && (opts[o] != 12 || p->hM.dense) && fixed + opts[o] * slab <= 227 * 1024) { wpc = opts[o]; break; }
+    const int opts[6] = {16, 14, 8, 4, 2, 1};
+    for (int o = 0; o < 6; ++o)
+      if (opts[o] <= wpc && fixed + opts[o] * slab <= 227 * 1024) { wpc = opts[o]; break; }
   }
   // lock-step pays off when the warps of a CTA do similar work; the dense (elliptic) path has a
   // heavy-tailed iteration count per sample, so its warps run free (measured 172 vs 221 ms)
@@ -414,9 +413,6 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
     case 4: return launch_rollout<4>(p, A, st);
     case 8: return launch_rollout<8>(p, A, st);
     case 14: return launch_rollout<14>(p, A, st);
-#if DIAL_HAS_VARIANT(3)
-    case 12: if (p->variant == 3) return launch_rollout_t<12, -1, 22>(p, A, st); else return cudaErrorInvalidValue;
-#endif
     default: return launch_rollout<16>(p, A, st);
   }
 }
