@@ -86,4 +86,13 @@ def build_library(reward_path: str, model=None, variant: Optional[int] = None, f
             os.remove(tmp)
         raise RuntimeError(f"nvcc failed for {reward_path}:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, out)  # atomic: concurrent ranks may build the same library
+    # superseded builds of the same reward (older kernel or reward sources) are dropped
+    import glob
+    stem = os.path.splitext(os.path.basename(reward_path))[0]
+    for old in glob.glob(os.path.join(CACHE_DIR, f"libdial_b200_{stem}_v{variant}_*.so")):
+        if old != out:
+            try:
+                os.remove(old)
+            except OSError:
+                pass
     return out
