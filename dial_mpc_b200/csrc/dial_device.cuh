@@ -1172,6 +1172,7 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
     if (done) break;
+#ifndef DIAL_NO_LS_CYCLE   // (tests build the emulator both ways and compare bit for bit)
     if (stop_at == M.m.ls_iterations && it > 0) {
       const bool same = swap == snap_swap && lo.alpha == snap_lo.alpha && hi.alpha == snap_hi.alpha &&
                         lo.d0 == snap_lo.d0 && hi.d0 == snap_hi.d0 && lo.d1 == snap_lo.d1 && hi.d1 == snap_hi.d1;
@@ -1183,6 +1184,7 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
         snap_lo = lo; snap_hi = hi; snap_swap = swap; snap_it = it; power *= 2;
       }
     }
+#endif
     LSPoint pt[3];
     float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
     dense_ls_points<3, false>(S, C, K, l_jv, cv, qg, a3, pt);

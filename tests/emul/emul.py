@@ -11,7 +11,7 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_DIR, "libdial_emul.so")
 
 
-def build(force=False, reward_source=None):
+def build(force=False, reward_source=None, defines=()):
     """g++ build of the device code for the lock-step warp emulator.  ``reward_source``: a custom
     reward file (include/dial_custom_reward.h) compiled in, as dial_mpc_b200.custom does with nvcc."""
     srcs = [os.path.join(_DIR, "emul_main.cpp"), os.path.join(_DIR, "warp_emul.h"),
@@ -26,6 +26,9 @@ def build(force=False, reward_source=None):
         so = os.path.join(_DIR, f"libdial_emul_custom_{tag}.so")
         extra = [f'-DDIAL_CUSTOM_REWARD_FILE="{reward_source}"']
         srcs += [reward_source, os.path.join(_DIR, "..", "..", "include", "dial_custom_reward.h")]
+    if defines:
+        so = so[:-3] + "_" + "_".join(d.replace("=", "-") for d in defines) + ".so"
+        extra = extra + [f"-D{d}" for d in defines]
     if so not in _LIBS or force:
         if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", _DIR, "-shared", "-fPIC"] + extra +
@@ -42,8 +45,8 @@ def _p(a):
 
 
 def rollout(env, plan_desc, qpos, qvel, warm, step0=0, stage0=0, us=None, eps=None, Ybar=None,
-            noise=None, key=(0, 0), mode=0, nrows=None, H=None, want_traj=True):
-    lib = build(reward_source=getattr(env, "reward_source", None) or None)
+            noise=None, key=(0, 0), mode=0, nrows=None, H=None, want_traj=True, defines=()):
+    lib = build(reward_source=getattr(env, "reward_source", None) or None, defines=defines)
     md = _capi.fill_model_desc(env.sys.model)
     nq, nv, nu, nb = md.nq, md.nv, md.nu, md.nbody
     f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)

@@ -128,3 +128,21 @@ def test_emulated_dense_path_matches_oracle():
     out = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us)
     assert np.abs(out["q"] - q).max() < 5e-4
     assert np.abs(out["rewss"] - rew).max() < 2e-3 * (1 + np.abs(rew).max())
+
+
+def test_line_search_cycle_detection_is_bit_identical():
+    """dense_linesearch stops MJX's 50-iteration bracket loop early once its (lo, hi, swap) state
+    has become periodic and replays only the remainder modulo the period (Brent).  The claim is
+    that the result is the state after the full budget, bit for bit: build the device code with
+    the detection compiled out and compare every output of a contact-rich rollout."""
+    from tests.emul import emul
+    env, o = make_pair("allegro_reorient")
+    s = o.reset()
+    rng = np.random.default_rng(3)
+    us = np.clip(rng.normal(size=(2, 8, 16)) * 0.6, -1, 1)
+    a = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us)
+    b = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us,
+                     defines=("DIAL_NO_LS_CYCLE",))
+    for k in ("rewss", "q", "qd", "xpos", "warm_out", "qvel_out"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.abs(a["qd"]).max() > 0.5     # the ball is being pushed around: contacts are active
