@@ -65,3 +65,30 @@ def test_emulated_planner_rows_and_native_rng():
     out2 = emul.rollout(env, desc, s.qpos[0], s.qvel[0], s.qacc_warmstart[0], Ybar=Ybar, noise=pl.sigma_control,
                         eps=eps, mode=1, nrows=4, H=Hs + 1)
     assert np.abs(out2["rews"] - out["rews"]).max() < 1e-4
+
+
+def test_emulated_planner_extreme_shapes():
+    """Capacity edges of the planner rows: one sample (+ the mean row), the longest horizon and
+    the most knots the fixed-size plan allows (DIAL_MAXH = 64 steps, DIAL_MAXNODE = 8 knots)."""
+    from dial_mpc_b200 import _capi
+    from dial_mpc_b200.utils.spline import interp_matrix
+    from oracle.planner_oracle import PlannerOracle, jax_normal_legacy
+    env, o = make_pair("unitree_go2_walk")
+    N, Hs, Hn = 1, _capi.DEFINES["DIAL_MAXH"] - 1, _capi.DEFINES["DIAL_MAXNODE"] - 1
+    pl = PlannerOracle(o, N, Hs, Hn, 0.05, 0.9, 0.5)
+    s = o.reset()
+    key = (7, 9)
+    eps = jax_normal_legacy(key, (N, Hn + 1, 12))
+    Ybar = np.zeros((Hn + 1, 12))
+    Yo, info = pl.reverse_once(s, eps, Ybar, pl.sigma_control * 0.3)
+    desc = env.plan_desc(Nsample=N, Hsample=Hs, Hnode=Hn, temp_sample=0.05,
+                         M_n2u=interp_matrix(pl.step_nodes, pl.step_us))
+    out = emul.rollout(env, desc, s.qpos[0], s.qvel[0], s.qacc_warmstart[0], Ybar=Ybar,
+                       noise=pl.sigma_control * 0.3, key=key, mode=1, nrows=N + 1, H=Hs + 1)
+    # 64 steps of contact dynamics: fp32 vs fp64 drift is visible but bounded
+    assert np.abs(out["rews"] - info["rews"]).max() < 2e-2 * (1 + np.abs(info["rews"]).max())
+    assert np.isfinite(out["q"]).all() and out["q"].shape == (2, Hs + 1, 19)
+    with pytest.raises(ValueError):
+        env.plan_desc(Nsample=1, Hsample=Hs + 1, Hnode=Hn)
+    with pytest.raises(ValueError):
+        env.plan_desc(Nsample=1, Hsample=Hs, Hnode=Hn + 1)
