@@ -33,6 +33,7 @@ DEV float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 DEV int shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 DEV void cta_sync() { __syncthreads(); }
+DEV bool cta_sync_or(bool p) { return __syncthreads_or(p) != 0; }
 DEV void fast_sincos(float x, float& s, float& c) { __sincosf(x, &s, &c); }
 DEV float fast_cos(float x) { return __cosf(x); }
 #endif
@@ -280,6 +281,7 @@ struct WarpCtx {
   int mylevel;         // elimination level of the dof (leaves = 0), -1 for non-dof lanes
   int parent;          // parent dof or -1
   int midsync;         // lock-step CTAs: extra CTA barrier before the Newton loop
+  int itersync;        // lock-step level 3 (dense path): CTA barrier per Newton iteration
   float* dbg;          // optional counters (tests / tuning): [0] physics steps, [1] Newton iterations
   int chain[DIAL_MAXCHAIN];
 };
@@ -1348,18 +1350,28 @@ DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float
     S.prev_cost = 0.f;
   }
   int it = 0;
+  bool done = false;
   while (true) {
-    dense_update_constraint(w, S, C);
-    bool done = it >= m.iterations;
-    if (m.iterations != 1 || it > 0) {
-      float improvement = (S.prev_cost - S.cost) / scale;
-      float gradient = sqrtf(S.gradnorm2) / scale;
-      if (m.iterations != 1) done = done || (improvement < m.tolerance) || (gradient < m.tolerance);
+    if (!done) {
+      dense_update_constraint(w, S, C);
+      done = it >= m.iterations;
+      if (m.iterations != 1 || it > 0) {
+        float improvement = (S.prev_cost - S.cost) / scale;
+        float gradient = sqrtf(S.gradnorm2) / scale;
+        if (m.iterations != 1) done = done || (improvement < m.tolerance) || (gradient < m.tolerance);
+      }
+      // a diverged sample (NaN / inf cost) can never satisfy the convergence tests: stop instead of
+      // burning iterations x ls_iterations on it (its result is garbage either way, weight 0 later)
+      if (!(fabsf(S.cost) <= 3.0e38f)) done = true;
     }
-    // a diverged sample (NaN / inf cost) can never satisfy the convergence tests: stop instead of
-    // burning iterations x ls_iterations on it (its result is garbage either way, weight 0 later)
-    if (!(fabsf(S.cost) <= 3.0e38f)) done = true;
-    if (done) break;
+    if (w.itersync) {
+      // lock-step level 3: the warps of the CTA start every Newton iteration together (shared
+      // instruction fetch inside the solver); a finished warp keeps arriving until all are done
+      if (!cta_sync_or(!done)) break;
+      if (done) continue;
+    } else if (done) {
+      break;
+    }
     dense_build_H<NVD>(w, S, C, Hrow);
     S.search = -dense_factor_solve<NVD>(w, Hrow, S.grad);
     dense_linesearch(w, S, C);
@@ -1726,6 +1738,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
 
   float qacc, qacc_int;
   if constexpr (NL < 0) {
+    if (w.midsync) cta_sync();   // lock-step CTAs: enter the constraint solve together
     qacc = dense_constraint_solve<NR>(w, S, Mrow, myqvel);
     qacc_int = qacc;
     if (m.eulerdamp) {   // implicit joint damping: (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
@@ -2036,6 +2049,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
   WarpCtx w;
   w.M = Mp; w.P = Pp; w.s = slab; w.lane = lane;
   w.midsync = A.lockstep >= 2;
+  w.itersync = A.lockstep >= 3;
   w.dbg = A.dbg;
   const DevModel& M = *Mp;
   const dial_model_desc& m = M.m;

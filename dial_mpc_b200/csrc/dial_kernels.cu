@@ -404,9 +404,16 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
   }
   // lock-step pays off when the warps of a CTA do similar work; the dense (elliptic) path has a
   // heavy-tailed iteration count per sample, so its warps run free (measured 172 vs 221 ms)
-  A.lockstep = (wpc >= 2 && !p->hM.dense && !getenv("DIAL_NO_LOCKSTEP")) ? 1 : 0;
-  if (p->hM.dense && A.nrows > wpc * p->num_sms && !getenv("DIAL_NO_DYNAMIC_ROWS")) A.row_counter = p->row_counter;
+  // lock-step pays off on both solver paths.  The dense (elliptic) path used to run free with
+  // dynamic row assignment because MJX's 50-iteration line searches made its rows heavy-tailed;
+  // since the line search stops at the detected cycle, sharing the instruction fetch wins there
+  // too (N=4096: 91.9 ms free-running + dynamic rows, 73.5 ms lock-step).  DIAL_NO_LOCKSTEP=1
+  // restores the free-running warps; DIAL_DENSE_LOCKSTEP=3 adds a barrier per Newton iteration.
+  A.lockstep = (wpc >= 2 && !getenv("DIAL_NO_LOCKSTEP")) ? 1 : 0;
+  if (p->hM.dense && !A.lockstep && A.nrows > wpc * p->num_sms && !getenv("DIAL_NO_DYNAMIC_ROWS")) A.row_counter = p->row_counter;
   if (A.lockstep && !getenv("DIAL_NO_MIDSYNC")) A.lockstep = 2;  // second barrier before the Newton loop (+1-3 %)
+  const char* dl = getenv("DIAL_DENSE_LOCKSTEP");
+  if (A.lockstep == 2 && p->hM.dense && dl && atoi(dl) == 3) A.lockstep = 3;
   switch (wpc) {
     case 1: return launch_rollout<1>(p, A, st);
     case 2: return launch_rollout<2>(p, A, st);

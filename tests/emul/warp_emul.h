@@ -74,5 +74,6 @@ inline int shfl_i(int v, int src) {
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline void cta_sync() {}
+inline bool cta_sync_or(bool p) { return p; }  // one emulated warp per CTA
 inline void fast_sincos(float x, float& s, float& c) { s = sinf(x); c = cosf(x); }
 inline float fast_cos(float x) { return cosf(x); }
