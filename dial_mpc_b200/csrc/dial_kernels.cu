@@ -407,13 +407,15 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
   // lock-step pays off on both solver paths.  The dense (elliptic) path used to run free with
   // dynamic row assignment because MJX's 50-iteration line searches made its rows heavy-tailed;
   // since the line search stops at the detected cycle, sharing the instruction fetch wins there
-  // too (N=4096: 91.9 ms free-running + dynamic rows, 73.5 ms lock-step).  DIAL_NO_LOCKSTEP=1
-  // restores the free-running warps; DIAL_DENSE_LOCKSTEP=3 adds a barrier per Newton iteration.
+  // too, and the finer the better: Allegro N=4096, 14 warps per CTA: 91.9 ms free-running with
+  // dynamic rows, 76.9 ms with a barrier per env step, 52.8 ms per physics substep, 48.4 ms per
+  // Newton iteration (level 3, the dense default).  DIAL_NO_LOCKSTEP=1 restores the free-running
+  // warps, DIAL_NO_MIDSYNC=1 / DIAL_DENSE_LOCKSTEP=2 select the coarser levels.
   A.lockstep = (wpc >= 2 && !getenv("DIAL_NO_LOCKSTEP")) ? 1 : 0;
   if (p->hM.dense && !A.lockstep && A.nrows > wpc * p->num_sms && !getenv("DIAL_NO_DYNAMIC_ROWS")) A.row_counter = p->row_counter;
-  if (A.lockstep && !getenv("DIAL_NO_MIDSYNC")) A.lockstep = 2;  // second barrier before the Newton loop (+1-3 %)
+  if (A.lockstep && !getenv("DIAL_NO_MIDSYNC")) A.lockstep = 2;  // second barrier before the Newton loop (+1-3 % on the tree paths)
   const char* dl = getenv("DIAL_DENSE_LOCKSTEP");
-  if (A.lockstep == 2 && p->hM.dense && dl && atoi(dl) == 3) A.lockstep = 3;
+  if (A.lockstep == 2 && p->hM.dense && !(dl && atoi(dl) == 2)) A.lockstep = 3;
   switch (wpc) {
     case 1: return launch_rollout<1>(p, A, st);
     case 2: return launch_rollout<2>(p, A, st);
