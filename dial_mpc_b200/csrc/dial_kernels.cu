@@ -384,17 +384,12 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
   if (wpc == 0) {
     const int per_sm = (A.nrows + p->num_sms - 1) / p->num_sms;
     wpc = per_sm <= 1 ? 1 : per_sm <= 2 ? 2 : per_sm <= 4 ? 4 : per_sm <= 8 ? 8 : per_sm <= 14 ? 14 : 16;
-    // more than one wave of rows (tree path): two resident 8-warp CTAs per SM overlap each other's
-    // barriers and tail (Go2 N=8192: 3.81 ms vs 3.85 / 3.93 ms for 14 / 16 warps per CTA)
-    // (only when two such CTAs fit the SM's 228 KB of shared memory, 1 KB reserved per CTA)
-    {
-      const size_t cta8 = sizeof(DevModel) + sizeof(DevPlan) + 8 * (size_t)p->hM.warp_floats * sizeof(float) + 1024;
-      if (per_sm > 14 && !p->hM.dense && 2 * cta8 <= 228 * 1024) wpc = 8;
-      else if (per_sm > 16 && !p->hM.dense) {
-        // one CTA per SM: balance the waves (H1 N=8192: 4 waves of 14 beat 3.5 waves of 16, 5.57 vs 5.76 ms)
-        const int waves = (per_sm + 15) / 16;
-        wpc = (per_sm + waves - 1) / waves <= 14 ? 14 : 16;
-      }
+    // more than one wave of rows: balance the waves of one CTA per SM.  Measured at N=8192
+    // (56 rows per SM): H1 4 waves of 14 warps 5.57 ms, 16 warps 5.76 ms, two resident 8-warp
+    // CTAs 5.91 ms; Go2 3.85 / 3.93 / 3.81 ms.
+    if (per_sm > 16) {
+      const int waves = (per_sm + 15) / 16;
+      wpc = (per_sm + waves - 1) / waves <= 14 ? 14 : 16;
     }
     // respect the 227 KB shared-memory limit of one CTA
     const size_t fixed = sizeof(DevModel) + sizeof(DevPlan), slab = (size_t)p->hM.warp_floats * sizeof(float);
@@ -402,8 +397,6 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
     for (int o = 0; o < 6; ++o)
       if (opts[o] <= wpc && fixed + opts[o] * slab <= 227 * 1024) { wpc = opts[o]; break; }
   }
-  // lock-step pays off when the warps of a CTA do similar work; the dense (elliptic) path has a
-  // heavy-tailed iteration count per sample, so its warps run free (measured 172 vs 221 ms)
   // lock-step pays off on both solver paths.  The dense (elliptic) path used to run free with
   // dynamic row assignment because MJX's 50-iteration line searches made its rows heavy-tailed;
   // since the line search stops at the detected cycle, sharing the instruction fetch wins there
