@@ -18,7 +18,7 @@ finite values by 0.0 in the reference).
 from __future__ import annotations
 
 import os
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, Optional
 
 import numpy as np

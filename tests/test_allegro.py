@@ -1,8 +1,6 @@
 """Allegro reorient (BASELINE configs[3]): model compiler (mesh inertias), elliptic-cone oracle
 pieces validated by finite differences, and the dense solver path of the kernel under the CPU
 warp emulator.  GPU parity is in test_gpu_parity.py."""
-import os
-
 import numpy as np
 import pytest
 

@@ -2,7 +2,6 @@
 calls without a GPU), struct layouts agree, and the host-side logic mirrors the reference API."""
 import ctypes as C
 import dataclasses
-import os
 import re
 
 import numpy as np

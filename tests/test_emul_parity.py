@@ -4,7 +4,7 @@ infrastructure only; the GPU tests (test_gpu_parity.py) check the real CUDA buil
 import numpy as np
 import pytest
 
-from tests.conftest import ENV_CASES, make_pair
+from tests.conftest import make_pair
 from tests.emul import emul
 
 

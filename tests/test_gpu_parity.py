@@ -203,7 +203,6 @@ def test_full_size_properties(built):
 
 
 def test_error_paths(built):
-    from dial_mpc_b200 import _capi
     from dial_mpc_b200.core.dial_config import DialConfig
     from dial_mpc_b200.core.dial_core import MBDPI
     env, _ = make_pair("unitree_go2_walk")
