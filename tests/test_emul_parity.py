@@ -92,3 +92,31 @@ def test_emulated_planner_extreme_shapes():
         env.plan_desc(Nsample=1, Hsample=Hs + 1, Hnode=Hn)
     with pytest.raises(ValueError):
         env.plan_desc(Nsample=1, Hsample=Hs, Hnode=Hn + 1)
+
+
+@pytest.mark.parametrize("name", ["unitree_go2_walk", "unitree_h1_walk", "unitree_h1_loco"])
+def test_emulated_random_states_match_oracle(name):
+    """States away from the nominal trajectory: tilted base, base height in and out of contact,
+    joints pushed beyond their limits (limit rows active), joint rates up to tens of rad/s."""
+    from oracle.envs_oracle import OState
+    env, o = make_pair(name)
+    s0 = o.reset()
+    nv, nu = o.m.nv, o.m.nu
+    rng = np.random.default_rng(11)
+    for _ in range(4):
+        q = s0.qpos[0].copy()
+        q[2] += rng.uniform(-0.06, 0.15)
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        ang = rng.uniform(0, 0.5)
+        q[3:7] = [np.cos(ang / 2), *(np.sin(ang / 2) * ax)]
+        lo, hi = o.physical_joint_range[:, 0], o.physical_joint_range[:, 1]
+        q[7:7 + nu] = np.clip(q[7:7 + nu] + rng.normal(size=nu) * 0.4, lo - 0.05, hi + 0.05)
+        v = rng.normal(size=nv) * np.r_[np.ones(3) * 0.5, np.ones(3), np.ones(nv - 6) * 3.0]
+        st = OState(q[None], v[None], np.zeros((1, nv)), np.array([17]), np.array([0]))
+        us = np.clip(rng.normal(size=(1, 3, nu)), -1, 1)
+        rew, qq, qd, x = o.rollout(st, us)
+        out = emul.rollout(env, env.plan_desc(), q, v, np.zeros(nv), us=us, step0=17)
+        assert np.abs(out["q"] - qq).max() < 5e-5
+        assert np.abs(out["qd"] - qd).max() < 2e-3 * (1 + np.abs(qd).max() / 10)
+        assert np.abs(out["rewss"] - rew).max() < 1e-4 * (1 + np.abs(rew).max())
