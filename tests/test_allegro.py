@@ -144,3 +144,30 @@ def test_line_search_cycle_detection_is_bit_identical():
     for k in ("rewss", "q", "qd", "xpos", "warm_out", "qvel_out"):
         assert np.array_equal(a[k], b[k]), k
     assert np.abs(a["qd"]).max() > 0.5     # the ball is being pushed around: contacts are active
+
+
+def test_emulated_dense_path_random_states():
+    """Dense / elliptic path away from the reset pose: random finger configurations (some joints
+    beyond their limits), displaced and spinning ball, two env steps (8 physics substeps)."""
+    from oracle.envs_oracle import OState
+    from tests.emul import emul
+    env, o = make_pair("allegro_reorient")
+    s0 = o.reset()
+    nv, nu = o.m.nv, o.m.nu
+    rng = np.random.default_rng(5)
+    active = 0
+    for _ in range(6):
+        q = s0.qpos[0].copy()
+        q[:3] += rng.normal(size=3) * 0.004
+        lo, hi = o.physical_joint_range[:, 0], o.physical_joint_range[:, 1]
+        q[7:7 + nu] = np.clip(q[7:7 + nu] + rng.normal(size=nu) * 0.15, lo - 0.02, hi + 0.02)
+        v = np.r_[rng.normal(size=3) * 0.05, rng.normal(size=3), rng.normal(size=nv - 6)]
+        st = OState(q[None], v[None], np.zeros((1, nv)), np.array([3]), np.array([0]))
+        us = np.clip(rng.normal(size=(1, 2, nu)) * 0.5, -1, 1)
+        rew, qq, qd, x = o.rollout(st, us)
+        out = emul.rollout(env, env.plan_desc(), q, v, np.zeros(nv), us=us, step0=3)
+        assert np.abs(out["q"] - qq).max() < 2e-4
+        assert np.abs(out["qd"] - qd).max() < 5e-3
+        assert np.abs(out["rewss"] - rew).max() < 1e-3 * (1 + np.abs(rew).max())
+        active += int(np.abs(out["qd"] - qd).max() > 1e-4)   # contact-rich trials show fp32 noise
+    assert active >= 1
