@@ -291,6 +291,21 @@ class DeviceLoop:
         return State(ps, None, b["reward"][0].clone(), 0.0, {}, info)
 
 
+def save_run(output_dir, rollout, infos, timestamp=None):
+    """End-of-run dumps of the reference (dial_core.py:305-323): ``*_states.npy`` rows
+    ``[i, qpos, qvel, ctrl]`` and ``*_predictions.npy`` = per control step the ``xbar`` of the LAST
+    diffusion iteration, shape [n_steps, Hsample+1, nbody-1, 3] (``infos[i]["xbar"][-1]`` there:
+    ``lax.scan`` stacks the iterations, ``[-1]`` picks the last one, not the last horizon step)."""
+    os.makedirs(output_dir, exist_ok=True)
+    timestamp = timestamp or time.strftime("%Y%m%d-%H%M%S")
+    states = torch.stack([torch.as_tensor(r) for r in rollout]).cpu().numpy()
+    preds = torch.stack([torch.as_tensor(x) for x in infos]).cpu().numpy()
+    assert preds.ndim == 4 and preds.shape[-1] == 3, preds.shape
+    np.save(os.path.join(output_dir, f"{timestamp}_states"), states)
+    np.save(os.path.join(output_dir, f"{timestamp}_predictions"), preds)
+    return states, preds
+
+
 def main():
     """Synchronous MPC loop — dial_core.py:175-268 without the rendering / flask tail."""
     parser = argparse.ArgumentParser()
@@ -337,7 +352,7 @@ def main():
             loop.step(dial_config.Ndiffuse_init if t == 0 else dial_config.Ndiffuse)
             rollout.append(torch.cat([torch.tensor([float(t)], device=mbdpi.device), b["qpos"], b["qvel"], b["ctrl"]]))
             rews.append(b["reward"][0].clone())
-            infos.append(b["xbar"][-1].clone())
+            infos.append(b["xbar"].clone())   # = infos[i]["xbar"][-1] of the reference: last diffusion iteration, full horizon
             if t % 10 == 0:
                 r = float(rews[-1])  # synchronises: the rate below is whole control steps per second
                 print(f"step {t}: rew={r:.3e} freq={(t - tlast) / (time.time() - t0):.1f} Hz")
@@ -354,15 +369,12 @@ def main():
             rng, Y0, info = mbdpi.reverse_scan(state, rng, Y0, mbdpi.schedule(n_diffuse))
             torch.cuda.synchronize()
             freq = 1 / (time.time() - t0)
-            infos.append(info["xbar"][-1])
+            infos.append(info["xbar"])
             if t % 10 == 0:
                 print(f"step {t}: rew={float(state.reward):.3e} freq={freq:.1f} Hz")
     rew = torch.stack([torch.as_tensor(r) for r in rews]).mean()
     print(f"mean reward = {float(rew):.2e}")
-    os.makedirs(dial_config.output_dir, exist_ok=True)
-    timestamp = time.strftime("%Y%m%d-%H%M%S")
-    np.save(os.path.join(dial_config.output_dir, f"{timestamp}_states"), torch.stack(rollout).cpu().numpy())
-    np.save(os.path.join(dial_config.output_dir, f"{timestamp}_predictions"), torch.stack(infos).cpu().numpy())
+    save_run(dial_config.output_dir, rollout, infos)
 
 
 if __name__ == "__main__":

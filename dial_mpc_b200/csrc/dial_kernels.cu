@@ -21,124 +21,106 @@ static thread_local std::string g_err;
 static int fail(const std::string& s) { g_err = s; return -1; }
 #define CUDA_OK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
-// ---------------------------------------------------------------------------------
-// TMA bulk copy global -> shared (1-D), completion on an mbarrier
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n .reg .pred p;\n WAIT_%=:\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-static_assert(sizeof(DevModel) % 16 == 0, "DevModel must be a multiple of 16 bytes for cp.async.bulk");
-static_assert(sizeof(DevPlan) % 16 == 0, "DevPlan must be a multiple of 16 bytes for cp.async.bulk");
-
-template <int WPC, int NL, int NR>
-__global__ void __launch_bounds__(WPC * 32, (WPC > 8 ? 1 : 16 / WPC)) rollout_kernel(const DevModel* __restrict__ gM,
-                                                            const DevPlan* __restrict__ gP,
-                                                            const RolloutArgs A) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar;
-  DevModel* sM = reinterpret_cast<DevModel*>(smem);
-  DevPlan* sP = reinterpret_cast<DevPlan*>(smem + sizeof(DevModel));
-  float* slabs = reinterpret_cast<float*>(smem + sizeof(DevModel) + sizeof(DevPlan));
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    mbar_expect_tx(&bar, (uint32_t)(sizeof(DevModel) + sizeof(DevPlan)));
-    tma_bulk_g2s(sM, gM, (uint32_t)sizeof(DevModel), &bar);
-    tma_bulk_g2s(sP, gP, (uint32_t)sizeof(DevPlan), &bar);
-  }
-  __syncthreads();
-  mbar_wait(&bar, 0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* slab = slabs + (size_t)warp * sM->warp_floats;
-  if (A.row_counter) {
-    // persistent warps + dynamic row assignment: the dense path has a heavy-tailed cost per row
-    for (;;) {
-      int row = 0;
-      if (lane == 0) row = (int)atomicAdd(A.row_counter, 1u);
-      row = __shfl_sync(0xffffffffu, row, 0);
-      if (row >= A.nrows) return;
-      rollout_warp<NL, NR>(sM, sP, slab, A, row, lane);
-      __syncwarp();
-    }
-  }
-  int row = blockIdx.x * WPC + warp;
-  if (row >= A.nrows) {
-    if (!A.lockstep) return;
-    row = A.nrows - 1;  // lock-step CTAs need every warp at the barriers: duplicate the last row (benign)
-  }
-  rollout_warp<NL, NR>(sM, sP, slab, A, row, lane);
-}
+// The rollout kernel lives in dial_rollout_variant.cu, compiled once per solver variant
+// (-DDIAL_VARIANT=v) so that the five instantiations build in parallel; each object exports
+// one launcher.  Custom-reward builds (-DDIAL_ONLY_VARIANT=v) compile a single translation unit.
+#ifdef DIAL_ONLY_VARIANT
+#define DIAL_HAS_VARIANT(v) ((v) == DIAL_ONLY_VARIANT)
+#define DIAL_VARIANT DIAL_ONLY_VARIANT
+#include "dial_rollout_variant.cu"
+#else
+#define DIAL_HAS_VARIANT(v) 1
+#endif
+#define DIAL_DECL_LAUNCH(v) cudaError_t dial_launch_rollout_v##v(const DevModel*, const DevPlan*, const RolloutArgs&, int, int, size_t, cudaStream_t);
+#if DIAL_HAS_VARIANT(0)
+DIAL_DECL_LAUNCH(0)
+#endif
+#if DIAL_HAS_VARIANT(1)
+DIAL_DECL_LAUNCH(1)
+#endif
+#if DIAL_HAS_VARIANT(2)
+DIAL_DECL_LAUNCH(2)
+#endif
+#if DIAL_HAS_VARIANT(3)
+DIAL_DECL_LAUNCH(3)
+#endif
+#if DIAL_HAS_VARIANT(4)
+DIAL_DECL_LAUNCH(4)
+#endif
 
 // ---------------------------------------------------------------------------------
 // softmax weights over all rewards (core/dial_core.py:125-128), single CTA
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+// block-wide sum of K values per thread (+ optionally the max of one): shuffle tree, one smem
+// stage, result identical in every thread
+template <int K>
+__device__ __forceinline__ void block_reduce(float (&v)[K], float* mx, float* red) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    float t = __shfl_xor_sync(0xffffffffu, v, o);
-    v = is_max ? fmaxf(v, t) : v + t;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (mx) *mx = fmaxf(*mx, __shfl_xor_sync(0xffffffffu, *mx, o));
+  }
+  __syncthreads();   // previous use of `red` is over
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) red[k * 32 + wid] = v[k];
+    if (mx) red[K * 32 + wid] = *mx;
   }
   __syncthreads();
-  if (lane == 0) red[wid] = v;
-  __syncthreads();
-  float r = (lane < nw) ? red[lane] : (is_max ? -INFINITY : 0.f);
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = lane < nw ? red[k * 32 + lane] : 0.f;
+  if (mx) *mx = lane < nw ? red[K * 32 + lane] : -INFINITY;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    float t = __shfl_xor_sync(0xffffffffu, r, o);
-    r = is_max ? fmaxf(r, t) : r + t;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (mx) *mx = fmaxf(*mx, __shfl_xor_sync(0xffffffffu, *mx, o));
   }
-  return r;  // identical in every thread
 }
 
-// rews [n] (mean sample last) -> weights [n].  Non-finite rewards (diverged samples) get
-// weight 0 and are left out of the statistics (the reference has no guard: it would return NaN).
+// rews [n] (mean sample last) -> weights [n] = softmax((rews - rews[n-1]) / std(rews) / temp)
+// (core/dial_core.py:125-128).  Three passes: statistics of d = r - rbar (count, sum, sum of
+// squares, max: the shift keeps the one-pass variance accurate), exp + normaliser, scale.
+// Deviations from the reference, which has no guards:
+//   * non-finite rewards (diverged samples) get weight 0 and are left out of the statistics;
+//   * std == 0 (all finite rewards equal, e.g. zero noise): uniform weights over the finite
+//     samples instead of 0/0 = NaN;
+//   * no finite reward at all: the whole weight goes to the mean sample (Ybar is kept);
+//   * a non-finite rbar only changes the reference point of the shift (softmax is shift-invariant).
 __global__ void __launch_bounds__(1024) weights_kernel(const float* __restrict__ rews, int n, float temp,
                                                         float* __restrict__ weights) {
-  __shared__ float red[32];
+  __shared__ float red[4 * 32];
   const int tid = threadIdx.x;
-  float s = 0.f, cnt = 0.f;
-  for (int i = tid; i < n; i += blockDim.x) { float r = rews[i]; if (isfinite(r)) { s += r; cnt += 1.f; } }
-  s = block_reduce(s, red, false);
-  cnt = block_reduce(cnt, red, false);
-  const float mean = s / fmaxf(cnt, 1.f);
-  float v = 0.f;
-  for (int i = tid; i < n; i += blockDim.x) { float r = rews[i]; if (isfinite(r)) v += (r - mean) * (r - mean); }
-  v = block_reduce(v, red, false);
-  const float sd = sqrtf(v / fmaxf(cnt, 1.f));
-  const float rbar = rews[n - 1];
-  float mx = -INFINITY;
+  float rbar = rews[n - 1];
+  if (!isfinite(rbar)) rbar = 0.f;
+  float st[3] = {0.f, 0.f, 0.f}, dmax = -INFINITY;
   for (int i = tid; i < n; i += blockDim.x) {
-    float r = rews[i];
-    if (isfinite(r)) mx = fmaxf(mx, (r - rbar) / sd / temp);
+    const float r = rews[i];
+    if (isfinite(r)) { const float d = r - rbar; st[0] += 1.f; st[1] += d; st[2] += d * d; dmax = fmaxf(dmax, d); }
   }
-  mx = block_reduce(mx, red, true);
-  float z = 0.f;
+  block_reduce<3>(st, &dmax, red);
+  const float cnt = st[0];
+  if (cnt == 0.f) {
+    for (int i = tid; i < n; i += blockDim.x) weights[i] = (i == n - 1) ? 1.f : 0.f;
+    return;
+  }
+  const float mean = st[1] / cnt;
+  const float sd = sqrtf(fmaxf(st[2] / cnt - mean * mean, 0.f));
+  const bool flat = !(sd > 0.f);
+  const float inv = flat ? 0.f : 1.f / sd / temp;   // flat: every logit 0 -> uniform weights
+  const float mx = dmax * inv;
+  float z[1] = {0.f};
   for (int i = tid; i < n; i += blockDim.x) {
-    float r = rews[i];
-    float e = isfinite(r) ? expf((r - rbar) / sd / temp - mx) : 0.f;
+    const float r = rews[i];
+    const float e = isfinite(r) ? expf((r - rbar) * inv - mx) : 0.f;
     weights[i] = e;
-    z += e;
+    z[0] += e;
   }
-  z = block_reduce(z, red, false);
-  __syncthreads();
-  const float inv = 1.f / z;
-  for (int i = tid; i < n; i += blockDim.x) weights[i] *= inv;
+  block_reduce<1>(z, nullptr, red);
+  const float iz = 1.f / z[0];
+  for (int i = tid; i < n; i += blockDim.x) weights[i] *= iz;
 }
 
 // ---------------------------------------------------------------------------------
@@ -256,7 +238,7 @@ __global__ void __launch_bounds__(256) trajbar_partial_kernel(const TrajArgs T) 
         float wgt;
         if (r == T.mean_row) { if (!T.include_mean) continue; wgt = T.weights[T.mean_weight_index]; }
         else wgt = T.weights[T.w_offset + r];
-        a += wgt * traj[((size_t)r * T.H + t) * ncol + c];
+        if (wgt != 0.f) a += wgt * traj[((size_t)r * T.H + t) * ncol + c];   // weight 0: diverged sample (NaN trajectory)
       }
     }
     __syncthreads();
@@ -324,51 +306,33 @@ extern "C" size_t dial_sizeof(int which) {
        : which == 3 ? sizeof(dial_mpc_buffers) : 0;
 }
 
-template <int WPC, int NL, int NR>
-static cudaError_t launch_rollout_t(dial_plan* p, const RolloutArgs& A, cudaStream_t st) {
-  size_t smem = sizeof(DevModel) + sizeof(DevPlan) + (size_t)WPC * p->hM.warp_floats * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(rollout_kernel<WPC, NL, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  int grid = (A.nrows + WPC - 1) / WPC;
+// solver instantiation by tree shape: star<3,6> (quadruped), star<5,7> (humanoid), star<5,6>,
+// dense<22> (elliptic cones), generic tree.  `wpc` warps per CTA (1..16; one kernel serves all).
+static cudaError_t launch_rollout(dial_plan* p, const RolloutArgs& A, int wpc, cudaStream_t st) {
+  const size_t smem = sizeof(DevModel) + sizeof(DevPlan) + (size_t)wpc * p->hM.warp_floats * sizeof(float);
+  int grid = (A.nrows + wpc - 1) / wpc;
   if (A.row_counter) {
-    const int resident = p->num_sms * (WPC > 8 ? 1 : 16 / WPC);
+    const int resident = p->num_sms * (wpc > 8 ? 1 : 16 / wpc);
     grid = grid < resident ? grid : resident;
     cudaError_t e = cudaMemsetAsync(A.row_counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
   }
-  rollout_kernel<WPC, NL, NR><<<grid, WPC * 32, smem, st>>>(p->dM, p->dP, A);
   p->launches++;
-  return cudaGetLastError();
-}
-
-// solver instantiation by tree shape: star<3,6> (quadruped), star<5,7> (humanoid), generic tree
-template <int WPC>
-static cudaError_t launch_rollout(dial_plan* p, const RolloutArgs& A, cudaStream_t st) {
-  // custom-reward builds compile only the instantiation their model needs (-DDIAL_ONLY_VARIANT=v)
-#ifdef DIAL_ONLY_VARIANT
-#define DIAL_HAS_VARIANT(v) ((v) == DIAL_ONLY_VARIANT)
-#else
-#define DIAL_HAS_VARIANT(v) 1
-#endif
   switch (p->variant) {
 #if DIAL_HAS_VARIANT(1)
-    case 1: return launch_rollout_t<WPC, 3, 6>(p, A, st);
+    case 1: return dial_launch_rollout_v1(p->dM, p->dP, A, grid, wpc, smem, st);
 #endif
 #if DIAL_HAS_VARIANT(2)
-    case 2: return launch_rollout_t<WPC, 5, 7>(p, A, st);
+    case 2: return dial_launch_rollout_v2(p->dM, p->dP, A, grid, wpc, smem, st);
 #endif
 #if DIAL_HAS_VARIANT(3)
-    case 3: return launch_rollout_t<WPC, -1, 22>(p, A, st);
+    case 3: return dial_launch_rollout_v3(p->dM, p->dP, A, grid, wpc, smem, st);
 #endif
 #if DIAL_HAS_VARIANT(4)
-    case 4: return launch_rollout_t<WPC, 5, 6>(p, A, st);
+    case 4: return dial_launch_rollout_v4(p->dM, p->dP, A, grid, wpc, smem, st);
 #endif
 #if DIAL_HAS_VARIANT(0)
-    case 0: return launch_rollout_t<WPC, 0, 0>(p, A, st);
+    case 0: return dial_launch_rollout_v0(p->dM, p->dP, A, grid, wpc, smem, st);
 #endif
     default: return cudaErrorInvalidDeviceFunction;
   }
@@ -382,21 +346,22 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
   const char* f = getenv("DIAL_WPC");
   int wpc = f ? atoi(f) : 0;
   if (wpc == 0) {
+    // one CTA per SM holding that SM's share of the rows (any warp count 1..16: the kernel is
+    // not specialised on it)
     const int per_sm = (A.nrows + p->num_sms - 1) / p->num_sms;
-    wpc = per_sm <= 1 ? 1 : per_sm <= 2 ? 2 : per_sm <= 4 ? 4 : per_sm <= 8 ? 8 : per_sm <= 14 ? 14 : 16;
+    wpc = per_sm < 16 ? per_sm : 16;
     // more than one wave of rows: balance the waves of one CTA per SM.  Measured at N=8192
     // (56 rows per SM): H1 4 waves of 14 warps 5.57 ms, 16 warps 5.76 ms, two resident 8-warp
     // CTAs 5.91 ms; Go2 3.85 / 3.93 / 3.81 ms.
     if (per_sm > 16) {
       const int waves = (per_sm + 15) / 16;
-      wpc = (per_sm + waves - 1) / waves <= 14 ? 14 : 16;
+      wpc = (per_sm + waves - 1) / waves;
     }
     // respect the 227 KB shared-memory limit of one CTA
     const size_t fixed = sizeof(DevModel) + sizeof(DevPlan), slab = (size_t)p->hM.warp_floats * sizeof(float);
-    const int opts[6] = {16, 14, 8, 4, 2, 1};
-    for (int o = 0; o < 6; ++o)
-      if (opts[o] <= wpc && fixed + opts[o] * slab <= 227 * 1024) { wpc = opts[o]; break; }
+    while (wpc > 1 && fixed + wpc * slab > 227 * 1024) --wpc;
   }
+  if (wpc < 1 || wpc > 16) return cudaErrorInvalidValue;
   // lock-step pays off on both solver paths.  The dense (elliptic) path used to run free with
   // dynamic row assignment because MJX's 50-iteration line searches made its rows heavy-tailed;
   // since the line search stops at the detected cycle, sharing the instruction fetch wins there
@@ -409,14 +374,7 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
   if (A.lockstep && !getenv("DIAL_NO_MIDSYNC")) A.lockstep = 2;  // second barrier before the Newton loop (+1-3 % on the tree paths)
   const char* dl = getenv("DIAL_DENSE_LOCKSTEP");
   if (A.lockstep == 2 && p->hM.dense && !(dl && atoi(dl) == 2)) A.lockstep = 3;
-  switch (wpc) {
-    case 1: return launch_rollout<1>(p, A, st);
-    case 2: return launch_rollout<2>(p, A, st);
-    case 4: return launch_rollout<4>(p, A, st);
-    case 8: return launch_rollout<8>(p, A, st);
-    case 14: return launch_rollout<14>(p, A, st);
-    default: return launch_rollout<16>(p, A, st);
-  }
+  return launch_rollout(p, A, wpc, st);
 }
 
 extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_plan_desc* cfg) {
@@ -522,7 +480,7 @@ extern "C" int dial_env_step(dial_plan* p, const dial_state* s, const float* act
   fill_state(A, s);
   A.nrows = 1; A.H = 1; A.mode = 0; A.us = action; A.rewss = reward;
   A.qpos_out = qpos_out; A.qvel_out = qvel_out; A.warm_out = warm_out; A.ctrl_out = ctrl_out;
-  CUDA_OK(launch_rollout<1>(p, A, (cudaStream_t)stream));
+  CUDA_OK(launch_rollout(p, A, 1, (cudaStream_t)stream));
   return 0;
 }
 
@@ -532,7 +490,7 @@ extern "C" int dial_pipeline_init(dial_plan* p, const float* qpos, const float* 
   RolloutArgs A; memset(&A, 0, sizeof(A));
   A.qpos0 = qpos; A.qvel0 = qvel; A.warm0 = p->zeros;  // mjx.make_data: qacc_warmstart = 0
   A.nrows = 1; A.H = 1; A.mode = 2; A.qpos_out = qpos_out; A.warm_out = warm_out;
-  CUDA_OK(launch_rollout<1>(p, A, (cudaStream_t)stream));
+  CUDA_OK(launch_rollout(p, A, 1, (cudaStream_t)stream));
   return 0;
 }
 
@@ -598,6 +556,18 @@ extern "C" int dial_reverse_trajbar(dial_plan* p, const float* weights, int rank
   return 0;
 }
 
+extern "C" int dial_reverse_trajectories(dial_plan* p, float* q, float* qd, float* xpos, void* stream) {
+  if (!p) return fail("dial_reverse_trajectories: null plan");
+  const dial_plan_desc& c = p->hP.c;
+  const dial_model_desc& m = p->hM.m;
+  const size_t n = ((size_t)c.Nsample + 1) * (c.Hsample + 1) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (q) CUDA_OK(cudaMemcpyAsync(q, p->traj_q[p->cur], n * m.nq, cudaMemcpyDeviceToDevice, st));
+  if (qd) CUDA_OK(cudaMemcpyAsync(qd, p->traj_qd[p->cur], n * m.nv, cudaMemcpyDeviceToDevice, st));
+  if (xpos) CUDA_OK(cudaMemcpyAsync(xpos, p->traj_x[p->cur], n * 3 * (m.nbody - 1), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 // ---- device-resident synchronous MPC loop ---------------------------------------------------
 extern "C" int dial_mpc_bind(dial_plan* p, const dial_mpc_buffers* b, const float* M_shift) {
   if (!p || !b || !M_shift) return fail("dial_mpc_bind: null argument");
@@ -633,7 +603,7 @@ static int mpc_enqueue(dial_plan* p, int n_diffuse, int env_step, cudaStream_t s
     A.counters_in = B.counters; A.counters_out = B.counters;
     A.nrows = 1; A.H = 1; A.mode = 0; A.us = Y[cur]; A.rewss = B.reward;
     A.qpos_out = B.qpos; A.qvel_out = B.qvel; A.warm_out = B.qacc_warmstart; A.ctrl_out = B.ctrl;
-    CUDA_OK(launch_rollout<1>(p, A, st));
+    CUDA_OK(launch_rollout(p, A, 1, st));
     // Y0 = shift(Y0)  (dial_core.py:252)
     mpc_shift_kernel<<<1, DIAL_MAXNODE * DIAL_MAXU, 0, st>>>(p->mpc_Msh, Y[cur], Y[cur ^ 1], n1, nu);
     p->launches++;

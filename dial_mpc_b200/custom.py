@@ -29,7 +29,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def _sources(reward_path: str):
-    return [os.path.join(CSRC, f) for f in ("dial_kernels.cu", "dial_device.cuh", "dial_host.h")] + \
+    return [os.path.join(CSRC, f) for f in ("dial_kernels.cu", "dial_rollout_variant.cu", "dial_device.cuh", "dial_host.h")] + \
         [os.path.join(_ROOT, "include", "dial_b200.h"), os.path.join(_ROOT, "include", "dial_custom_reward.h"),
          reward_path]
 

@@ -132,6 +132,13 @@ class Plan:
         self._check(self.lib.dial_reverse_trajbar(self.handle, _ptr(weights), int(rank), _ptr(qbar), _ptr(qdbar),
                                                   _ptr(xbar), _stream()))
 
+    def reverse_trajectories(self):
+        """q, qd, x.pos [Nsample+1,Hs+1,*] of the last reverse_rollout (copies)."""
+        H = self.Hs + 1
+        q, qd, x = self.empty(self.N + 1, H, self.nq), self.empty(self.N + 1, H, self.nv), self.empty(self.N + 1, H, self.nbody - 1, 3)
+        self._check(self.lib.dial_reverse_trajectories(self.handle, _ptr(q), _ptr(qd), _ptr(x), _stream()))
+        return q, qd, x
+
     # -- device-resident MPC loop (one CUDA graph per control step) ---------------------------------
     def mpc_bind(self, bufs: dict, M_shift) -> None:
         """``bufs``: name -> CUDA tensor for every field of ``dial_mpc_buffers`` (qbar/qdbar/xbar may be

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DIAL_ABI_VERSION 4
+#define DIAL_ABI_VERSION 5
 
 /* capacities of the fixed-size device model */
 #define DIAL_MAXB 24   /* bodies incl. world            */
@@ -196,6 +196,11 @@ int dial_reverse_update(dial_plan* plan, const float* eps, const uint32_t key[2]
  * qbar [Hs+1,nq], qdbar [Hs+1,nv], xbar [Hs+1,nbody-1,3]. */
 int dial_reverse_trajbar(dial_plan* plan, const float* weights, int rank,
                          float* qbar, float* qdbar, float* xbar, void* stream);
+
+/* The stored trajectories of the LAST dial_reverse_rollout (the `pipeline_statess` that
+ * core/dial_core.py:120-124 keeps alive: q, qd, x.pos of every sample): device-to-device copies
+ * into caller buffers q [Nsample+1,Hs+1,nq], qd [..,nv], xpos [..,nbody-1,3] (each nullable). */
+int dial_reverse_trajectories(dial_plan* plan, float* q, float* qd, float* xpos, void* stream);
 
 /* ---- Device-resident synchronous MPC loop -------------------------------------------------
  * The reference's main loop (core/dial_core.py:242-268) is, per control step,

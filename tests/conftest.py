@@ -25,15 +25,7 @@ def pytest_collection_modifyitems(config, items):
                 item.add_marker(skip)
 
 
-ENV_CASES = {
-    "unitree_go2_walk": dict(default_vx=0.8, ramp_up_time=1.0),
-    "unitree_go2_seq_jump": dict(
-        pose_target_sequence=[[0, 0, 0.27], [0.4, 0, 0.27], [0.8, 0, 0.27], [1.2, 0, 0.27], [1.6, 0, 0.27]],
-        yaw_target_sequence=[0.0] * 5),
-    "unitree_h1_walk": dict(default_vx=2.0, ramp_up_time=3.0),
-    "allegro_reorient": dict(dt=0.02, timestep=0.005, leg_control="position"),
-    "unitree_h1_loco": dict(default_vx=0.6, ramp_up_time=3.0, gait="walk"),
-}
+from baseline_configs import ENV_CFG as ENV_CASES  # noqa: E402  (one table for bench.py and the tests)
 
 
 def make_pair(name):

@@ -1,0 +1,49 @@
+"""TEST-ONLY: oracle rollouts spread over host processes (spawned, so they never inherit a CUDA
+context).  The oracle is batched NumPy; the Allegro model (100 Newton x 50 line-search
+iterations, 4 substeps) needs minutes per hundred rows on one core."""
+from __future__ import annotations
+
+import os
+from concurrent.futures import ProcessPoolExecutor
+from multiprocessing import get_context
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rollout_chunk(args):
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    name, cfg, qpos, qvel, warm, step, stage, us = args
+    from oracle.envs_oracle import OState, make_env
+    o = make_env(name, cfg)
+    s = OState(qpos[None], qvel[None], warm[None], np.array([step], dtype=np.int64), np.array([stage], dtype=np.int64))
+    return o.rollout(s, us)
+
+
+def oracle_rollout(name, cfg, qpos, qvel, warm, step, stage, us, procs=None):
+    """o.rollout(state, us) with the rows of `us` split over `procs` processes.
+    Returns (rewss [B,H], q, qd, xpos) like OracleEnv.rollout."""
+    us = np.asarray(us, dtype=np.float64)
+    B = us.shape[0]
+    procs = max(1, min(procs or (os.cpu_count() or 1), B, 32))
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    base = (name, dict(cfg), f64(qpos), f64(qvel), f64(warm), int(step), int(stage))
+    if procs == 1:
+        return _rollout_chunk(base + (us,))
+    chunks = np.array_split(np.arange(B), procs)
+    old = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in old:
+        os.environ[k] = "1"       # inherited by the spawned workers before they import numpy
+    try:
+        with ProcessPoolExecutor(procs, mp_context=get_context("spawn")) as ex:
+            parts = list(ex.map(_rollout_chunk, [base + (us[c],) for c in chunks]))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return tuple(np.concatenate([p[i] for p in parts], 0) for i in range(4))

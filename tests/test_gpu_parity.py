@@ -41,13 +41,16 @@ def test_rollout_matches_oracle(built, name, H):
     torch.cuda.synchronize()
     if name == "allegro_reorient":
         # a 10 g ball between finger tips: single contact events change velocities by O(1) and
-        # amplify fp32 rounding, so parity is asserted (i) tightly before the first such event and
-        # (ii) statistically afterwards (outliers reported, not hidden: SURVEY.md 8c)
-        eq = np.abs(qg.cpu().numpy() - q).max(-1)                      # [B,H]
-        er = np.abs(rg.cpu().numpy() - rew) / (1 + np.abs(rew))
-        assert eq[:, :3].max() < 2e-4 and er[:, :3].max() < 2e-3
-        ok = (er.max(1) < 2e-3)
-        assert ok.mean() >= 0.5, (ok, er.max(1))
+        # amplify fp32 rounding.  Deterministic statement: every row within tolerance + YARD x the
+        # ORACLE's own sensitivity to fp32-sized noise on the actions (per-substep parity from
+        # identical states is in test_gpu_at_size.py::test_single_physics_step_qacc_parity)
+        from tests.test_gpu_at_size import YARD
+        rewp, qp, _, _ = o.rollout(s, us + 1e-6 * rng.standard_normal(us.shape))
+        eq = np.abs(qg.cpu().numpy() - q)
+        er = np.abs(rg.cpu().numpy() - rew)
+        assert (eq <= 2e-4 + YARD * np.abs(qp - q)).all(), (eq.max(), np.abs(qp - q).max())
+        assert (er <= 2e-3 * (1 + np.abs(rew)) + YARD * np.abs(rewp - rew)).all(), (er.max(), np.abs(rewp - rew).max())
+        assert eq[:, :3].max() < 2e-4 and (er[:, :3] / (1 + np.abs(rew[:, :3]))).max() < 2e-3   # before the first contact event
         assert np.isfinite(rg.cpu().numpy()).all()
         return
     assert np.abs(qg.cpu().numpy() - q).max() < 2e-4
@@ -90,9 +93,10 @@ def test_reverse_once_matches_golden(built, name):
     rews = info["rews"].cpu().numpy()
     w = info["weights"].cpu().numpy()
     assert abs(w.sum() - 1) < 1e-4
-    if name == "allegro_reorient":   # chaotic contact events: statistical parity (see test_rollout_matches_oracle)
-        okr = np.abs(rews - g["rews"]) < 2e-3 * (1 + np.abs(g["rews"]))
-        assert okr.mean() >= 0.7 and np.isfinite(rews).all(), np.abs(rews - g["rews"])
+    if name == "allegro_reorient":   # chaotic contact events: budget = tolerance + YARD x oracle sensitivity (fixture)
+        from tests.test_gpu_at_size import YARD
+        err = np.abs(rews - g["rews"])
+        assert (err <= 2e-3 * (1 + np.abs(g["rews"])) + YARD * g["rews_sens"]).all() and np.isfinite(rews).all(), (err, g["rews_sens"])
         assert int(np.argmax(w)) == int(np.argmax(g["weights"]))
         return
     assert (np.abs(rews - g["rews"]) < 1e-3 * (1 + np.abs(g["rews"]))).all()
@@ -132,6 +136,18 @@ def test_update_stage_exact_on_given_rewards(built):
     mb.plan.reverse_update(mb.plan.f32(eps), None, mb.plan.f32(Ybar), noise, mb.plan.f32(rews2), out, w)
     wn = w.cpu().numpy()
     assert wn[5] == 0 and wn[7] == 0 and np.isfinite(wn).all() and abs(wn.sum() - 1) < 1e-4
+    # a diverged MEAN sample (rbar non-finite) only moves the reference point of the softmax shift
+    rews3 = rews.copy(); rews3[-1] = np.nan
+    mb.plan.reverse_update(mb.plan.f32(eps), None, mb.plan.f32(Ybar), noise, mb.plan.f32(rews3), out, w)
+    w3 = w.cpu().numpy()
+    r3 = r[:-1]
+    l3 = (r3 - r3.max()) / r3.std() / 0.05
+    e3 = np.exp(l3); e3 /= e3.sum()
+    assert w3[-1] == 0 and np.abs(w3[:-1] - e3).max() < 5e-5 and torch.isfinite(out).all()
+    # no finite reward at all: the whole weight goes to the mean sample, Ybar is kept (clipped)
+    mb.plan.reverse_update(mb.plan.f32(eps), None, mb.plan.f32(Ybar), noise, mb.plan.f32(np.full(N + 1, np.nan)), out, w)
+    assert float(w[-1]) == 1.0 and float(w[:-1].abs().max()) == 0.0
+    assert np.abs(out.cpu().numpy() - np.clip(Ybar, -1, 1)).max() < 1e-6
 
 
 def test_native_rng_matches_oracle_restatement(built):
@@ -200,6 +216,11 @@ def test_full_size_properties(built):
     # mean of zero-noise rows equals the mean row
     _, Yz, iz = mb.reverse_once(st, rng, Y0, torch.zeros(Hn + 1, device="cuda"))
     assert float((iz["rews"] - iz["rews"][-1]).abs().max()) == 0.0
+    # ... and std(rews) == 0 must not poison the update (the reference would return NaN): uniform
+    # weights, Ybar = the clipped input knots
+    assert torch.isfinite(Yz).all() and torch.allclose(Yz, Y0.clamp(-1, 1), atol=1e-6)
+    assert torch.allclose(iz["weights"], torch.full_like(iz["weights"], 1.0 / (N + 1)), rtol=1e-4)
+    assert torch.isfinite(iz["xbar"]).all()
 
 
 def test_error_paths(built):
