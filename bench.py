@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """bench.py — DIAL-MPC sampling core on B200.
 
-One "step" = one MPC planning step of BASELINE.json configs[1] (unitree_go2_seq_jump,
-Nsample=2048 per GPU, Hsample=25, Hnode=5, Ndiffuse=4): shift + Ndiffuse x reverse_once
-(sample -> spline -> batched full-order rollout -> reward -> softmax update).
+One "step" = one MPC planning step of a BASELINE.json config: shift + Ndiffuse x reverse_once
+(sample -> spline -> batched full-order rollout -> reward -> softmax update).  The headline is
+configs[1] (unitree_go2_seq_jump, Nsample=2048 per GPU, Hsample=25, Hnode=5, Ndiffuse=4);
+`--config i` selects another one, and the default run appends a compact block for every other
+single-GPU config (and, at --gpus 8, configs[4] = 65536 samples over 8 GPUs).
 Metric: sample-steps/s = Ndiffuse * Nsample_total * Hsample / seconds per step.
 
     python bench.py --gpus 1 --steps 20 --warmup 5
@@ -12,87 +14,148 @@ Metric: sample-steps/s = Ndiffuse * Nsample_total * Hsample / seconds per step.
 """
 from __future__ import annotations
 
-import argparse
-import json
 import os
-import subprocess
-import sys
-import threading
-import time
 
-import numpy as np
+# the CPU arms run one process per core: BLAS / OpenMP pools inside each would oversubscribe the
+# host (round 1: 128 procs x BLAS threads -> 5.9x spread between boxes).  Must precede `import numpy`.
+for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ[_k] = "1"
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import sys  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+from baseline_configs import BASELINE, ENV_CFG, dial_config, product_env  # noqa: E402
 
-WORKLOAD = dict(env_name="unitree_go2_seq_jump", Nsample=2048, Hsample=25, Hnode=5, Ndiffuse=4,
-                temp_sample=0.05, horizon_diffuse_factor=0.9, traj_diffuse_factor=0.5)
-ENV_CFG = dict(pose_target_sequence=[[0, 0, 0.27], [0.4, 0, 0.27], [0.8, 0, 0.27], [1.2, 0, 0.27], [1.6, 0, 0.27]],
-               yaw_target_sequence=[0.0] * 5)
 METRIC = "sample-steps/s (Nsample*Hsample/wall-s) per MPC reverse_once, Go2"
 
 
+def usable_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 # --------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the fp64 NumPy oracle (CPU restatement, NOT reference JAX)
+# CPU arms: the oracle (CPU restatement, NOT reference JAX) on the host cores.
+#   kind "port"     fp64 NumPy oracle (oracle/*.py), batched over the rows of one worker
+#   kind "port-c"   fp32 C port of the per-sample step (oracle/c), one sample at a time
+# Both roll ONE reverse_once of the chosen config: its Nsample+1 rows are split over the worker
+# processes (pinned, one per core), the softmax update runs once on the gathered rewards.
 # --------------------------------------------------------------------------------------------
-def _oracle_worker(args):
-    seed, nrows, n_calls = args
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
+def _cpu_worker(args):
+    ci, rows_lo, rows_hi, core, kind, seed, n_calls = args
+    try:
+        os.sched_setaffinity(0, {core})
+    except (AttributeError, OSError):
+        pass
     from oracle.envs_oracle import make_env
     from oracle.planner_oracle import PlannerOracle
-    env = make_env(WORKLOAD["env_name"], ENV_CFG)
+    b = BASELINE[ci]
+    env = make_env(b["env"], ENV_CFG[b["env"]])
     s = env.reset()
     for _ in range(10):
         s, _, _ = env.step(s, np.zeros((1, env.nu)))
-    pl = PlannerOracle(env, nrows, WORKLOAD["Hsample"], WORKLOAD["Hnode"], WORKLOAD["temp_sample"],
-                       WORKLOAD["horizon_diffuse_factor"], WORKLOAD["traj_diffuse_factor"])
+    N, Hs, Hn = b["N"], b["Hs"], b["Hn"]
+    pl = PlannerOracle(env, N, Hs, Hn, b["temp"], b["hdf"], b["tdf"])
     rng = np.random.default_rng(seed)
-    Y = np.zeros((WORKLOAD["Hnode"] + 1, env.nu))
-    t0 = time.perf_counter()
+    Y = np.zeros((Hn + 1, env.nu))
+    roll = None
+    if kind == "port-c":
+        from oracle.c_port import CPort
+        roll = CPort(env, b).rollout_rews
+    t_in = 0.0
+    out = None
     for i in range(n_calls):
-        eps = rng.standard_normal((nrows, WORKLOAD["Hnode"] + 1, env.nu))
-        Y, _ = pl.reverse_once(s, eps, Y, pl.sigma_control * WORKLOAD["traj_diffuse_factor"] ** (i % WORKLOAD["Ndiffuse"]))
-    return time.perf_counter() - t0
+        eps = rng.standard_normal((N, Hn + 1, env.nu))        # same eps on every worker (same seed)
+        Y0s = pl.make_Y0s(eps, Y, pl.sigma_control * b["tdf"] ** (i % b["Ndiffuse"]))
+        us = pl.node2u(Y0s[rows_lo:rows_hi])
+        t0 = time.perf_counter()
+        if roll is not None:
+            rews = roll(s, us)
+        else:
+            rews = env.rollout(s, us)[0].mean(-1)
+        t_in += time.perf_counter() - t0
+        out = rews
+    return t_in, out
 
 
-def oracle_throughput(rows_per_proc: int, n_calls: int, procs: int):
-    """sample-steps/s of the oracle's reverse_once on `procs` host processes, each rolling
-    `rows_per_proc` samples of the bench workload `n_calls` times."""
+def cpu_reverse_once(ci: int, procs: int, kind: str, n_calls: int = 1, rows_cap=None):
+    """One (or n_calls) reverse_once of config ci with its rows split over `procs` pinned workers.
+    rows_cap bounds the sample (first rows_cap rows) when the whole config would take too long.
+    Returns (sample-steps/s, wall seconds of the slowest worker, rows rolled)."""
     import multiprocessing as mp
-    ctx = mp.get_context("fork")
+    b = BASELINE[ci]
+    rows = b["N"] + 1 if rows_cap is None else min(b["N"] + 1, rows_cap)
+    procs = max(1, min(procs, rows))
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = list(range(os.cpu_count() or 1))
+    bounds = np.linspace(0, rows, procs + 1).astype(int)
+    jobs = [(ci, int(bounds[i]), int(bounds[i + 1]), cores[i % len(cores)], kind, 0, n_calls) for i in range(procs)]
     if procs == 1:
-        inner = [_oracle_worker((0, rows_per_proc, n_calls))]
+        res = [_cpu_worker(jobs[0])]
     else:
-        with ctx.Pool(procs) as pool:
-            inner = pool.map(_oracle_worker, [(i, rows_per_proc, n_calls) for i in range(procs)])
-    wall = max(inner)   # slowest worker's time inside reverse_once (model load / reset excluded)
-    units = procs * rows_per_proc * WORKLOAD["Hsample"] * n_calls
-    return units / wall, wall
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    wall = max(r[0] for r in res)
+    rews = np.concatenate([r[1] for r in res])
+    t0 = time.perf_counter()                 # the one softmax on the gathered rewards (negligible)
+    lp = (rews - rews[-1]) / rews.std() / b["temp"]
+    w = np.exp(lp - lp.max())
+    w /= w.sum()
+    wall += time.perf_counter() - t0
+    units = (rows - 1) * b["Hs"] * n_calls if rows_cap is None else rows * b["Hs"] * n_calls
+    return units / wall, wall, rows
+
+
+def have_c_port() -> bool:
+    try:
+        from oracle import c_port
+        return c_port.available()
+    except Exception:
+        return False
 
 
 def run_reference(args):
+    """Reference arm for this tier: the CPU restatement of the path on all host cores, SAME config
+    (Nsample, Hsample, env) as the own arm; a step = one reverse_once (the own arm's step is
+    Ndiffuse of them: the metric is per reverse_once, so the two are comparable)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    rows = 128
-    for _ in range(args.warmup and 1):
-        oracle_throughput(rows, 1, cores)
+    ci = args.config
+    b = BASELINE[ci]
+    cores = usable_cores()
+    kind = "port-c" if have_c_port() and not args.numpy_oracle else "port"
+    for _ in range(1 if args.warmup else 0):
+        cpu_reverse_once(ci, cores, kind)
     vals, t_all = [], 0.0
     for _ in range(args.steps):
-        v, wall = oracle_throughput(rows, 1, cores)
+        v, wall, rows = cpu_reverse_once(ci, cores, kind)
         vals.append(v)
         t_all += wall
-    value = float(np.sum([cores * rows * WORKLOAD["Hsample"]] * args.steps) / t_all)
-    sample = (f"{cores} procs x {rows} samples x (Hsample+1)={WORKLOAD['Hsample'] + 1} env steps per step "
-              f"(one reverse_once of the bench workload at Nsample={cores * rows}); fp64 NumPy oracle port, "
-              "CPU restatement, not reference JAX")
+    value = float(b["N"] * b["Hs"] * args.steps / t_all)
+    what = ("fp32 C port of the per-sample step (oracle/c)" if kind == "port-c" else "fp64 NumPy oracle port")
+    sample = (f"one reverse_once of {b['name']} per step: all {b['N']}+1 rows x (Hsample+1)={b['Hs'] + 1} env steps split over "
+              f"{cores} pinned single-threaded processes, one softmax; {what}; CPU restatement, not reference JAX")
     line = dict(impl="reference", metric=METRIC, value=value, unit="sample-steps/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * t_all / args.steps,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload="unitree_go2_seq_jump Nsample=2048 Hsample=25 Hnode=5 Ndiffuse=4 (bounded sample)",
-                            **{k: WORKLOAD[k] for k in ("Hsample", "Hnode")}),
-                cpu_baseline=dict(value=value, unit="sample-steps/s", cores=cores, kind="port", sample=sample),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32" if kind == "port-c" else "f64",
+                data="synthetic",
+                config=dict(workload=f"{b['name']} (BASELINE configs[{ci}])", Nsample_per_gpu=b["N"], Nsample_total=b["N"],
+                            Hsample=b["Hs"], Hnode=b["Hn"], Ndiffuse=b["Ndiffuse"],
+                            step="one reverse_once (metric is per reverse_once)"),
+                cpu_baseline=dict(value=value, unit="sample-steps/s", cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="sample-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -145,34 +208,25 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # own arm
 # --------------------------------------------------------------------------------------------
-def run_own(args):
+def _load_json(*path):
+    try:
+        return json.load(open(os.path.join(ROOT, *path)))
+    except Exception:
+        return {}
+
+
+def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, full=True, fp32_peak_tf=None):
+    """Time config ci on this process group.  Returns the JSON fields of the config (rank 0: all
+    of them; other ranks: partial).  full=False skips the clocks / cpu arms (secondary blocks)."""
     import torch
     import torch.distributed as dist
-    import __graft_entry__ as graft
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if rank == 0:
-        graft.build()
-    if world > 1:
-        dist.barrier()
-    import dial_mpc_b200.envs as E
     from dial_mpc_b200 import random as drandom
-    from dial_mpc_b200.core.dial_config import DialConfig
     from dial_mpc_b200.core.dial_core import MBDPI
 
-    W = WORKLOAD
-    Ntotal = W["Nsample"] * world          # weak scaling: 2048 samples per GPU
-    cfg = DialConfig(env_name=W["env_name"], Nsample=Ntotal, Hsample=W["Hsample"], Hnode=W["Hnode"],
-                     Ndiffuse=W["Ndiffuse"], temp_sample=W["temp_sample"],
-                     horizon_diffuse_factor=W["horizon_diffuse_factor"], traj_diffuse_factor=W["traj_diffuse_factor"])
-    ecfg = E.UnitreeGo2SeqJumpEnvConfig(**{k: np.array(v) for k, v in ENV_CFG.items()})
-    env = E.get_environment(cfg.env_name, config=ecfg)
+    b = BASELINE[ci]
+    cfg = dial_config(ci, world=world)       # weak scaling: b["N"] samples per GPU
+    Ntotal = cfg.Nsample
+    env = product_env(b["env"])
     mb = MBDPI(cfg, env, rank=rank, world_size=world)
     dev = mb.device
     # synthetic state: reset, then 10 env steps with zero action so contacts are settled
@@ -195,17 +249,14 @@ def run_own(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         Y, rng, info = mpc_step(Y, rng)
     sync_all()
     launches0 = mb.plan.launches
     evs = []
     sync_all()
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.zero_()                                   # L2 flush, outside the timed events
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -215,14 +266,14 @@ def run_own(args):
     sync_all()
     t_wall = time.perf_counter() - t_wall0
     launches = mb.plan.launches - launches0
-    clocks = sampler.stop(t_wall0, t_wall0 + t_wall) if rank == 0 else None
-    t_dev = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+    clocks = sampler.stop(t_wall0, t_wall0 + t_wall) if (sampler is not None and rank == 0) else None
+    t_dev = sum(a.elapsed_time(b_) for a, b_ in evs) / 1e3
     if world > 1:
         t = torch.tensor([t_dev], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev = float(t.item())
     units_per_step = cfg.Ndiffuse * Ntotal * cfg.Hsample
-    value = units_per_step * args.steps / t_dev
+    value = units_per_step * steps / t_dev
 
     # ---- e2e: public API with HOST buffers (pinned), H2D of the state + plan, D2H of the plan ----
     ps = state.pipeline_state
@@ -247,7 +298,7 @@ def run_own(args):
         rng, _ = e2e_step(rng)
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         rng, _ = e2e_step(rng)
     sync_all()
     t_e2e = time.perf_counter() - t0
@@ -255,7 +306,15 @@ def run_own(args):
         t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
-    e2e_value = units_per_step * args.steps / t_e2e
+    e2e_value = units_per_step * steps / t_e2e
+
+    # ---- per-phase device times of one reverse_once (CUDA events between the stages) ---------------
+    phases = mb.phase_times(state, drandom.split(rng)[1], Y, factors[0], reps=10)
+    if world > 1:
+        keys = sorted(phases)
+        t = torch.tensor([phases[k] for k in keys], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        phases = {k: float(v) for k, v in zip(keys, t.tolist())}
 
     # ---- roofline of the dominant kernel (rollout_kernel), timed alone with CUDA events ----------
     m = env.sys
@@ -264,7 +323,7 @@ def run_own(args):
     for _ in range(3):
         mb.plan.reverse_rollout(state, None, key, Y0, mb.sigma_control, mb._rews_local)
     torch.cuda.synchronize()
-    reps = 20
+    reps = 20 if b["env"] != "allegro_reorient" else 5
     ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ks.record()
     for _ in range(reps):
@@ -273,37 +332,87 @@ def run_own(args):
     torch.cuda.synchronize()
     t_kernel = ks.elapsed_time(ke) / 1e3 / reps
     rows, H = mb.Nlocal + 1, cfg.Hsample + 1
+    nfr = env._n_frames
     per_rowstep = 4 * (m.nq + m.nv + 3 * (m.nbody - 1))            # q, qd, x.pos written once per env step
     alg_bytes = rows * H * per_rowstep + rows * 4 + (m.nq + 2 * m.nv) * 4
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / t_kernel / 1e9
-    traffic, fp32 = None, None
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "rollout_traffic.json")))
-        traffic = prof["dram_bytes_per_launch"]
-        # compute-side view (the binding resource): flop per physics step counted by ncu (committed
-        # capture) x physics steps per second measured live, against the nominal fp32 peak
-        fpp = prof["fp32"]["flop_per_physics_step"]
-        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
-        peak_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-        ach_tf = fpp * rows * H / t_kernel / 1e12
-        fp32 = dict(flop_per_physics_step=fpp, achieved_tflops=ach_tf, peak_tflops=peak_tf, frac=ach_tf / peak_tf,
-                    peak_source="nominal 148 SM x 128 FFMA/clk x 2 x sm_max_mhz", flop_source="ncu capture profiles/rollout_traffic.json")
-    except Exception:
-        pass
-    roofline = dict(bound="hbm", kernel="rollout_kernel", achieved=achieved, peak=peak, unit="GB/s",
-                    frac=achieved / peak, traffic=traffic, peak_source="measured" if peaks else "fallback",
-                    kernel_ms=t_kernel * 1e3, algorithmic_bytes_per_launch=alg_bytes,
-                    kernel_share_of_step=cfg.Ndiffuse * t_kernel / (t_dev / args.steps),
-                    note=("the path is fp32-issue/latency bound (~140 flop/B, SURVEY.md 8d): the HBM fraction is "
-                          "reported as required but cannot approach 1; see DESIGN.md"),
-                    physics_steps_per_s=rows * H / t_kernel, fp32=fp32)
+    peaks = _load_json("MEASURED_PEAKS.json")
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_ach = alg_bytes / t_kernel / 1e9
+    prof = _load_json("profiles", "rollout_counts.json").get(b["name"], {})
+    traffic = prof.get("dram_bytes_per_launch")
+    fpp = prof.get("flop_per_physics_step")
+    hbm = dict(achieved=hbm_ach, peak=hbm_peak, unit="GB/s", frac=hbm_ach / hbm_peak, traffic=traffic,
+               peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s", algorithmic_bytes_per_launch=alg_bytes,
+               bytes_per_row_step=per_rowstep)
+    roofline = dict(kernel="rollout_kernel", kernel_ms=t_kernel * 1e3,
+                    kernel_share_of_step=cfg.Ndiffuse * t_kernel / (t_dev / steps),
+                    physics_steps_per_s=rows * H * nfr / t_kernel, hbm=hbm)
+    if fpp and fp32_peak_tf:
+        ach_tf = fpp * rows * H * nfr / t_kernel / 1e12
+        roofline.update(bound="fp32", achieved=ach_tf, peak=fp32_peak_tf, unit="TFLOP/s", frac=ach_tf / fp32_peak_tf,
+                        traffic=traffic, flop_per_physics_step=fpp,
+                        peak_source="measured in-run: dial_fp32_peak (independent FFMA chains, full occupancy, CUDA events)",
+                        flop_source="ncu thread-instruction counts FADD+FMUL+2*FFMA, profiles/rollout_counts.json",
+                        note=("the path has ~140 flop per algorithmic byte (SURVEY.md 8d): bound by fp32 issue / "
+                              "dependent-instruction latency, not HBM; the HBM fraction is kept under `hbm`"))
+    else:
+        roofline.update(bound="hbm", achieved=hbm_ach, peak=hbm_peak, unit="GB/s", frac=hbm_ach / hbm_peak, traffic=traffic,
+                        note="no flop count for this config under profiles/: HBM view only (the path is fp32-bound)")
+    out = dict(value=value, ms_per_step=1e3 * t_dev / steps, gpu_launches=int(launches), wall_s_timed_region=t_wall,
+               e2e=dict(value=e2e_value, unit="sample-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                        ms_per_step=1e3 * t_e2e / steps),
+               roofline=roofline, phases_us_per_reverse_once=phases, clocks=clocks,
+               config=dict(workload=f"{b['name']} (BASELINE configs[{ci}])", Nsample_per_gpu=b["N"], Nsample_total=Ntotal,
+                           Hsample=b["Hs"], Hnode=b["Hn"], Ndiffuse=b["Ndiffuse"], n_frames=nfr,
+                           step="shift + Ndiffuse x reverse_once (rollout, exchange, update, bars)",
+                           rng="in-kernel Threefry-2x32", l2="256 MiB memset between steps (outside the timed events)",
+                           parallelism=f"samples sharded over {world} GPU(s), {mb.exchange_name} of rewards per reverse_once"))
+    del mb, flush
+    torch.cuda.empty_cache()
+    return out
 
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as graft
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        graft.build()
+    if world > 1:
+        dist.barrier()
+    from dial_mpc_b200 import _capi
+    tf = _capi.C.c_float(0.0)
+    _capi.check(_capi.lib().dial_fp32_peak(2000, _capi.C.byref(tf)))
+    fp32_peak = float(tf.value)
+
+    ci = args.config
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    head = measure_config(ci, args, rank, world, local, args.steps, args.warmup, sampler=sampler, fp32_peak_tf=fp32_peak)
+    others = {}
+    if not args.only:
+        todo = [i for i in (0, 1, 2, 3) if i != ci] if world == 1 else []
+        if world == 1 and ci != 4:
+            todo.append(4)                  # one 8192-sample shard of configs[4]
+        if world == 8 and ci != 4:
+            todo = [4]                      # the real configs[4]: 65536 samples over 8 GPUs
+        for i in todo:
+            st = max(3, min(args.steps, 10 if i != 3 else 4))
+            r = measure_config(i, args, rank, world, local, st, 3, fp32_peak_tf=fp32_peak)
+            keep = {k: r[k] for k in ("value", "ms_per_step", "gpu_launches", "e2e", "roofline", "phases_us_per_reverse_once", "config")}
+            keep.update(steps=st, warmup=3, unit="sample-steps/s")
+            if i == 4 and world == 1:
+                keep["note"] = "ONE 8192-sample shard of configs[4] on one GPU (the full config needs --gpus 8)"
+            others[f"configs[{i}]"] = keep
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -311,27 +420,32 @@ def run_own(args):
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 / N=1 only -------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        v1, wall1 = oracle_throughput(256, 1, 1)
-        vall, wall = oracle_throughput(256, 1, cores)
-        cpu = dict(value=vall, unit="sample-steps/s", cores=cores, kind="port",
-                   sample=(f"{cores} procs x 256 samples x {W['Hsample'] + 1} env steps (one reverse_once, same env/state); "
-                           f"single-core: {v1:.1f} sample-steps/s on 256 samples; fp64 NumPy oracle — CPU restatement, "
-                           "not reference JAX"),
-                   single_core_value=v1, wall_s=wall + wall1)
-    line = dict(metric=METRIC, value=value, unit="sample-steps/s", n_gpus=world, steps=args.steps,
-                warmup=max(args.warmup, 3), ms_per_step=1e3 * t_dev / args.steps, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="unitree_go2_seq_jump (BASELINE configs[1])", Nsample_per_gpu=W["Nsample"],
-                            Nsample_total=Ntotal, Hsample=W["Hsample"], Hnode=W["Hnode"], Ndiffuse=W["Ndiffuse"],
-                            step="shift + Ndiffuse x reverse_once (rollout, allgather, update, bars)",
-                            rng="in-kernel Threefry-2x32", l2="256 MiB memset between steps (outside the timed events)",
-                            parallelism=f"samples sharded over {world} GPU(s), 1 allgather(rews) + 1 allreduce(bars) per reverse_once"),
-                clocks=clocks, e2e=dict(value=e2e_value, unit="sample-steps/s", h2d_bytes_per_step=h2d,
-                                        d2h_bytes_per_step=d2h, ms_per_step=1e3 * t_e2e / args.steps),
-                gpu_launches=int(launches), wall_s_timed_region=t_wall, roofline=roofline)
+        cores = usable_cores()
+        b = BASELINE[ci]
+        kind = "port-c" if have_c_port() else "port"
+        cap1 = 256 if kind == "port" else None
+        v1, wall1, rows1 = cpu_reverse_once(ci, 1, kind, rows_cap=cap1)
+        vall, wall, rows = cpu_reverse_once(ci, cores, kind)
+        cpu = dict(value=vall, unit="sample-steps/s", cores=cores, kind=kind,
+                   sample=(f"one reverse_once of {b['name']}: all {rows} rows x {b['Hs'] + 1} env steps split over {cores} pinned "
+                           f"single-threaded processes; single core: {v1:.1f} sample-steps/s on {rows1} rows; "
+                           + ("fp32 C port of the per-sample step" if kind == "port-c" else "fp64 NumPy oracle")
+                           + " — CPU restatement, not reference JAX"),
+                   single_core_value=v1, scaling_vs_linear=vall / (v1 * cores), wall_s=wall + wall1)
+        if kind == "port-c":               # the NumPy oracle beside it (bounded), for continuity with round 1
+            vn, walln, rowsn = cpu_reverse_once(ci, cores, "port")
+            cpu["numpy_oracle_value"] = vn
+            cpu["wall_s"] += walln
+    line = dict(metric=METRIC, value=head["value"], unit="sample-steps/s", n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=head["ms_per_step"], higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=head["config"],
+                clocks=head["clocks"], e2e=head["e2e"], gpu_launches=head["gpu_launches"],
+                wall_s_timed_region=head["wall_s_timed_region"], roofline=head["roofline"],
+                phases_us_per_reverse_once=head["phases_us_per_reverse_once"], fp32_peak_tflops_measured=fp32_peak)
     if cpu:
         line["cpu_baseline"] = cpu
+    if others:
+        line["other_configs"] = others
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -343,7 +457,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=sorted(BASELINE), help="BASELINE.json configs[i] (default 1: the headline)")
+    ap.add_argument("--only", action="store_true", help="time only --config (no block for the other configs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--numpy-oracle", action="store_true", help="reference arm: NumPy oracle even if the C port is built")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

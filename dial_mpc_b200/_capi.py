@@ -132,10 +132,16 @@ def _bind(path: str) -> C.CDLL:
     U2 = C.POINTER(C.c_uint32)
     lib.dial_reverse_rollout.argtypes = [V, C.POINTER(dial_state), P, U2, P, P, P, V]
     lib.dial_reverse_update.argtypes = [V, P, U2, P, P, P, P, P, V]
+    lib.dial_reverse_update_x.argtypes = [V, P, U2, P, P, P, P, P, P, V]
     lib.dial_reverse_trajbar.argtypes = [V, P, I, P, P, P, V]
+    lib.dial_exchange_create.argtypes = [V, I, I, P]
+    lib.dial_exchange_connect.argtypes = [V, P]
+    lib.dial_exchange_status.argtypes = [V, U2]
     lib.dial_reverse_trajectories.argtypes = [V, P, P, P, V]
     lib.dial_key_split.argtypes = [U2, U2, U2]
     lib.dial_key_split.restype = None
+    lib.dial_fp32_peak.argtypes = [I, C.POINTER(C.c_float)]
+    lib.dial_fp32_peak.restype = C.c_int
     lib.dial_launch_count.argtypes = [V]
     lib.dial_launch_count.restype = C.c_int64
     lib.dial_debug_counters.argtypes = [V, C.POINTER(C.c_float)]
@@ -148,7 +154,8 @@ def _bind(path: str) -> C.CDLL:
     lib.dial_mpc_step.argtypes = [V, I, I, V]
     lib.dial_mpc_step.restype = C.c_int
     for fn in ("dial_rollout", "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout",
-               "dial_reverse_update", "dial_reverse_trajbar", "dial_reverse_trajectories"):
+               "dial_reverse_update", "dial_reverse_update_x", "dial_reverse_trajbar", "dial_reverse_trajectories",
+               "dial_exchange_create", "dial_exchange_connect", "dial_exchange_status"):
         getattr(lib, fn).restype = C.c_int
     if lib.dial_abi_version() != DEFINES["DIAL_ABI_VERSION"]:
         raise RuntimeError(f"{os.path.basename(path)} ABI version does not match include/dial_b200.h")
@@ -175,6 +182,7 @@ def check(rc: int) -> None:
 
 
 EXPORTS = ["dial_abi_version", "dial_last_error", "dial_sizeof", "dial_plan_create", "dial_plan_destroy", "dial_rollout",
-           "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout", "dial_reverse_update",
-           "dial_reverse_trajbar", "dial_reverse_trajectories", "dial_key_split", "dial_launch_count", "dial_debug_counters",
+           "dial_env_step", "dial_pipeline_init", "dial_reverse_rollout", "dial_reverse_update", "dial_reverse_update_x",
+           "dial_exchange_create", "dial_exchange_connect", "dial_exchange_status",
+           "dial_reverse_trajbar", "dial_reverse_trajectories", "dial_key_split", "dial_fp32_peak", "dial_launch_count", "dial_debug_counters",
            "dial_solver_variant", "dial_custom_reward_id", "dial_mpc_bind", "dial_mpc_step"]

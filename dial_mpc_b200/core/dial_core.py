@@ -95,6 +95,18 @@ class MBDPI:
         # the info-only bars (+ their allreduce) run on a side stream and overlap the next rollout
         self._side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._bar_events = []
+        # sharded plans: rewards (and bars) are exchanged through NVLink peer memory by the kernels
+        # themselves (dial_exchange_*).  DIAL_EXCHANGE=nccl keeps the host-issued NCCL collectives;
+        # they are also the fallback when CUDA IPC cannot map the peers (different nodes / no P2P).
+        self.xch = False
+        self.xch_error = None
+        if world_size > 1 and dev.type == "cuda" and hasattr(self.plan, "exchange_setup") \
+                and os.environ.get("DIAL_EXCHANGE", "p2p") != "nccl":
+            try:
+                self.plan.exchange_setup(rank, world_size, process_group)
+                self.xch = True
+            except Exception as e:  # noqa: BLE001  (kept: reported through exchange_name / bench line)
+                self.xch_error = str(e)
 
     # -- spline maps (dial_core.py:82-101) -------------------------------------------------------
     def node2u(self, nodes):
@@ -138,18 +150,25 @@ class MBDPI:
         if self._side is not None and len(self._bar_events) >= 2:
             # the trajectory buffer about to be overwritten was read by the bars two iterations ago
             torch.cuda.current_stream().wait_event(self._bar_events.pop(0))
-        self.plan.reverse_rollout(state, eps, key, Ybar_i, noise_scale, self._rews_local)
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self._rews_all[:N], self._rews_local[:Nl], group=self.pg)
-            self._rews_all[N:].copy_(self._rews_local[Nl:])
-            rews_all = self._rews_all
-        else:
-            rews_all = self._rews_local
         Ybar = torch.empty_like(Ybar_i)
         weights = torch.empty_like(self._weights)
-        self.plan.reverse_update(eps, key, Ybar_i, noise_scale, rews_all, Ybar, weights)
-        info: Dict[str, Any] = {"rews": rews_all.clone(), "new_noise_scale": noise_scale, "weights": weights}
+        if self.world_size == 1:
+            rews = torch.empty_like(self._rews_local)      # fresh output (functional API), written by the kernel
+            self.plan.reverse_rollout(state, eps, key, Ybar_i, noise_scale, rews)
+            self.plan.reverse_update(eps, key, Ybar_i, noise_scale, rews, Ybar, weights)
+        elif self.xch:
+            # the rollout epilogue stores the rewards into every rank's mailbox; the weights kernel waits
+            rews = torch.empty_like(self._rews_all)
+            self.plan.reverse_rollout(state, eps, key, Ybar_i, noise_scale, self._rews_local)
+            self.plan.reverse_update(eps, key, Ybar_i, noise_scale, None, Ybar, weights, rews_gathered=rews)
+        else:
+            import torch.distributed as dist
+            self.plan.reverse_rollout(state, eps, key, Ybar_i, noise_scale, self._rews_local)
+            dist.all_gather_into_tensor(self._rews_all[:N], self._rews_local[:Nl], group=self.pg)
+            self._rews_all[N:].copy_(self._rews_local[Nl:])
+            rews = self._rews_all.clone()
+            self.plan.reverse_update(eps, key, Ybar_i, noise_scale, rews, Ybar, weights)
+        info: Dict[str, Any] = {"rews": rews, "new_noise_scale": noise_scale, "weights": weights}
         if self.compute_bars:
             m = self.env.sys
             Hs1 = self.args.Hsample + 1
@@ -164,8 +183,8 @@ class MBDPI:
                 import contextlib
                 ctx = contextlib.nullcontext()
             with ctx:
-                self.plan.reverse_trajbar(weights, self.rank, qbar, qdbar, xbar)
-                if self.world_size > 1:
+                self.plan.reverse_trajbar(weights, self.rank, qbar, qdbar, xbar)   # exchange on: already the all-rank sum
+                if self.world_size > 1 and not self.xch:
                     import torch.distributed as dist
                     dist.all_reduce(bars, group=self.pg)
                 if self._side is not None:
@@ -180,6 +199,50 @@ class MBDPI:
             info["qdbar"] = qdbar.view(Hs1, m.nv)
             info["xbar"] = xbar.view(Hs1, m.nbody - 1, 3)
         return rng, Ybar, info
+
+    @property
+    def exchange_name(self) -> str:
+        if self.world_size == 1:
+            return "no exchange (single GPU)"
+        return ("one peer-memory exchange fused into the rollout epilogue / weights prologue (NVLink stores + flags)"
+                if self.xch else "one NCCL allgather" + (f" (peer exchange unavailable: {self.xch_error})" if self.xch_error else ""))
+
+    def phase_times(self, state, key, Ybar_i, noise_scale, reps: int = 10) -> Dict[str, float]:
+        """Device time (microseconds, CUDA events on the current stream) of the stages of one
+        ``reverse_once``: rollout | rewards exchange | weights + Ybar | bars (+ their allreduce).
+        Measurement aid for bench.py; the stages run back to back on one stream here."""
+        Ybar_i, noise_scale = self._t(Ybar_i), self._t(noise_scale)
+        N, Nl = self.args.Nsample, self.Nlocal
+        m = self.env.sys
+        Hs1 = self.args.Hsample + 1
+        n1, n2 = Hs1 * m.nq, Hs1 * m.nv
+        bars = torch.empty_like(self._bars)
+        Ybar = torch.empty_like(Ybar_i)
+        acc = {"rollout": 0.0, "exchange": 0.0, "update": 0.0, "bars": 0.0}
+        for rep in range(reps + 2):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
+            self.plan.reverse_rollout(state, None, key, Ybar_i, noise_scale, self._rews_local)
+            ev[1].record()
+            if self.world_size > 1 and not self.xch:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self._rews_all[:N], self._rews_local[:Nl], group=self.pg)
+                self._rews_all[N:].copy_(self._rews_local[Nl:])
+                rews_all = self._rews_all
+            else:
+                rews_all = None if self.xch else self._rews_local   # exchange: the wait is inside the update stage
+            ev[2].record()
+            self.plan.reverse_update(None, key, Ybar_i, noise_scale, rews_all, Ybar, self._weights)
+            ev[3].record()
+            self.plan.reverse_trajbar(self._weights, self.rank, bars[:n1], bars[n1:n1 + n2], bars[n1 + n2:])
+            if self.world_size > 1 and not self.xch:
+                dist.all_reduce(bars, group=self.pg)
+            ev[4].record()
+            torch.cuda.synchronize()
+            if rep >= 2:
+                for i, k in enumerate(acc):
+                    acc[k] += ev[i].elapsed_time(ev[i + 1]) * 1e3 / reps
+        return acc
 
     def reverse_scan(self, state, rng, Y0, factors):
         """``lax.scan(reverse_scan, (rng, Y0, state), factors)`` of dial_core.py:177-180,262-264."""
@@ -212,12 +275,14 @@ class DeviceLoop:
     State, step counters, rng and control knots live in device tensors owned by this object; the
     host only launches the graph and reads back what it needs (e.g. ``action``).  Equals the
     eager ``env.step`` + ``MBDPI.shift`` + ``MBDPI.reverse_scan`` sequence (tests/test_gpu_parity.py).
-    Single-GPU plans."""
+    Sharded plans replay the same graph on every rank (one process per GPU): the rewards cross
+    the GPUs inside the kernels (peer-memory exchange), so no host collective sits in the step."""
 
     def __init__(self, mbdpi: "MBDPI", state, rng, Y0=None, n_diffuse_max: Optional[int] = None,
                  compute_bars: bool = True):
-        if mbdpi.world_size != 1:
-            raise RuntimeError("DeviceLoop is single-GPU; sharded runs use MBDPI.reverse_once")
+        if mbdpi.world_size != 1 and not mbdpi.xch:
+            raise RuntimeError("DeviceLoop on a sharded plan needs the peer-memory exchange (dial_exchange_*); "
+                               f"it is off: {mbdpi.xch_error or 'DIAL_EXCHANGE=nccl'}")
         self.mbdpi, self.plan = mbdpi, mbdpi.plan
         a, pl, dev = mbdpi.args, mbdpi.plan, mbdpi.device
         nmax = int(n_diffuse_max or max(a.Ndiffuse, a.Ndiffuse_init))
@@ -234,7 +299,8 @@ class DeviceLoop:
             rng=torch.as_tensor(key.copy(), device=dev),
             Y=(torch.zeros(a.Hnode + 1, mbdpi.nu, device=dev) if Y0 is None else f(Y0).clone()),
             ctrl=torch.zeros(mbdpi.nu, device=dev), reward=torch.zeros(1, device=dev),
-            rews=torch.zeros(a.Nsample + 1, device=dev),
+            rews=torch.zeros(mbdpi.Nlocal + 1, device=dev),
+            rews_all=(torch.zeros(a.Nsample + 1, device=dev) if mbdpi.world_size > 1 else None),
             qbar=e(Hs1, m.nq) if compute_bars else None, qdbar=e(Hs1, m.nv) if compute_bars else None,
             xbar=e(Hs1, m.nbody - 1, 3) if compute_bars else None,
             noise=mbdpi.schedule(nmax).contiguous())
@@ -272,7 +338,7 @@ class DeviceLoop:
 
     def info(self) -> Dict[str, Any]:
         b = self.buf
-        d = {"rews": b["rews"]}
+        d = {"rews": b["rews_all"] if b["rews_all"] is not None else b["rews"]}
         if b["qbar"] is not None:
             d.update(qbar=b["qbar"], qdbar=b["qdbar"], xbar=b["xbar"])
         return d

@@ -123,6 +123,14 @@ struct RolloutArgs {
   const uint32_t* key_dev;      // non-null: sampling key read from here
   unsigned int* row_counter;  // non-null: persistent warps pull rows from this counter (dense path)
   float* dbg;           // optional device counters (DIAL_DEBUG_COUNTERS, see dial_debug_counters)
+  // multi-GPU reward exchange fused into the epilogue (dial_exchange_*): every finished row stores
+  // its mean reward straight into the mailbox of EVERY rank over NVLink peer memory; the last CTA
+  // of the grid then raises this rank's flag in every mailbox.  xch_world <= 1: off.
+  int32_t xch_world, xch_rank;
+  float* xch_mbox[DIAL_MAXRANK];         // mailbox of rank p: [2][Ntotal+1] floats (double-buffered by sequence parity)
+  uint32_t* xch_flags[DIAL_MAXRANK];     // flags of rank p:   [2][DIAL_MAXRANK], slot [buf][source rank] = sequence + 1
+  const uint32_t* xch_seq;               // local: sequence number of the current reverse_once
+  unsigned int* xch_done;                // local: CTAs of this launch that have finished
 };
 
 // ---------------------------------------------------------------------------------
@@ -2153,6 +2161,17 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     if (A.xpos) for (int i = lane; i < 3 * (nb - 1); i += 32) A.xpos[rt * 3 * (nb - 1) + i] = SM(xpos)[3 + i];
   }
   if (A.rews && lane == 0 && !fwd_only) A.rews[row] = rsum / (float)A.H;
+  if (A.xch_world > 1 && lane == 0 && !fwd_only && A.mode == 1) {
+    // sample rows go to every rank's mailbox at their GLOBAL index; the mean row (rolled by every
+    // rank, bitwise identical) only to the local one
+    const float val = rsum / (float)A.H;
+    const uint32_t buf = (*A.xch_seq) & 1u;
+    const size_t base = (size_t)buf * (size_t)(c.Ntotal + 1);
+    const bool sample = row < c.Nsample;
+    const size_t slot = base + (size_t)(sample ? c.shard_offset + row : c.Ntotal);
+    for (int p = 0; p < A.xch_world; ++p)
+      if (sample || p == A.xch_rank) A.xch_mbox[p][slot] = val;
+  }
   if (row == 0) {
     if (A.qpos_out) for (int i = lane; i < nq; i += 32) A.qpos_out[i] = SM(qpos)[i];
     if (A.qvel_out) for (int i = lane; i < nv; i += 32) A.qvel_out[i] = SM(qvel)[i];

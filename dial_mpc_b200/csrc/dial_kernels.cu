@@ -89,21 +89,58 @@ __device__ __forceinline__ void block_reduce(float (&v)[K], float* mx, float* re
 //     samples instead of 0/0 = NaN;
 //   * no finite reward at all: the whole weight goes to the mean sample (Ybar is kept);
 //   * a non-finite rbar only changes the reference point of the shift (softmax is shift-invariant).
+// Multi-GPU consumer side of the reward exchange (dial_exchange_*): wait until every rank's flag
+// in the local mailbox carries the current sequence number.  Bounded spin (~4 s of %globaltimer):
+// a peer that never arrives sets *err instead of hanging the GPU.
+struct XchWait {
+  const float* mbox;            // local mailbox [2][n]; null: no exchange, `rews` is used as given
+  const uint32_t* flags;        // local flags [2][DIAL_MAXRANK]
+  uint32_t* seq;                // local sequence number, bumped when the weights are done
+  uint32_t* err;                // local error word (1: timeout)
+  float* rews_copy;             // optional compact copy of the gathered rewards [n]
+  int world;
+};
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void xch_wait_flags(const uint32_t* flags, uint32_t want, int world, uint32_t* err) {
+  if ((int)threadIdx.x < world) {
+    const volatile uint32_t* f = flags + threadIdx.x;
+    const unsigned long long t0 = globaltimer_ns();
+    while (*f < want) {
+      if (globaltimer_ns() - t0 > 4000000000ull) { *err = 1u; break; }
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024) weights_kernel(const float* __restrict__ rews, int n, float temp,
-                                                        float* __restrict__ weights) {
+                                                        float* __restrict__ weights, const XchWait X) {
   __shared__ float red[4 * 32];
   const int tid = threadIdx.x;
-  float rbar = rews[n - 1];
+  if (X.mbox) {
+    const uint32_t seq = *X.seq, buf = seq & 1u;
+    xch_wait_flags(X.flags + buf * DIAL_MAXRANK, seq + 1u, X.world, X.err);
+    rews = X.mbox + (size_t)buf * n;
+    if (X.rews_copy)
+      for (int i = tid; i < n; i += blockDim.x) X.rews_copy[i] = __ldcg(rews + i);
+  }
+  float rbar = __ldcg(rews + n - 1);
   if (!isfinite(rbar)) rbar = 0.f;
   float st[3] = {0.f, 0.f, 0.f}, dmax = -INFINITY;
   for (int i = tid; i < n; i += blockDim.x) {
-    const float r = rews[i];
+    const float r = __ldcg(rews + i);
     if (isfinite(r)) { const float d = r - rbar; st[0] += 1.f; st[1] += d; st[2] += d * d; dmax = fmaxf(dmax, d); }
   }
   block_reduce<3>(st, &dmax, red);
   const float cnt = st[0];
   if (cnt == 0.f) {
     for (int i = tid; i < n; i += blockDim.x) weights[i] = (i == n - 1) ? 1.f : 0.f;
+    if (X.mbox && tid == 0) *X.seq = *X.seq + 1u;
     return;
   }
   const float mean = st[1] / cnt;
@@ -113,7 +150,7 @@ __global__ void __launch_bounds__(1024) weights_kernel(const float* __restrict__
   const float mx = dmax * inv;
   float z[1] = {0.f};
   for (int i = tid; i < n; i += blockDim.x) {
-    const float r = rews[i];
+    const float r = __ldcg(rews + i);
     const float e = isfinite(r) ? expf((r - rbar) * inv - mx) : 0.f;
     weights[i] = e;
     z[0] += e;
@@ -121,6 +158,47 @@ __global__ void __launch_bounds__(1024) weights_kernel(const float* __restrict__
   block_reduce<1>(z, nullptr, red);
   const float iz = 1.f / z[0];
   for (int i = tid; i < n; i += blockDim.x) weights[i] *= iz;
+  if (X.mbox && tid == 0) *X.seq = *X.seq + 1u;   // the next reverse_once uses the other mailbox half
+}
+
+// Sum of the per-rank partial bars (qbar|qdbar|xbar, core/dial_core.py:133-135) over NVLink peer
+// memory: push my partial into slot [rank] of every rank's bars mailbox, raise my flag there,
+// wait for all flags here, add the slots in rank order (bitwise identical on every rank).
+struct BarsXch {
+  float* mbox[DIAL_MAXRANK];        // bars mailbox of rank p: [2][DIAL_MAXRANK][nbar]
+  uint32_t* flags[DIAL_MAXRANK];    // bars flags of rank p:   [2][DIAL_MAXRANK]
+  uint32_t* seq;                    // local bars sequence number
+  uint32_t* err;
+  int world, rank, nbar;
+  const float* partial;             // local partial [nbar]
+  float* out[3];
+  int n0, n1;                       // nbar = n0 (q) + n1 (qd) + rest (x)
+};
+__global__ void __launch_bounds__(1024) bars_allreduce_kernel(const BarsXch B) {
+  const uint32_t seq = *B.seq, buf = seq & 1u;
+  const size_t half = (size_t)buf * DIAL_MAXRANK * B.nbar;
+  for (int p = 0; p < B.world; ++p) {
+    float* dst = B.mbox[p] + half + (size_t)B.rank * B.nbar;
+    for (int i = threadIdx.x; i < B.nbar; i += blockDim.x) dst[i] = B.partial[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int p = 0; p < B.world; ++p)
+      *reinterpret_cast<volatile uint32_t*>(B.flags[p] + buf * DIAL_MAXRANK + B.rank) = seq + 1u;
+  }
+  __syncthreads();
+  xch_wait_flags(B.flags[B.rank] + buf * DIAL_MAXRANK, seq + 1u, B.world, B.err);
+  const float* mine = B.mbox[B.rank] + half;
+  for (int i = threadIdx.x; i < B.nbar; i += blockDim.x) {
+    float s_ = 0.f;
+    for (int p = 0; p < B.world; ++p) s_ += __ldcg(mine + (size_t)p * B.nbar + i);
+    float* o = i < B.n0 ? B.out[0] + i : (i < B.n0 + B.n1 ? B.out[1] + (i - B.n0) : B.out[2] + (i - B.n0 - B.n1));
+    *o = s_;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *B.seq = seq + 1u;
 }
 
 // ---------------------------------------------------------------------------------
@@ -297,7 +375,39 @@ struct dial_plan {
   uint32_t* mpc_key = nullptr;  // sampling key of the current reverse_once
   struct MpcGraph { int n_diffuse, env_step, seen; cudaGraphExec_t exec; int64_t launches; };
   std::vector<MpcGraph> mpc_graphs;
+  // multi-GPU exchange over NVLink peer memory (dial_exchange_*): one cudaMalloc per rank, mapped
+  // into every peer with CUDA IPC.  Word offsets inside the block are the same on every rank.
+  struct Exchange {
+    bool on = false;
+    int rank = 0, world = 1, nbar = 0;
+    uint32_t* base[DIAL_MAXRANK] = {nullptr};   // base[rank] = own allocation, others = IPC mappings
+    size_t words = 0, o_mbox = 0, o_bars = 0, o_flags = 0, o_bflags = 0, o_local = 0;
+    float* bars_partial = nullptr;              // local staging of this rank's partial bars [nbar]
+    float* mbox(int p) const { return reinterpret_cast<float*>(base[p] + o_mbox); }
+    float* bars(int p) const { return reinterpret_cast<float*>(base[p] + o_bars); }
+    uint32_t* flags(int p) const { return base[p] + o_flags; }
+    uint32_t* bflags(int p) const { return base[p] + o_bflags; }
+    uint32_t* seq() const { return base[rank] + o_local; }
+    unsigned int* done() const { return base[rank] + o_local + 1; }
+    uint32_t* err() const { return base[rank] + o_local + 2; }
+    uint32_t* bseq() const { return base[rank] + o_local + 3; }
+  } xch;
 };
+
+static void fill_xch(const dial_plan* p, RolloutArgs& A) {
+  if (!p->xch.on) return;
+  A.xch_world = p->xch.world; A.xch_rank = p->xch.rank;
+  for (int r = 0; r < p->xch.world; ++r) { A.xch_mbox[r] = p->xch.mbox(r); A.xch_flags[r] = p->xch.flags(r); }
+  A.xch_seq = p->xch.seq(); A.xch_done = p->xch.done();
+}
+static XchWait xch_wait_args(const dial_plan* p, float* rews_copy) {
+  XchWait X; memset(&X, 0, sizeof(X));
+  if (p->xch.on) {
+    X.mbox = p->xch.mbox(p->xch.rank); X.flags = p->xch.flags(p->xch.rank); X.seq = p->xch.seq(); X.err = p->xch.err();
+    X.rews_copy = rews_copy; X.world = p->xch.world;
+  }
+  return X;
+}
 
 extern "C" int dial_abi_version(void) { return DIAL_ABI_VERSION; }
 extern "C" const char* dial_last_error(void) { return g_err.c_str(); }
@@ -453,6 +563,11 @@ extern "C" void dial_plan_destroy(dial_plan* p) {
   cudaFree(p->dM); cudaFree(p->dP);
   for (int b = 0; b < 2; ++b) { cudaFree(p->traj_q[b]); cudaFree(p->traj_qd[b]); cudaFree(p->traj_x[b]); }
   for (auto& g : p->mpc_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (int r = 0; r < DIAL_MAXRANK; ++r) {
+    if (!p->xch.base[r]) continue;
+    if (r == p->xch.rank) cudaFree(p->xch.base[r]); else cudaIpcCloseMemHandle(p->xch.base[r]);
+  }
+  cudaFree(p->xch.bars_partial);
   cudaFree(p->mpc_Msh); cudaFree(p->mpc_Y1); cudaFree(p->mpc_key);
   cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->tb_partial); cudaFree(p->counter); cudaFree(p->row_counter); cudaFree(p->zeros); cudaFree(p->dbg);
   delete p;
@@ -507,6 +622,7 @@ extern "C" int dial_reverse_rollout(dial_plan* p, const dial_state* s, const flo
   p->cur ^= 1;
   A.rews = rews_local; A.q = p->traj_q[p->cur]; A.qd = p->traj_qd[p->cur]; A.xpos = p->traj_x[p->cur];
   A.dbg = p->dbg;
+  fill_xch(p, A);   // sharded plans with a connected exchange: rewards go straight to every rank's mailbox
   CUDA_OK(launch_rollout_any(p, A, (cudaStream_t)stream));
   return 0;
 }
@@ -514,12 +630,23 @@ extern "C" int dial_reverse_rollout(dial_plan* p, const dial_state* s, const flo
 extern "C" int dial_reverse_update(dial_plan* p, const float* eps, const uint32_t key[2], const float* Ybar,
                                    const float* noise_scale, const float* rews_all, float* Ybar_out,
                                    float* weights, void* stream) {
-  if (!p || !Ybar || !noise_scale || !rews_all || !Ybar_out) return fail("dial_reverse_update: null argument");
+  return dial_reverse_update_x(p, eps, key, Ybar, noise_scale, rews_all, Ybar_out, weights, nullptr, stream);
+}
+
+extern "C" int dial_reverse_update_x(dial_plan* p, const float* eps, const uint32_t key[2], const float* Ybar,
+                                     const float* noise_scale, const float* rews_all, float* Ybar_out,
+                                     float* weights, float* rews_gathered, void* stream) {
+  if (!p || !Ybar || !noise_scale || !Ybar_out) return fail("dial_reverse_update: null argument");
+  if (!rews_all && !p->xch.on) return fail("dial_reverse_update: rews_all may be NULL only with a connected exchange");
   if (!eps && !key) return fail("dial_reverse_update: need eps or key");
   const dial_plan_desc& c = p->hP.c;
   cudaStream_t st = (cudaStream_t)stream;
   float* w = weights ? weights : p->weights;
-  weights_kernel<<<1, 1024, 0, st>>>(rews_all, c.Ntotal + 1, c.temp_sample, w);
+  // rews_all == NULL: the rewards are in this rank's mailbox (written by every rank's rollout
+  // epilogue over NVLink); the kernel waits for the flags, and rews_gathered gets a compact copy
+  XchWait X = xch_wait_args(p, rews_gathered);
+  if (rews_all) X.mbox = nullptr;
+  weights_kernel<<<1, 1024, 0, st>>>(rews_all, c.Ntotal + 1, c.temp_sample, w, X);
   p->launches++;
   CUDA_OK(cudaGetLastError());
   ybar_kernel<<<p->ybar_grid, YBAR_THREADS, 0, st>>>(w, eps, key ? key[0] : 0u, key ? key[1] : 0u, Ybar, noise_scale,
@@ -542,6 +669,10 @@ extern "C" int dial_reverse_trajbar(dial_plan* p, const float* weights, int rank
   TrajArgs T;
   T.traj[0] = p->traj_q[p->cur]; T.traj[1] = p->traj_qd[p->cur]; T.traj[2] = p->traj_x[p->cur];
   T.out[0] = qbar; T.out[1] = qdbar; T.out[2] = xbar;
+  const bool xsum = p->xch.on && qbar && qdbar && xbar;   // sum over ranks on the device (peer memory)
+  if (xsum) {
+    T.out[0] = p->xch.bars_partial; T.out[1] = T.out[0] + (size_t)H * m.nq; T.out[2] = T.out[1] + (size_t)H * m.nv;
+  }
   T.ncol[0] = m.nq; T.ncol[1] = m.nv; T.ncol[2] = 3 * (m.nbody - 1);
   T.coloff[0] = 0; T.coloff[1] = m.nq; T.coloff[2] = m.nq + m.nv;
   T.coltot = m.nq + m.nv + 3 * (m.nbody - 1);
@@ -553,6 +684,71 @@ extern "C" int dial_reverse_trajbar(dial_plan* p, const float* weights, int rank
   trajbar_final_kernel<<<H, 128, 0, st>>>(T);
   p->launches++;
   CUDA_OK(cudaGetLastError());
+  if (xsum) {
+    BarsXch Bx; memset(&Bx, 0, sizeof(Bx));
+    for (int r = 0; r < p->xch.world; ++r) { Bx.mbox[r] = p->xch.bars(r); Bx.flags[r] = p->xch.bflags(r); }
+    Bx.seq = p->xch.bseq(); Bx.err = p->xch.err(); Bx.world = p->xch.world; Bx.rank = p->xch.rank; Bx.nbar = p->xch.nbar;
+    Bx.partial = p->xch.bars_partial; Bx.out[0] = qbar; Bx.out[1] = qdbar; Bx.out[2] = xbar;
+    Bx.n0 = H * m.nq; Bx.n1 = H * m.nv;
+    bars_allreduce_kernel<<<1, 1024, 0, st>>>(Bx);
+    p->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ---- multi-GPU exchange over NVLink peer memory -------------------------------------------------
+extern "C" int dial_exchange_create(dial_plan* p, int rank, int world, unsigned char handle_out[DIAL_IPC_HANDLE_BYTES]) {
+  if (!p || !handle_out) return fail("dial_exchange_create: null argument");
+  if (world < 2 || world > DIAL_MAXRANK || rank < 0 || rank >= world) return fail("dial_exchange_create: need 2 <= world <= DIAL_MAXRANK");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= DIAL_IPC_HANDLE_BYTES, "IPC handle does not fit");
+  const dial_plan_desc& c = p->hP.c;
+  const dial_model_desc& m = p->hM.m;
+  if (c.Ntotal != c.Nsample * world || c.shard_offset != rank * c.Nsample) return fail("dial_exchange_create: plan shard does not match rank/world");
+  if (p->xch.base[p->xch.rank]) return fail("dial_exchange_create: already created");
+  dial_plan::Exchange& x = p->xch;
+  x.rank = rank; x.world = world;
+  x.nbar = (c.Hsample + 1) * (m.nq + m.nv + 3 * (m.nbody - 1));
+  auto up = [](size_t n) { return (n + 31) & ~(size_t)31; };
+  size_t o = 0;
+  x.o_mbox = o; o += up(2 * ((size_t)c.Ntotal + 1));
+  x.o_bars = o; o += up(2 * (size_t)DIAL_MAXRANK * x.nbar);
+  x.o_flags = o; o += up(2 * DIAL_MAXRANK);
+  x.o_bflags = o; o += up(2 * DIAL_MAXRANK);
+  x.o_local = o; o += 32;
+  x.words = o;
+  void* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, x.words * sizeof(uint32_t)));
+  CUDA_OK(cudaMemset(d, 0, x.words * sizeof(uint32_t)));
+  x.base[rank] = reinterpret_cast<uint32_t*>(d);
+  CUDA_OK(cudaMalloc(&x.bars_partial, (size_t)x.nbar * sizeof(float)));
+  cudaIpcMemHandle_t h;
+  CUDA_OK(cudaIpcGetMemHandle(&h, d));
+  memset(handle_out, 0, DIAL_IPC_HANDLE_BYTES);
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+extern "C" int dial_exchange_connect(dial_plan* p, const unsigned char* handles) {
+  if (!p || !handles) return fail("dial_exchange_connect: null argument");
+  dial_plan::Exchange& x = p->xch;
+  if (!x.base[x.rank]) return fail("dial_exchange_connect: call dial_exchange_create first");
+  for (int r = 0; r < x.world; ++r) {
+    if (r == x.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * DIAL_IPC_HANDLE_BYTES, sizeof(h));
+    void* d = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess));
+    x.base[r] = reinterpret_cast<uint32_t*>(d);
+  }
+  x.on = true;
+  return 0;
+}
+
+extern "C" int dial_exchange_status(dial_plan* p, uint32_t out[4]) {
+  if (!p || !out) return fail("dial_exchange_status: null argument");
+  if (!p->xch.on) { out[0] = out[1] = out[2] = out[3] = 0; return 0; }
+  CUDA_OK(cudaMemcpy(out, p->xch.base[p->xch.rank] + p->xch.o_local, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -575,7 +771,9 @@ extern "C" int dial_mpc_bind(dial_plan* p, const dial_mpc_buffers* b, const floa
       !b->rews || !b->noise)
     return fail("dial_mpc_bind: only qbar/qdbar/xbar may be null");
   const dial_plan_desc& c = p->hP.c;
-  if (c.Ntotal != c.Nsample) return fail("dial_mpc_bind: the device-resident loop is single-GPU (sharded plans use reverse_once)");
+  if (c.Ntotal != c.Nsample && !p->xch.on)
+    return fail("dial_mpc_bind: a sharded plan needs a connected exchange (dial_exchange_create / dial_exchange_connect) for the device-resident loop");
+  if (c.Ntotal != c.Nsample && !b->rews_all) return fail("dial_mpc_bind: sharded plans need rews_all [Ntotal+1]");
   const int n1 = c.Hnode + 1, nu = p->hM.m.nu;
   for (auto& g : p->mpc_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   p->mpc_graphs.clear();
@@ -622,8 +820,12 @@ static int mpc_enqueue(dial_plan* p, int n_diffuse, int env_step, cudaStream_t s
     p->cur ^= 1;
     A.rews = B.rews; A.q = p->traj_q[p->cur]; A.qd = p->traj_qd[p->cur]; A.xpos = p->traj_x[p->cur];
     A.dbg = p->dbg;
+    fill_xch(p, A);
     CUDA_OK(launch_rollout_any(p, A, st));
-    weights_kernel<<<1, 1024, 0, st>>>(B.rews, c.Ntotal + 1, c.temp_sample, p->weights);
+    {
+      XchWait X = xch_wait_args(p, B.rews_all);
+      weights_kernel<<<1, 1024, 0, st>>>(B.rews, c.Ntotal + 1, c.temp_sample, p->weights, X);
+    }
     p->launches++;
     CUDA_OK(cudaGetLastError());
     ybar_kernel<<<p->ybar_grid, YBAR_THREADS, 0, st>>>(p->weights, nullptr, 0u, 0u, Y[cur], noise, c.Ntotal, n1, nu,
@@ -635,7 +837,7 @@ static int mpc_enqueue(dial_plan* p, int n_diffuse, int env_step, cudaStream_t s
   if (cur != 0) CUDA_OK(cudaMemcpyAsync(Y[0], Y[1], (size_t)n1 * nu * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // the info-only bars of the LAST reverse_once (the one the reference's scan returns)
   if (n_diffuse > 0 && B.qbar && B.qdbar && B.xbar) {
-    int rc = dial_reverse_trajbar(p, nullptr, 0, B.qbar, B.qdbar, B.xbar, (void*)st);
+    int rc = dial_reverse_trajbar(p, nullptr, p->xch.on ? p->xch.rank : 0, B.qbar, B.qdbar, B.xbar, (void*)st);
     if (rc) return rc;
   }
   return 0;
@@ -708,6 +910,54 @@ extern "C" const char* dial_custom_reward_id(void) {
 #else
   return "";
 #endif
+}
+
+// ---- in-run fp32 peak (roofline denominator): independent FFMA chains at full occupancy ------
+__global__ void __launch_bounds__(1024) fp32_peak_kernel(float* out, int iters, float a, float b) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], a, b);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == 123.456f) out[0] = s;   // never true: keeps the chains alive
+}
+
+extern "C" int dial_fp32_peak(int iters, float* tflops_out) {
+  if (!tflops_out || iters < 1) return fail("dial_fp32_peak: bad argument");
+  int dev = 0, sms = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  float* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, sizeof(float)));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  const int grid = sms * 2;
+  fp32_peak_kernel<<<grid, 1024>>>(d, 64, 0.999f, 1e-3f);   // warm-up
+  float best = 0.f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    fp32_peak_kernel<<<grid, 1024>>>(d, iters, 0.999f, 1e-3f);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { cudaFree(d); return fail(std::string("fp32 peak kernel: ") + cudaGetErrorString(e)); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * 8 * 16 * (double)iters * 1024.0 * grid;
+    const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+    best = tf > best ? tf : best;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops_out = best;
+  return 0;
 }
 
 extern "C" int64_t dial_launch_count(const dial_plan* p) { return p ? p->launches : 0; }

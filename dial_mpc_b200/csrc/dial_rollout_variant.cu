@@ -89,11 +89,29 @@ __global__ void __launch_bounds__(512, 1) rollout_kernel(const DevModel* __restr
     }
   }
   int row = blockIdx.x * wpc + warp;
+  bool active = true;
   if (row >= A.nrows) {
-    if (!A.lockstep) return;
+    active = A.lockstep != 0;
     row = A.nrows - 1;  // lock-step CTAs need every warp at the barriers: duplicate the last row (benign)
   }
-  rollout_warp<NL, NR>(sM, sP, slab, A, row, lane);
+  if (active) rollout_warp<NL, NR>(sM, sP, slab, A, row, lane);
+  if (A.xch_world > 1) {
+    // reward exchange epilogue: the rows of this CTA are in every rank's mailbox (peer stores over
+    // NVLink); the last CTA of the grid publishes them by raising this rank's flag everywhere
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const unsigned int old = atomicAdd(A.xch_done, 1u);
+      if (old == gridDim.x - 1) {
+        __threadfence_system();
+        const uint32_t seq = *A.xch_seq, buf = seq & 1u;
+        for (int p = 0; p < A.xch_world; ++p)
+          *reinterpret_cast<volatile uint32_t*>(A.xch_flags[p] + buf * DIAL_MAXRANK + A.xch_rank) = seq + 1u;
+        *A.xch_done = 0u;
+        __threadfence_system();
+      }
+    }
+  }
 }
 
 #define DIAL_CAT2(a, b) a##b

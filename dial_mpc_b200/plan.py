@@ -49,6 +49,7 @@ class Plan:
         self.nq, self.nv, self.nu, self.nbody = m.nq, m.nv, m.nu, m.nbody
         self.N, self.Ntotal = desc.Nsample, desc.Ntotal
         self.Hs, self.Hn = desc.Hsample, desc.Hnode
+        self.exchange_on = False
 
     def _check(self, rc: int) -> None:
         if rc != 0:
@@ -124,9 +125,35 @@ class Plan:
         self._check(self.lib.dial_reverse_rollout(self.handle, C.byref(s), _ptr(eps), _key(key), _ptr(Ybar),
                                                   _ptr(noise_scale), _ptr(rews_local), _stream()))
 
-    def reverse_update(self, eps, key, Ybar, noise_scale, rews_all, Ybar_out, weights=None):
-        self._check(self.lib.dial_reverse_update(self.handle, _ptr(eps), _key(key), _ptr(Ybar), _ptr(noise_scale),
-                                                 _ptr(rews_all), _ptr(Ybar_out), _ptr(weights), _stream()))
+    def reverse_update(self, eps, key, Ybar, noise_scale, rews_all, Ybar_out, weights=None, rews_gathered=None):
+        """``rews_all=None``: the rewards come from this rank's exchange mailbox (sharded plans with a
+        connected exchange); ``rews_gathered`` then receives a compact copy of all Ntotal+1 rewards."""
+        self._check(self.lib.dial_reverse_update_x(self.handle, _ptr(eps), _key(key), _ptr(Ybar), _ptr(noise_scale),
+                                                   _ptr(rews_all), _ptr(Ybar_out), _ptr(weights), _ptr(rews_gathered),
+                                                   _stream()))
+
+    # -- multi-GPU exchange over NVLink peer memory (include/dial_b200.h: dial_exchange_*) -------------
+    def exchange_setup(self, rank: int, world: int, group=None) -> None:
+        """Create this rank's mailbox, all-gather the CUDA IPC handles over ``torch.distributed`` and
+        map the peers' mailboxes.  Raises if peer memory cannot be mapped (the caller then keeps NCCL)."""
+        import torch.distributed as dist
+        nb = _capi.DEFINES["DIAL_IPC_HANDLE_BYTES"]
+        h = (C.c_ubyte * nb)()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.dial_exchange_create(self.handle, int(rank), int(world), h))
+            mine = torch.tensor(list(bytes(h)), dtype=torch.uint8, device=self.device)
+            allh = torch.empty(world * nb, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            buf = (C.c_ubyte * (world * nb)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
+            self._check(self.lib.dial_exchange_connect(self.handle, buf))
+            torch.cuda.synchronize()
+            dist.barrier(group=group)      # every rank has mapped every mailbox before anyone writes
+        self.exchange_on = True
+
+    def exchange_status(self) -> dict:
+        out = (C.c_uint32 * 4)()
+        self._check(self.lib.dial_exchange_status(self.handle, out))
+        return dict(seq=int(out[0]), done=int(out[1]), error=int(out[2]), bars_seq=int(out[3]))
 
     def reverse_trajbar(self, weights, rank, qbar, qdbar, xbar):
         self._check(self.lib.dial_reverse_trajbar(self.handle, _ptr(weights), int(rank), _ptr(qbar), _ptr(qdbar),

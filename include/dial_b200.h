@@ -41,6 +41,8 @@ extern "C" {
 #define DIAL_MAXH 64   /* Hsample+1                     */
 #define DIAL_MAXSTAGE 8
 #define DIAL_MAXUSER 64 /* user constants of a custom reward */
+#define DIAL_MAXRANK 8  /* GPUs of one NVLink domain sharing the samples */
+#define DIAL_IPC_HANDLE_BYTES 64
 
 /* environments (reward functors fused into the rollout kernel) */
 enum {
@@ -190,6 +192,13 @@ int dial_reverse_update(dial_plan* plan, const float* eps, const uint32_t key[2]
                         const float* Ybar, const float* noise_scale, const float* rews_all,
                         float* Ybar_out, float* weights, void* stream);
 
+/* dial_reverse_update with the rewards taken from this rank's exchange mailbox when
+ * rews_all == NULL (see dial_exchange_*); rews_gathered (nullable) [dev][Ntotal+1] receives a
+ * compact copy of the gathered rewards (the `rews` of the reference's info dict). */
+int dial_reverse_update_x(dial_plan* plan, const float* eps, const uint32_t key[2],
+                          const float* Ybar, const float* noise_scale, const float* rews_all,
+                          float* Ybar_out, float* weights, float* rews_gathered, void* stream);
+
 /* qbar/qdbar/xbar (core/dial_core.py:133-135): weighted sums of this rank's stored
  * trajectories with `weights` [dev][Ntotal+1]; sharded runs sum the outputs across
  * ranks (the mean sample is counted on rank 0 only).  Outputs [dev]:
@@ -202,6 +211,25 @@ int dial_reverse_trajbar(dial_plan* plan, const float* weights, int rank,
  * into caller buffers q [Nsample+1,Hs+1,nq], qd [..,nv], xpos [..,nbody-1,3] (each nullable). */
 int dial_reverse_trajectories(dial_plan* plan, float* q, float* qd, float* xpos, void* stream);
 
+/* ---- Multi-GPU reward exchange over NVLink peer memory (one process per GPU) -----------------
+ * The reference is single-device; sharding the samples needs ONE exchange per reverse_once: all
+ * ranks need all Ntotal rewards for std / softmax (core/dial_core.py:125-128).  Instead of a host-
+ * issued collective the exchange is fused into the kernels on either side of it: the epilogue of
+ * the rollout kernel stores each finished row's reward straight into the mailbox of EVERY rank
+ * (peer stores through NVSwitch) and its last CTA raises a flag per rank; the weights kernel
+ * spins on the W flags of its own mailbox (bounded), then reads the rewards locally.  The
+ * info-only bars are summed the same way (push partial, flag, wait, add in rank order).  No host
+ * round trip, no extra launch: a sharded control step is graph-capturable (dial_mpc_step).
+ *   1. every rank: dial_exchange_create(plan, rank, world, handle)   -> 64-byte CUDA IPC handle
+ *   2. all-gather the handles with any host transport (torch.distributed, MPI, a file)
+ *   3. every rank: dial_exchange_connect(plan, handles[world][64])
+ * From then on dial_reverse_rollout publishes, dial_reverse_update(_x) with rews_all == NULL
+ * consumes, dial_reverse_trajbar returns the all-rank sums.  dial_exchange_status reads
+ * {sequence, CTAs done, error (1 = a wait timed out after ~4 s), bars sequence}. */
+int dial_exchange_create(dial_plan* plan, int rank, int world, unsigned char handle_out[DIAL_IPC_HANDLE_BYTES]);
+int dial_exchange_connect(dial_plan* plan, const unsigned char* handles);
+int dial_exchange_status(dial_plan* plan, uint32_t out[4]);
+
 /* ---- Device-resident synchronous MPC loop -------------------------------------------------
  * The reference's main loop (core/dial_core.py:242-268) is, per control step,
  *     state = step_env(state, Y0[0]); Y0 = shift(Y0);
@@ -211,7 +239,8 @@ int dial_reverse_trajectories(dial_plan* plan, float* q, float* qd, float* xpos,
  * splitting / shift / counter bookkeeping between kernels runs as tiny glue kernels, and
  * `dial_mpc_step` only replays the graph (captured on the second use of an
  * (n_diffuse, env_step) shape; the first use runs eagerly).  Results equal the eager
- * `dial_env_step` + `dial_reverse_*` sequence.  Single-GPU plans only (Ntotal == Nsample). */
+ * `dial_env_step` + `dial_reverse_*` sequence.  Sharded plans (Ntotal > Nsample) need a connected
+ * exchange: every rank replays the same graph, the env step runs redundantly on every rank. */
 typedef struct dial_mpc_buffers { /* all [dev], caller-owned, fixed while bound */
   float* qpos;            /* [nq]  state, advanced in place by the env step                  */
   float* qvel;            /* [nv]                                                            */
@@ -221,7 +250,8 @@ typedef struct dial_mpc_buffers { /* all [dev], caller-owned, fixed while bound 
   float* Y;               /* [Hn+1,nu] control knots, in/out                                 */
   float* ctrl;            /* [nu]  out: control applied by the env step                      */
   float* reward;          /* [1]   out: reward of the env step                               */
-  float* rews;            /* [Nsample+1] out: sample rewards of the last reverse_once        */
+  float* rews;            /* [Nsample+1] out: this rank's sample rewards of the last reverse_once */
+  float* rews_all;        /* [Ntotal+1]  out, sharded plans only (else NULL): all ranks' rewards  */
   float* qbar;            /* [Hs+1,nq]        nullable (all three or none): bars of the last  */
   float* qdbar;           /* [Hs+1,nv]        reverse_once                                    */
   float* xbar;            /* [Hs+1,nbody-1,3]                                                 */
@@ -253,6 +283,11 @@ int dial_solver_variant(const dial_model_desc* model);
 /* "" for the stock library; the identifier (-DDIAL_CUSTOM_REWARD_ID) of the reward source a
  * custom build was compiled with.  Only such a build accepts env_id == DIAL_ENV_CUSTOM. */
 const char* dial_custom_reward_id(void);
+
+/* Measured fp32 FFMA throughput of the current device in TFLOP/s (independent FMA chains at full
+ * occupancy, best of 3, CUDA events; synchronous): the roofline denominator bench.py reports the
+ * rollout kernel's flop rate against.  iters = loop trips of 128 FFMAs per thread. */
+int dial_fp32_peak(int iters, float* tflops_out);
 
 /* kernel launches issued by this plan since creation (bench bookkeeping) */
 int64_t dial_launch_count(const dial_plan* plan);

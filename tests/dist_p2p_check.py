@@ -1,0 +1,129 @@
+"""Worker of tests/test_gpu_multi.py (one process per GPU, launched by torch.distributed.run):
+the sharded planner with the peer-memory exchange against (a) the same plan over NCCL and (b)
+the unsharded single-GPU plan, and the sharded CUDA-graph control step against the eager one."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from baseline_configs import product_env
+    from dial_mpc_b200 import random as drandom
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import DeviceLoop, MBDPI
+    name = "unitree_go2_seq_jump"
+    env = product_env(name)
+    N, Hs, Hn = 256 * world, 12, 4
+    cfg = DialConfig(env_name=name, Nsample=N, Hsample=Hs, Hnode=Hn, Ndiffuse=3, Ndiffuse_init=4, temp_sample=0.05,
+                     horizon_diffuse_factor=0.9, traj_diffuse_factor=0.5)
+    res = {}
+    mb = MBDPI(cfg, env, rank=rank, world_size=world)
+    assert mb.xch, f"peer exchange not available: {mb.xch_error}"
+    os.environ["DIAL_EXCHANGE"] = "nccl"
+    mb_nccl = MBDPI(cfg, env, rank=rank, world_size=world)
+    del os.environ["DIAL_EXCHANGE"]
+    assert not mb_nccl.xch
+    st = env.reset(drandom.PRNGKey(0))
+    st.info["step"] = 47
+    rng = drandom.PRNGKey(3)
+    Y = torch.zeros(Hn + 1, mb.nu, device=mb.device)
+    fac = mb.schedule(3)
+    # (a) three annealing iterations: exchange == NCCL, bit for bit (same kernels, same rewards)
+    r1, Y1, i1 = mb.reverse_scan(st, rng, Y, fac)
+    r2, Y2, i2 = mb_nccl.reverse_scan(st, rng, Y, fac)
+    torch.cuda.synchronize()
+    res["xch_eq_nccl_rews"] = bool(torch.equal(i1["rews"], i2["rews"]))
+    res["xch_eq_nccl_Y"] = bool(torch.equal(Y1, Y2))
+    res["xch_vs_nccl_xbar"] = float((i1["xbar"] - i2["xbar"]).abs().max())
+    # every rank holds the same result
+    ys = [torch.empty_like(Y1) for _ in range(world)]
+    dist.all_gather(ys, Y1)
+    res["ranks_agree_Y"] = bool(all(torch.equal(ys[0], y) for y in ys))
+    xs = [torch.empty_like(i1["xbar"]) for _ in range(world)]
+    dist.all_gather(xs, i1["xbar"].contiguous())
+    res["ranks_agree_xbar"] = bool(all(torch.equal(xs[0], x) for x in xs))
+    # (b) against the unsharded plan on one GPU
+    if rank == 0:
+        one = MBDPI(cfg, env)
+        _, Y3, i3 = one.reverse_scan(st, rng, Y, fac)
+        torch.cuda.synchronize()
+        res["sharded_vs_single_rews"] = float((i1["rews"] - i3["rews"]).abs().max())
+        res["sharded_vs_single_Y"] = float((Y1 - Y3).abs().max())
+        res["sharded_vs_single_xbar"] = float((i1["xbar"] - i3["xbar"]).abs().max())
+    dist.barrier()
+    # (c) the sharded control step as ONE CUDA graph per rank == eager env.step + shift + reverse_scan
+    loop = DeviceLoop(mb, st, rng, Y)
+    s_e, Y_e, r_e = st, Y, rng
+    worst = 0.0
+    for t in range(5):               # step 0 eager (Ndiffuse_init), 1 eager, 2.. graph replays
+        nd = cfg.Ndiffuse_init if t == 0 else cfg.Ndiffuse
+        s_e = env.step(s_e, Y_e[0])
+        Y_e = mb_nccl.shift(Y_e)
+        r_e, Y_e, info_e = mb_nccl.reverse_scan(s_e, r_e, Y_e, mb_nccl.schedule(nd))
+        loop.step(nd)
+        torch.cuda.synchronize()
+        worst = max(worst, float((loop.Y - Y_e).abs().max()))
+        worst_r = float((loop.info()["rews"] - info_e["rews"]).abs().max())
+        worst = max(worst, worst_r / (1 + float(info_e["rews"].abs().max())))
+    res["graph_vs_eager"] = worst
+    s2 = loop.state()
+    res["graph_step"] = int(s2.info["step"])
+    res["graph_rng_equal"] = bool(np.array_equal(np.asarray(r_e, dtype=np.uint32), s2.info["rng"]))
+    stt = mb.plan.exchange_status()
+    res["exchange_error"] = stt["error"]
+    res["exchange_seq"] = stt["seq"]
+    # timing: one reverse_once, exchange vs NCCL (CUDA events, max over ranks), Go2 seq-jump 2048/GPU
+    cfgb = DialConfig(env_name=name, Nsample=2048 * world, Hsample=25, Hnode=5, Ndiffuse=4, temp_sample=0.05)
+    tm = {}
+    for label, envv in (("p2p", None), ("nccl", "nccl")):
+        if envv:
+            os.environ["DIAL_EXCHANGE"] = envv
+        m2 = MBDPI(cfgb, env, rank=rank, world_size=world)
+        os.environ.pop("DIAL_EXCHANGE", None)
+        Yb = torch.zeros(6, mb.nu, device=mb.device)
+        f4 = m2.schedule(4)
+        rr = drandom.PRNGKey(0)
+        for _ in range(3):
+            rr, Yb2, _ = m2.reverse_scan(st, rr, Yb, f4)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            rr, Yb2, _ = m2.reverse_scan(st, rr, Yb, f4)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 20], device=mb.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tm[label + "_ms_per_scan"] = float(t.item())
+        if label == "p2p":
+            lp = DeviceLoop(m2, st, drandom.PRNGKey(0), Yb)
+            for _ in range(4):
+                lp.step(4)
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                lp.step(4)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / 20], device=mb.device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tm["p2p_graph_ms_per_step"] = float(t.item())
+        del m2
+    res.update(tm)
+    if rank == 0:
+        print("P2PCHECK " + json.dumps(res))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

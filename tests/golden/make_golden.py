@@ -42,11 +42,13 @@ def main():
         pl = PlannerOracle(env, N, Hs, Hn, 0.05, 0.9 if "go2" in name else 1.0, 0.5)
         Ybar0 = np.clip(rng.standard_normal((Hn + 1, env.nu)) * 0.2 + (hold if name == "allegro_reorient" else 0.0), -1, 1).astype(np.float32).astype(np.float64)
         Ybar, info = pl.reverse_once(s, eps, Ybar0, pl.sigma_control)
-        # the oracle's own sensitivity to fp32-sized input noise (1e-6 on the actions): the yardstick
+        # the oracle's own sensitivity to fp32-sized input noise (max over three re-runs with 1e-5 noise on the actions): the yardstick
         # for chaotic rows in the GPU parity tests (tests/test_gpu_at_size.py)
         prng = np.random.default_rng(7)
-        rp = env.rollout(s, info["us"] + 1e-6 * prng.standard_normal(info["us"].shape))[0]
-        rews_sens = np.abs(rp.mean(-1) - info["rews"])
+        rews_sens = np.zeros_like(info["rews"])
+        for _ in range(3):
+            rp = env.rollout(s, info["us"] + 1e-5 * prng.standard_normal(info["us"].shape))[0]
+            rews_sens = np.maximum(rews_sens, np.abs(rp.mean(-1) - info["rews"]))
         np.savez_compressed(
             os.path.join(OUT, f"{name}.npz"),
             qpos=s.qpos[0], qvel=s.qvel[0], qacc_warmstart=s.qacc_warmstart[0], step=int(s.step[0]),

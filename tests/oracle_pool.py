@@ -47,3 +47,33 @@ def oracle_rollout(name, cfg, qpos, qvel, warm, step, stage, us, procs=None):
             else:
                 os.environ[k] = v
     return tuple(np.concatenate([p[i] for p in parts], 0) for i in range(4))
+
+
+def oracle_with_yardstick(name, cfg, qpos, qvel, warm, step, stage, us, rng, K=3, scale=1e-5, procs=None):
+    """Nominal oracle rollout of `us` plus the oracle's own sensitivity to fp32-sized noise, per
+    output element: the max over K re-runs with the actions perturbed by `scale`*N(0,1) and — for
+    the tree models, which the C port covers — the fp32 build of the C port against the fp64
+    oracle (the oracle's own fp32-vs-fp64 divergence).  Returns (nominal 4-tuple, sens 4-tuple)."""
+    us = np.asarray(us, dtype=np.float64)
+    n = us.shape[0]
+    stack = np.concatenate([us] + [us + scale * rng.standard_normal(us.shape) for _ in range(K)], 0)
+    out = oracle_rollout(name, cfg, qpos, qvel, warm, step, stage, stack, procs=procs)
+    nom = tuple(a[:n] for a in out)
+    sens = [np.zeros_like(a) for a in nom]
+    for k in range(K):
+        for i in range(4):
+            sens[i] = np.maximum(sens[i], np.abs(out[i][(k + 1) * n:(k + 2) * n] - nom[i]))
+    try:
+        from oracle import build_oracle
+        from oracle.c_port import CPort
+        from oracle.envs_oracle import OState, make_env
+        build_oracle.build()
+        o = make_env(name, cfg)
+        s = OState(np.asarray(qpos, dtype=np.float64)[None], np.asarray(qvel, dtype=np.float64)[None],
+                   np.asarray(warm, dtype=np.float64)[None], np.array([int(step)]), np.array([int(stage)]))
+        f32 = CPort(o, real="float").rollout(s, us)[:4]
+        for i in range(4):
+            sens[i] = np.maximum(sens[i], np.abs(f32[i] - nom[i]))
+    except NotImplementedError:
+        pass        # dense / elliptic model: perturbation yardstick only
+    return nom, tuple(sens)

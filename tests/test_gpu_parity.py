@@ -45,11 +45,14 @@ def test_rollout_matches_oracle(built, name, H):
         # ORACLE's own sensitivity to fp32-sized noise on the actions (per-substep parity from
         # identical states is in test_gpu_at_size.py::test_single_physics_step_qacc_parity)
         from tests.test_gpu_at_size import YARD
-        rewp, qp, _, _ = o.rollout(s, us + 1e-6 * rng.standard_normal(us.shape))
+        sq_, sr_ = np.zeros_like(q), np.zeros_like(rew)
+        for _ in range(3):      # yardstick: max over three re-runs with 1e-5 noise on the actions
+            rewp, qp, _, _ = o.rollout(s, us + 1e-5 * rng.standard_normal(us.shape))
+            sq_, sr_ = np.maximum(sq_, np.abs(qp - q)), np.maximum(sr_, np.abs(rewp - rew))
         eq = np.abs(qg.cpu().numpy() - q)
         er = np.abs(rg.cpu().numpy() - rew)
-        assert (eq <= 2e-4 + YARD * np.abs(qp - q)).all(), (eq.max(), np.abs(qp - q).max())
-        assert (er <= 2e-3 * (1 + np.abs(rew)) + YARD * np.abs(rewp - rew)).all(), (er.max(), np.abs(rewp - rew).max())
+        assert (eq <= 2e-4 + YARD * sq_).all(), (eq.max(), sq_.max())
+        assert (er <= 2e-3 * (1 + np.abs(rew)) + YARD * sr_).all(), (er.max(), sr_.max())
         assert eq[:, :3].max() < 2e-4 and (er[:, :3] / (1 + np.abs(rew[:, :3]))).max() < 2e-3   # before the first contact event
         assert np.isfinite(rg.cpu().numpy()).all()
         return
