@@ -238,10 +238,20 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
     Y = torch.zeros(cfg.Hnode + 1, mb.nu, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def mpc_step(Y, rng):
-        Y = mb.shift(Y)
-        rng, Y, info = mb.reverse_scan(state, rng, Y, factors)
-        return Y, rng, info
+    # The timed step goes through the public device-resident loop (DeviceLoop -> C ABI dial_mpc_step):
+    # shift + Ndiffuse x reverse_once replayed as ONE CUDA graph per rank, the bars of every
+    # iteration on a side branch.  Sharded runs without the peer-memory exchange (no CUDA IPC) fall
+    # back to the eager MBDPI.reverse_scan with NCCL collectives.
+    from dial_mpc_b200.core.dial_core import DeviceLoop
+    use_graph = world == 1 or mb.xch
+    loop = DeviceLoop(mb, state, rng, Y) if use_graph else None
+    carry = {"Y": Y, "rng": rng}
+
+    def mpc_step():
+        if use_graph:
+            loop.step(cfg.Ndiffuse, env_step=2)
+        else:
+            carry["rng"], carry["Y"], _ = mb.reverse_scan(state, carry["rng"], mb.shift(carry["Y"]), factors)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -250,7 +260,7 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
             torch.cuda.synchronize()
 
     for _ in range(max(warmup, 3)):
-        Y, rng, info = mpc_step(Y, rng)
+        mpc_step()
     sync_all()
     launches0 = mb.plan.launches
     evs = []
@@ -260,7 +270,7 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
         flush.zero_()                                   # L2 flush, outside the timed events
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        Y, rng, info = mpc_step(Y, rng)
+        mpc_step()
         e1.record()
         evs.append((e0, e1))
     sync_all()
@@ -275,7 +285,8 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
     units_per_step = cfg.Ndiffuse * Ntotal * cfg.Hsample
     value = units_per_step * steps / t_dev
 
-    # ---- e2e: public API with HOST buffers (pinned), H2D of the state + plan, D2H of the plan ----
+    # ---- e2e: the same public call with HOST buffers (pinned): H2D of the state + knots, D2H of the
+    # new knots and the plan's reward, every step, inside the timed region -------------------------------
     ps = state.pipeline_state
     h_q, h_v, h_w = (t.cpu().pin_memory() for t in (ps.qpos, ps.qvel, ps.qacc_warmstart))
     h_Y = torch.zeros(cfg.Hnode + 1, mb.nu).pin_memory()
@@ -284,22 +295,32 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
     h2d = sum(t.numel() * 4 for t in (h_q, h_v, h_w, h_Y))
     d2h = h_out.numel() * 4 + 4
 
-    def e2e_step(rng):
-        d_state = State(PipelineState(h_q.to(dev, non_blocking=True), h_v.to(dev, non_blocking=True),
-                                      h_w.to(dev, non_blocking=True)), None, 0.0, 0.0, {}, dict(state.info))
-        Yd = mb.shift(h_Y.to(dev, non_blocking=True))
-        rng, Yd, info = mb.reverse_scan(d_state, rng, Yd, factors)
-        h_out.copy_(Yd, non_blocking=True)
-        r = float(info["rews"][-1])                      # D2H read of the plan's reward (syncs)
+    def e2e_step():
+        if use_graph:
+            b = loop.buf
+            b["qpos"].copy_(h_q, non_blocking=True)
+            b["qvel"].copy_(h_v, non_blocking=True)
+            b["qacc_warmstart"].copy_(h_w, non_blocking=True)
+            b["Y"].copy_(h_Y, non_blocking=True)
+            loop.step(cfg.Ndiffuse, env_step=2)
+            h_out.copy_(b["Y"], non_blocking=True)
+            r = float(loop.info()["rews"][-1])           # D2H read of the plan's reward (syncs)
+        else:
+            d_state = State(PipelineState(h_q.to(dev, non_blocking=True), h_v.to(dev, non_blocking=True),
+                                          h_w.to(dev, non_blocking=True)), None, 0.0, 0.0, {}, dict(state.info))
+            Yd = mb.shift(h_Y.to(dev, non_blocking=True))
+            carry["rng"], Yd, info = mb.reverse_scan(d_state, carry["rng"], Yd, factors)
+            h_out.copy_(Yd, non_blocking=True)
+            r = float(info["rews"][-1])
         h_Y.copy_(h_out)
-        return rng, r
+        return r
 
     for _ in range(3):
-        rng, _ = e2e_step(rng)
+        e2e_step()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(steps):
-        rng, _ = e2e_step(rng)
+        e2e_step()
     sync_all()
     t_e2e = time.perf_counter() - t0
     if world > 1:
@@ -307,6 +328,7 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e_value = units_per_step * steps / t_e2e
+    rng = carry["rng"]
 
     # ---- per-phase device times of one reverse_once (CUDA events between the stages) ---------------
     phases = mb.phase_times(state, drandom.split(rng)[1], Y, factors[0], reps=10)
@@ -364,10 +386,11 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
                roofline=roofline, phases_us_per_reverse_once=phases, clocks=clocks,
                config=dict(workload=f"{b['name']} (BASELINE configs[{ci}])", Nsample_per_gpu=b["N"], Nsample_total=Ntotal,
                            Hsample=b["Hs"], Hnode=b["Hn"], Ndiffuse=b["Ndiffuse"], n_frames=nfr,
-                           step="shift + Ndiffuse x reverse_once (rollout, exchange, update, bars)",
+                           step=("shift + Ndiffuse x reverse_once (rollout, exchange, update, bars of every iteration) "
+                                 + ("as one CUDA graph per rank (DeviceLoop / dial_mpc_step)" if use_graph else "eager (MBDPI.reverse_scan)")),
                            rng="in-kernel Threefry-2x32", l2="256 MiB memset between steps (outside the timed events)",
                            parallelism=f"samples sharded over {world} GPU(s), {mb.exchange_name} of rewards per reverse_once"))
-    del mb, flush
+    del loop, mb, flush
     torch.cuda.empty_cache()
     return out
 

@@ -170,7 +170,8 @@ _LIBS: Dict[str, C.CDLL] = {}
 
 def lib(path: Optional[str] = None) -> C.CDLL:
     """The stock library (default) or a custom-reward build (``dial_mpc_b200.custom``)."""
-    path = os.path.abspath(path or LIB_PATH)
+    # DIAL_B200_LIB: an alternative build of the stock library (kernel experiments, A/B timing)
+    path = os.path.abspath(path or os.environ.get("DIAL_B200_LIB") or LIB_PATH)
     if path not in _LIBS:
         _LIBS[path] = _bind(path)
     return _LIBS[path]

@@ -307,8 +307,9 @@ class DeviceLoop:
         self.n_diffuse_max = nmax
         pl.mpc_bind(self.buf, mbdpi.M_shift.cpu().numpy())
 
-    def step(self, n_diffuse: Optional[int] = None, env_step: bool = True) -> None:
-        """One control step (asynchronous on the current stream)."""
+    def step(self, n_diffuse: Optional[int] = None, env_step=True) -> None:
+        """One control step (asynchronous on the current stream).  env_step: True = env step + shift
+        + plan (the reference's main loop), False = plan only, 2 = shift + plan (state untouched)."""
         n = self.mbdpi.args.Ndiffuse if n_diffuse is None else int(n_diffuse)
         if n > self.n_diffuse_max:
             raise ValueError("n_diffuse exceeds the bound noise schedule")

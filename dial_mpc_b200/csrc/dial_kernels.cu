@@ -359,6 +359,9 @@ struct dial_plan {
   float *traj_q[2] = {nullptr, nullptr}, *traj_qd[2] = {nullptr, nullptr}, *traj_x[2] = {nullptr, nullptr};
   int cur = 0;
   float* weights = nullptr;                                        // [Ntotal+1]
+  float* weights2 = nullptr;                                       // second buffer: the bars of iteration i overlap iteration i+1
+  cudaStream_t side = nullptr;                                     // bars branch of the control-step graph
+  cudaEvent_t ev_main[2] = {nullptr, nullptr}, ev_side[2] = {nullptr, nullptr};
   float* partial = nullptr;
   float* tb_partial = nullptr;
   unsigned int* counter = nullptr;
@@ -541,6 +544,12 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
     if ((e = cudaMalloc(&p->traj_x[b], rows * H * 3 * (m.nbody - 1) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(traj_x)");
   }
   if ((e = cudaMalloc(&p->weights, ((size_t)c.Ntotal + 1) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(weights)");
+  if ((e = cudaMalloc(&p->weights2, ((size_t)c.Ntotal + 1) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(weights2)");
+  if ((e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking)) != cudaSuccess) return bad(e, "cudaStreamCreate(side)");
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaEventCreateWithFlags(&p->ev_main[i], cudaEventDisableTiming)) != cudaSuccess) return bad(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&p->ev_side[i], cudaEventDisableTiming)) != cudaSuccess) return bad(e, "cudaEventCreate");
+  }
   const int ne = (c.Hnode + 1) * m.nu, slots = YBAR_THREADS / ne;
   int g = (c.Ntotal + 1 + slots - 1) / slots;
   p->ybar_grid = g < 1 ? 1 : (g > 296 ? 296 : g);
@@ -569,6 +578,9 @@ extern "C" void dial_plan_destroy(dial_plan* p) {
   }
   cudaFree(p->xch.bars_partial);
   cudaFree(p->mpc_Msh); cudaFree(p->mpc_Y1); cudaFree(p->mpc_key);
+  for (int i = 0; i < 2; ++i) { if (p->ev_main[i]) cudaEventDestroy(p->ev_main[i]); if (p->ev_side[i]) cudaEventDestroy(p->ev_side[i]); }
+  if (p->side) cudaStreamDestroy(p->side);
+  cudaFree(p->weights2);
   cudaFree(p->weights); cudaFree(p->partial); cudaFree(p->tb_partial); cudaFree(p->counter); cudaFree(p->row_counter); cudaFree(p->zeros); cudaFree(p->dbg);
   delete p;
 }
@@ -794,7 +806,7 @@ static int mpc_enqueue(dial_plan* p, int n_diffuse, int env_step, cudaStream_t s
   const int n1 = c.Hnode + 1, nu = p->hM.m.nu;
   float* Y[2] = {B.Y, p->mpc_Y1};
   int cur = 0;
-  if (env_step) {
+  if (env_step == 1) {
     // state = step_env(state, Y0[0])  (dial_core.py:245): in place, counters advanced by the kernel
     RolloutArgs A; memset(&A, 0, sizeof(A));
     A.qpos0 = B.qpos; A.qvel0 = B.qvel; A.warm0 = B.qacc_warmstart;
@@ -802,17 +814,26 @@ static int mpc_enqueue(dial_plan* p, int n_diffuse, int env_step, cudaStream_t s
     A.nrows = 1; A.H = 1; A.mode = 0; A.us = Y[cur]; A.rewss = B.reward;
     A.qpos_out = B.qpos; A.qvel_out = B.qvel; A.warm_out = B.qacc_warmstart; A.ctrl_out = B.ctrl;
     CUDA_OK(launch_rollout(p, A, 1, st));
+  }
+  if (env_step == 1 || env_step == 2) {
     // Y0 = shift(Y0)  (dial_core.py:252)
     mpc_shift_kernel<<<1, DIAL_MAXNODE * DIAL_MAXU, 0, st>>>(p->mpc_Msh, Y[cur], Y[cur ^ 1], n1, nu);
     p->launches++;
     CUDA_OK(cudaGetLastError());
     cur ^= 1;
   }
+  // The info-only bars (qbar, qdbar, xbar; dial_core.py:133-135) are computed for EVERY iteration,
+  // like the reference's scan does (the caller sees those of the last one), on a side branch of
+  // the graph: the bars of iteration i read trajectory buffer i&1 and weights buffer i&1 while
+  // iteration i+1 rolls into the other pair; iteration i+2 waits for them.
+  const bool bars = B.qbar && B.qdbar && B.xbar;
+  float* wts[2] = {p->weights, p->weights2};
   for (int i = 0; i < n_diffuse; ++i) {
     const float* noise = B.noise + (size_t)i * n1;
     mpc_split_kernel<<<1, 32, 0, st>>>(B.rng, p->mpc_key);
     p->launches++;
     CUDA_OK(cudaGetLastError());
+    if (bars && i >= 2) CUDA_OK(cudaStreamWaitEvent(st, p->ev_side[i & 1], 0));
     RolloutArgs A; memset(&A, 0, sizeof(A));
     A.qpos0 = B.qpos; A.qvel0 = B.qvel; A.warm0 = B.qacc_warmstart; A.counters_in = B.counters;
     A.nrows = c.Nsample + 1; A.H = c.Hsample + 1; A.mode = 1;
@@ -822,24 +843,33 @@ static int mpc_enqueue(dial_plan* p, int n_diffuse, int env_step, cudaStream_t s
     A.dbg = p->dbg;
     fill_xch(p, A);
     CUDA_OK(launch_rollout_any(p, A, st));
+    float* w = wts[i & 1];
     {
       XchWait X = xch_wait_args(p, B.rews_all);
-      weights_kernel<<<1, 1024, 0, st>>>(B.rews, c.Ntotal + 1, c.temp_sample, p->weights, X);
+      weights_kernel<<<1, 1024, 0, st>>>(B.rews, c.Ntotal + 1, c.temp_sample, w, X);
     }
     p->launches++;
     CUDA_OK(cudaGetLastError());
-    ybar_kernel<<<p->ybar_grid, YBAR_THREADS, 0, st>>>(p->weights, nullptr, 0u, 0u, Y[cur], noise, c.Ntotal, n1, nu,
+    ybar_kernel<<<p->ybar_grid, YBAR_THREADS, 0, st>>>(w, nullptr, 0u, 0u, Y[cur], noise, c.Ntotal, n1, nu,
                                                        p->partial, p->counter, Y[cur ^ 1], p->mpc_key);
     p->launches++;
     CUDA_OK(cudaGetLastError());
     cur ^= 1;
+    if (bars) {
+      CUDA_OK(cudaEventRecord(p->ev_main[i & 1], st));
+      CUDA_OK(cudaStreamWaitEvent(p->side, p->ev_main[i & 1], 0));
+      int rc = dial_reverse_trajbar(p, w, p->xch.on ? p->xch.rank : 0, B.qbar, B.qdbar, B.xbar, (void*)p->side);
+      if (rc) return rc;
+      CUDA_OK(cudaEventRecord(p->ev_side[i & 1], p->side));
+    }
   }
   if (cur != 0) CUDA_OK(cudaMemcpyAsync(Y[0], Y[1], (size_t)n1 * nu * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  // the info-only bars of the LAST reverse_once (the one the reference's scan returns)
-  if (n_diffuse > 0 && B.qbar && B.qdbar && B.xbar) {
-    int rc = dial_reverse_trajbar(p, nullptr, p->xch.on ? p->xch.rank : 0, B.qbar, B.qdbar, B.xbar, (void*)st);
-    if (rc) return rc;
+  if (bars && n_diffuse > 0) {   // join the bars branch (both outstanding iterations)
+    if (n_diffuse >= 2) CUDA_OK(cudaStreamWaitEvent(st, p->ev_side[(n_diffuse - 2) & 1], 0));
+    CUDA_OK(cudaStreamWaitEvent(st, p->ev_side[(n_diffuse - 1) & 1], 0));
   }
+  if (n_diffuse > 0 && wts[(n_diffuse - 1) & 1] != p->weights)   // p->weights always holds the last iteration's weights
+    CUDA_OK(cudaMemcpyAsync(p->weights, p->weights2, ((size_t)c.Ntotal + 1) * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -847,6 +877,7 @@ extern "C" int dial_mpc_step(dial_plan* p, int n_diffuse, int env_step, void* st
   if (!p) return fail("dial_mpc_step: null plan");
   if (!p->mpc_bound) return fail("dial_mpc_step: call dial_mpc_bind first");
   if (n_diffuse < 0 || n_diffuse > 64) return fail("dial_mpc_step: n_diffuse out of range");
+  if (env_step < 0 || env_step > 2) return fail("dial_mpc_step: env_step must be 0 (plan only), 1 (env step + shift) or 2 (shift only)");
   cudaStream_t st = (cudaStream_t)stream;
   dial_plan::MpcGraph* g = nullptr;
   for (auto& e : p->mpc_graphs) if (e.n_diffuse == n_diffuse && e.env_step == env_step) g = &e;

@@ -184,5 +184,6 @@ class Plan:
         self._mpc_keep = (dict(bufs), b, M)
         self._check(self.lib.dial_mpc_bind(self.handle, C.byref(b), M.ctypes.data_as(C.c_void_p)))
 
-    def mpc_step(self, n_diffuse: int, env_step: bool = True) -> None:
-        self._check(self.lib.dial_mpc_step(self.handle, int(n_diffuse), int(bool(env_step)), _stream()))
+    def mpc_step(self, n_diffuse: int, env_step=True) -> None:
+        """env_step: True / 1 env step + shift, False / 0 plan only, 2 shift + plan (state untouched)."""
+        self._check(self.lib.dial_mpc_step(self.handle, int(n_diffuse), int(env_step), _stream()))

@@ -262,9 +262,11 @@ typedef struct dial_mpc_buffers { /* all [dev], caller-owned, fixed while bound 
  * (MBDPI.shift, core/dial_core.py:160-165).  Drops previously captured graphs. */
 int dial_mpc_bind(dial_plan* plan, const dial_mpc_buffers* buffers, const float* M_shift);
 
-/* One control step on `stream`: [env_step: state <- env.step(state, Y[0]); Y <- shift(Y)] then
- * n_diffuse x reverse_once with noise rows 0..n_diffuse-1.  env_step = 0 plans from the bound
- * state as it is (deploy/dial_plan.py: the state comes from the robot). */
+/* One control step on `stream`: [env_step == 1: state <- env.step(state, Y[0])], [env_step == 1
+ * or 2: Y <- shift(Y)], then n_diffuse x reverse_once with noise rows 0..n_diffuse-1.
+ * env_step = 0 plans from the bound state as it is (deploy/dial_plan.py: the state comes from
+ * the robot); env_step = 2 shifts and plans without advancing the state (a planner whose state
+ * is written by somebody else once per control period). */
 int dial_mpc_step(dial_plan* plan, int n_diffuse, int env_step, void* stream);
 
 /* jax.random.split(rng) / the planner's key threading (core/dial_core.py:106,145):

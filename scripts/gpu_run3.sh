@@ -1,0 +1,11 @@
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/tests3.log 2>&1
+tail -25 gpurun_out/tests3.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench3.json 2> gpurun_out/bench3.err
+tail -c 600 gpurun_out/bench3.err
+M=smsp__sass_thread_inst_executed_op_fadd_pred_on.sum,smsp__sass_thread_inst_executed_op_fmul_pred_on.sum,smsp__sass_thread_inst_executed_op_ffma_pred_on.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum
+for c in 0 1 2 3 4; do
+  ncu --metrics $M --clock-control none -k regex:rollout_kernel --launch-skip 11 -c 1 --csv --log-file gpurun_out/counts_cfg$c.csv python scripts/prof_cfg.py $c 2 > gpurun_out/counts_cfg$c.log 2>&1
+done
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench3_ref.json 2> gpurun_out/bench3_ref.err
