@@ -51,8 +51,12 @@ def usable_cores() -> int:
 # Both roll ONE reverse_once of the chosen config: its Nsample+1 rows are split over the worker
 # processes (pinned, one per core), the softmax update runs once on the gathered rewards.
 # --------------------------------------------------------------------------------------------
+_BARRIER = None     # multiprocessing.Barrier inherited by the forked workers
+
+
 def _cpu_worker(args):
     ci, rows_lo, rows_hi, core, kind, seed, n_calls = args
+    barrier = _BARRIER
     try:
         os.sched_setaffinity(0, {core})
     except (AttributeError, OSError):
@@ -74,6 +78,8 @@ def _cpu_worker(args):
         roll = CPort(env, b).rollout_rews
     t_in = 0.0
     out = None
+    if barrier is not None:
+        barrier.wait()       # every worker has finished its set-up (NumPy env build, 10 settle steps)
     for i in range(n_calls):
         eps = rng.standard_normal((N, Hn + 1, env.nu))        # same eps on every worker (same seed)
         Y0s = pl.make_Y0s(eps, Y, pl.sigma_control * b["tdf"] ** (i % b["Ndiffuse"]))
@@ -102,11 +108,12 @@ def cpu_reverse_once(ci: int, procs: int, kind: str, n_calls: int = 1, rows_cap=
         cores = list(range(os.cpu_count() or 1))
     bounds = np.linspace(0, rows, procs + 1).astype(int)
     jobs = [(ci, int(bounds[i]), int(bounds[i + 1]), cores[i % len(cores)], kind, 0, n_calls) for i in range(procs)]
-    if procs == 1:
-        res = [_cpu_worker(jobs[0])]
-    else:
-        with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(_cpu_worker, jobs)
+    global _BARRIER
+    _BARRIER = mp.get_context("fork").Barrier(procs)   # timed region = all workers rolling at the same time
+    # always in child processes: the workers pin themselves to one core each, and an affinity set
+    # in this process would be inherited by every later pool (round-2 bug: 128 workers on one core)
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
     wall = max(r[0] for r in res)
     rews = np.concatenate([r[1] for r in res])
     t0 = time.perf_counter()                 # the one softmax on the gathered rewards (negligible)

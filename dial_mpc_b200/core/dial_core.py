@@ -279,7 +279,9 @@ class DeviceLoop:
     the GPUs inside the kernels (peer-memory exchange), so no host collective sits in the step."""
 
     def __init__(self, mbdpi: "MBDPI", state, rng, Y0=None, n_diffuse_max: Optional[int] = None,
-                 compute_bars: bool = True):
+                 compute_bars: bool = True, noise=None):
+        """``noise`` [>= n_diffuse_max, Hnode+1]: annealing schedule, default ``mbdpi.schedule`` (the
+        deploy planner passes its own, dial_plan.py:199-209)."""
         if mbdpi.world_size != 1 and not mbdpi.xch:
             raise RuntimeError("DeviceLoop on a sharded plan needs the peer-memory exchange (dial_exchange_*); "
                                f"it is off: {mbdpi.xch_error or 'DIAL_EXCHANGE=nccl'}")
@@ -303,7 +305,8 @@ class DeviceLoop:
             rews_all=(torch.zeros(a.Nsample + 1, device=dev) if mbdpi.world_size > 1 else None),
             qbar=e(Hs1, m.nq) if compute_bars else None, qdbar=e(Hs1, m.nv) if compute_bars else None,
             xbar=e(Hs1, m.nbody - 1, 3) if compute_bars else None,
-            noise=mbdpi.schedule(nmax).contiguous())
+            noise=(mbdpi.schedule(nmax) if noise is None else f(noise)).contiguous())
+        assert tuple(self.buf["noise"].shape) == (nmax, a.Hnode + 1) or self.buf["noise"].shape[0] >= nmax
         self.n_diffuse_max = nmax
         pl.mpc_bind(self.buf, mbdpi.M_shift.cpu().numpy())
 
@@ -315,8 +318,14 @@ class DeviceLoop:
             raise ValueError("n_diffuse exceeds the bound noise schedule")
         self.plan.mpc_step(n, env_step)
 
+    def rng_host(self) -> np.ndarray:
+        """The planner rng after the steps launched so far (synchronises)."""
+        return self.buf["rng"].cpu().numpy().view(np.uint32).copy()
+
     def set_state(self, qpos, qvel, qacc_warmstart=None, step: Optional[int] = None) -> None:
-        """Overwrite the planning state (deploy: the state comes from the robot / simulator)."""
+        """Overwrite the planning state (deploy: the state comes from the robot / simulator).  ``step``
+        sets ``info["step"]`` only, like the reference's ``update_mjx_state`` (dial_plan.py:149-155):
+        a seq-jump ``contact_stage`` is whatever the bound state carries."""
         self.buf["qpos"].copy_(self.plan.f32(qpos))
         self.buf["qvel"].copy_(self.plan.f32(qvel))
         if qacc_warmstart is not None:

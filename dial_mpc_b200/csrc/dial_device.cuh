@@ -80,11 +80,21 @@ struct alignas(16) DevModel {
   int32_t star_nroot, star_nchain, star_maxlen;
   int32_t star_root[8], star_len[4], star_leaf[4], star_att[4];
   int32_t nedge;                      // 4 * ncon
+  // "star layout" of the solver matrices (star variants only, see the star_* functions): dofs are
+  // renumbered root chain first (NRP = NR rounded up to 4 slots), then each hanging chain in a slot
+  // of CS = NL rounded up to 4; a row of M / H / J is [NRP root columns | CS columns of its own chain]
+  int32_t s_on, s_nrp, s_cs, s_rs, s_npos;
+  int32_t s_pos[DIAL_MAXV];           // star position of a dof
+  int32_t s_chain[DIAL_MAXV];         // chain of a dof, -1: root dof
+  int32_t s_depth[DIAL_MAXV];         // depth inside its chain (0 = attached to the root chain) / root index a (0 = deepest)
+  int32_t s_top[4];                   // first (top) dof of chain l; its dofs are s_top[l] + depth (depth-first order)
+  int32_t s_con_chain[DIAL_MAXC];     // chain that moves the contact body (-1: root dofs only)
+  int32_t o_Ms, o_Hs, o_Js, o_xs;     // star-layout scratch (overlays Mb / L / J / xch)
   // per-warp shared-memory layout (float offsets)
   int32_t o_xpos, o_xquat, o_xmat, o_xipos, o_cinert, o_cdof, o_cdofdot, o_cvel, o_cacc,
       o_cfrc, o_Mb, o_L, o_J, o_qpos, o_qvel, o_warm, o_ctrl, o_vec, o_frow, o_cpos,
       o_cframe, o_cdist, o_rcom, o_xch, o_crb, o_cfs, o_Md, o_Ld, o_Jd, o_Gd, o_frow2, o_cact, o_hcs, warp_floats;
-  int32_t pad_[3];
+  int32_t pad_[2];
 };
 
 struct alignas(16) DevPlan {
@@ -179,6 +189,57 @@ DEV Q4 axisangle(V3 axis, float angle) {
   float s, c;
   fast_sincos(0.5f * angle, s, c);   // |angle/2| < pi: SFU sin/cos (abs err ~4e-7), same code in every instantiation
   Q4 q; q.w = c; q.x = axis.x * s; q.y = axis.y * s; q.z = axis.z * s; return q;
+}
+
+// 128 / 64-bit shared-memory accesses (addresses must be 16 / 8-byte aligned)
+struct F4 { float x, y, z, w; };
+DEV F4 ld4(const float* p) {
+#ifdef DIAL_HOST_EMUL
+  F4 r; r.x = p[0]; r.y = p[1]; r.z = p[2]; r.w = p[3]; return r;
+#else
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#endif
+}
+DEV void st4(float* p, float a, float b, float c, float d) {
+#ifdef DIAL_HOST_EMUL
+  p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#else
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+#endif
+}
+DEV void ld2(const float* p, float& a, float& b) {
+#ifdef DIAL_HOST_EMUL
+  a = p[0]; b = p[1];
+#else
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  a = v.x; b = v.y;
+#endif
+}
+DEV void st2(float* p, float a, float b) {
+#ifdef DIAL_HOST_EMUL
+  p[0] = a; p[1] = b;
+#else
+  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+#endif
+}
+// spatial vectors in the slab: cdof / cdofdot rows are padded to CDS = 8 floats, cinert / crb rows to
+// CIS = 12, so that a row is one 128-bit + one 64-bit access (two + one for the inertias)
+#define CDS 8
+#define CIS 12
+DEV void ld6(const float* p, float* o) {
+  F4 a = ld4(p);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+  ld2(p + 4, o[4], o[5]);
+}
+DEV void st6(float* p, const float* v) {
+  st4(p, v[0], v[1], v[2], v[3]);
+  st2(p + 4, v[4], v[5]);
+}
+DEV void ld10(const float* p, float* o) {
+  F4 a = ld4(p), b = ld4(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  ld2(p + 8, o[8], o[9]);
 }
 
 // spatial helpers on [ang(3), lin(3)] vectors
@@ -292,6 +353,15 @@ struct WarpCtx {
   int itersync;        // lock-step level 3 (dense path): CTA barrier per Newton iteration
   float* dbg;          // optional counters (tests / tuning): [0] physics steps, [1] Newton iterations
   int chain[DIAL_MAXCHAIN];
+  // star layout constants of this lane (star variants; DevModel::s_*)
+  int s_pos;           // star position of this lane's dof (0 for non-dof lanes)
+  int s_col;           // its column inside a row: root index a, or NRP + depth for a chain dof
+  int s_cb;            // first position of its chain (NRP for root / non-dof lanes)
+  int s_chain;         // chain id, -1: root dof, -2: not a dof
+  int s_depth;         // depth inside the chain / root index
+  int s_top;           // first dof of its chain
+  uint32_t s_conmask;  // contacts whose rows can be non-zero in this lane's column
+  int e_cb;            // edge lanes: first position of the contact's chain (NRP if the body hangs off the root chain)
 };
 
 #define SM(name) (w.s + w.M->o_##name)
@@ -696,57 +766,375 @@ DEV void build_H(WarpCtx& w, const Solver& S, const float* Mrow, float* R) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Star-layout solver kernels (star variants NL > 0).  Rows of M, H = M + J^T D J and J are kept
+// as [NRP root columns | CS columns of the row's own chain] (NRP, CS: NR, NL rounded up to 4):
+// every inner product below has compile-time offsets, vector (128-bit) shared-memory loads and no
+// table look-ups — the compact-chain code above spends a third of its instructions on index
+// arithmetic.  Per lane i (= dof i): Rr[NR] = H[i][root a], Rc[NL] = H[i][own chain, depth q].
+//   Ms / Hs   [pos][RS]   full symmetric rows of M / H at the star position of the dof
+//   Js        [edge][RS]  contact pyramid rows: root part + the part on the contact's chain
+//   xs        [npos]      a dof vector in star order (zero in the padding slots)
+// ---------------------------------------------------------------------------------
+template <int NL, int NR>
+struct StarDims {
+  static constexpr int NRP = (NR + 3) & ~3, CS = (NL + 3) & ~3, RS = NRP + CS;
+};
+
+// N floats (N <= 8, rounded up to whole float4 loads; the source is padded) from a 16-byte aligned address
+template <int N>
+DEV void ldv(const float* p, float* out) {
+  F4 a = ld4(p);
+  out[0] = a.x; if (N > 1) out[1] = a.y; if (N > 2) out[2] = a.z; if (N > 3) out[3] = a.w;
+  if (N > 4) {
+    F4 b = ld4(p + 4);
+    out[4] = b.x; if (N > 5) out[5] = b.y; if (N > 6) out[6] = b.z; if (N > 7) out[7] = b.w;
+  }
+}
+// publish a row [Rr | Rc] at p (RS floats, padding written as zero)
+template <int NL, int NR>
+DEV void star_store_row(float* p, const float* Rr, const float* Rc) {
+  using SD = StarDims<NL, NR>;
+  float t[SD::RS];
+#pragma unroll
+  for (int i = 0; i < SD::RS; ++i) t[i] = 0.f;
+#pragma unroll
+  for (int a = 0; a < NR; ++a) t[a] = Rr[a];
+#pragma unroll
+  for (int q = 0; q < NL; ++q) t[SD::NRP + q] = Rc[q];
+#pragma unroll
+  for (int i = 0; i < SD::RS; i += 4) st4(p + i, t[i], t[i + 1], t[i + 2], t[i + 3]);
+}
+
+// y = M x and (edge lanes) J x with one publication of x.  Mr/Mc: this lane's row of M.
+template <int NL, int NR, bool WITH_M, bool WITH_J>
+DEV void star_mul_MJ(WarpCtx& w, const float* Mr, const float* Mc, float x, float& Mx, float& Jx) {
+  using SD = StarDims<NL, NR>;
+  const DevModel& M = *w.M;
+  float* xs = SM(xs);
+  const float* Ms = SM(Ms);
+  syncwarp();
+  if (w.s_chain >= -1) xs[w.s_pos] = x;
+  syncwarp();
+  float xr[SD::NRP], xc[SD::CS];
+  ldv<NR>(xs, xr);
+  ldv<NL>(xs + w.s_cb, xc);
+  float y = 0.f;
+  if (WITH_M) {
+#pragma unroll
+  for (int a = 0; a < NR; ++a) y += Mr[a] * xr[a];
+  if (w.s_chain >= 0) {
+#pragma unroll
+    for (int q = 0; q < NL; ++q) y += Mc[q] * xc[q];
+  } else if (w.s_chain == -1) {
+    // root dof: the coupling column, sum over every chain slot of M[slot dof][root a] x[slot dof]
+    const float* col = Ms + SD::NRP * SD::RS + w.s_col;
+    const int nslot = M.star_nchain * SD::CS;
+    for (int s0 = 0; s0 < nslot; s0 += 4) {
+      F4 xv = ld4(xs + SD::NRP + s0);
+      y += col[(s0 + 0) * SD::RS] * xv.x + col[(s0 + 1) * SD::RS] * xv.y + col[(s0 + 2) * SD::RS] * xv.z + col[(s0 + 3) * SD::RS] * xv.w;
+    }
+  }
+  }
+  Mx = y;
+  if (WITH_J) {
+    float j = 0.f;
+    if (w.lane < M.nedge) {
+      const float* row = SM(Js) + w.lane * SD::RS;
+      float jr[SD::NRP], jc[SD::CS], xe[SD::CS];
+      ldv<NR>(row, jr);
+      ldv<NL>(row + SD::NRP, jc);
+      ldv<NL>(xs + w.e_cb, xe);
+#pragma unroll
+      for (int a = 0; a < NR; ++a) j += jr[a] * xr[a];
+#pragma unroll
+      for (int q = 0; q < NL; ++q) j += jc[q] * xe[q];
+    }
+    Jx = j;
+  }
+}
+
+// J^T f: edge lane e holds f_e; dof lane returns sum_e J[e][my column] f_e
+template <int NL, int NR>
+DEV float star_mul_JT(WarpCtx& w, float f) {
+  using SD = StarDims<NL, NR>;
+  const DevModel& M = *w.M;
+  const float* Js = SM(Js);
+  float* frow = SM(frow);
+  syncwarp();
+  frow[w.lane] = f;
+  syncwarp();
+  float y = 0.f;
+  const float* col = Js + w.s_col;
+  for (int c = 0; c < M.m.ncon; ++c) {
+    const F4 fv = ld4(frow + 4 * c);
+    if ((w.s_conmask >> c) & 1u) {
+      const float* jc = col + 4 * c * SD::RS;
+      y += jc[0] * fv.x + jc[SD::RS] * fv.y + jc[2 * SD::RS] * fv.z + jc[3 * SD::RS] * fv.w;
+    }
+  }
+  return y;
+}
+
+// H row of this lane: M + active limit + sum over active edges d_e j_e^T j_e
+template <int NL, int NR>
+DEV void star_build_H(WarpCtx& w, const Solver& S, const float* Mr, const float* Mc, float* Rr, float* Rc) {
+  using SD = StarDims<NL, NR>;
+  const DevModel& M = *w.M;
+  const float* Js = SM(Js);
+  float* frow = SM(frow);
+  syncwarp();
+  frow[w.lane] = (S.e_Jaref < 0.f) ? S.e_D : 0.f;
+  syncwarp();
+#pragma unroll
+  for (int a = 0; a < NR; ++a) Rr[a] = Mr[a];
+#pragma unroll
+  for (int q = 0; q < NL; ++q) Rc[q] = Mc[q];
+  const float ld = (S.l_Jaref < 0.f) ? S.l_D : 0.f;   // limit rows are +-e_d: diagonal only
+  if (w.s_chain >= 0) {
+#pragma unroll
+    for (int q = 0; q < NL; ++q) Rc[q] += (q == w.s_depth) ? ld : 0.f;
+  } else if (w.s_chain == -1) {
+#pragma unroll
+    for (int a = 0; a < NR; ++a) Rr[a] += (a == w.s_depth) ? ld : 0.f;
+  }
+  for (int e = 0; e < M.nedge; ++e) {
+    const float de = frow[e];
+    if (de == 0.f) continue;                           // warp-uniform
+    const float* row = Js + e * SD::RS;
+    const float je = ((w.s_conmask >> (e >> 2)) & 1u) ? row[w.s_col] : 0.f;
+    const float al = de * je;
+    float jr[SD::NRP], jc[SD::CS];
+    ldv<NR>(row, jr);
+    ldv<NL>(row + SD::NRP, jc);
+#pragma unroll
+    for (int a = 0; a < NR; ++a) Rr[a] += al * jr[a];
+#pragma unroll
+    for (int q = 0; q < NL; ++q) Rc[q] += al * jc[q];   // other chains / root lanes: al == 0 or Rc unused
+  }
+}
+
+// Solve H x = g for the star structure (block elimination, see star_solve above); rows in the
+// star layout are published once and gathered with compile-time offsets.
+template <int NL, int NR>
+DEV float star_solve2(WarpCtx& w, const float* Rr, const float* Rc, float g) {
+  using SD = StarDims<NL, NR>;
+  static_assert(NR + 1 <= 8, "root block + rhs must fit the 8 lanes of a group");
+  const DevModel& M = *w.M;
+  const int lane = w.lane;
+  float* Hs = SM(Hs);
+  float* xs = SM(xs);
+  syncwarp();
+  if (w.s_chain >= -1) {
+    star_store_row<NL, NR>(Hs + w.s_pos * SD::RS, Rr, Rc);
+    xs[w.s_pos] = g;
+  }
+  syncwarp();
+  const int grp = lane >> 3, j = lane & 7, gbase = lane & ~7;
+  const bool ischain = grp < M.star_nchain;
+  const int len = ischain ? M.star_len[grp] : 0;
+  const int cb = SD::NRP + grp * SD::CS;
+  // ---- gather: chain block A (whole group) and this lane's column of [C | g] -------------------
+  float A[NL][NL], wv[NL];
+#pragma unroll
+  for (int p = 0; p < NL; ++p) {
+    const bool on = p < len;
+    const float* row = Hs + (cb + p) * SD::RS;
+    float rc[SD::CS];
+    ldv<NL>(row + SD::NRP, rc);
+#pragma unroll
+    for (int p2 = p; p2 < NL; ++p2) A[p][p2] = (on && p2 < len) ? rc[p2] : (p2 == p ? 1.f : 0.f);
+    float cv = 0.f;
+    if (on && j < NR) cv = row[j];
+    if (on && j == NR) cv = xs[cb + p];
+    wv[p] = cv;
+  }
+  // ---- A = R^T R (upper R in place), w = R^-T c ------------------------------------------------------
+  float rinv[NL];
+#pragma unroll
+  for (int p = 0; p < NL; ++p) {
+    float d = A[p][p];
+#pragma unroll
+    for (int k = 0; k < p; ++k) d -= A[k][p] * A[k][p];
+    const float inv = rsqrtf(fmaxf(d, DIAL_MINVAL));
+    rinv[p] = inv;
+#pragma unroll
+    for (int p2 = p + 1; p2 < NL; ++p2) {
+      float v = A[p][p2];
+#pragma unroll
+      for (int k = 0; k < p; ++k) v -= A[k][p] * A[k][p2];
+      A[p][p2] = v * inv;
+    }
+    float v = wv[p];
+#pragma unroll
+    for (int k = 0; k < p; ++k) v -= A[k][p] * wv[k];
+    wv[p] = v * inv;
+  }
+  // ---- row j of W^T [W | z], summed over the chains ---------------------------------------------------
+  float t[NR + 1];
+#pragma unroll
+  for (int j2 = 0; j2 <= NR; ++j2) {
+    float acc = 0.f;
+#pragma unroll
+    for (int p = 0; p < NL; ++p) acc += wv[p] * shfl(wv[p], gbase + j2);
+    t[j2] = acc;
+  }
+#pragma unroll
+  for (int j2 = 0; j2 <= NR; ++j2) {
+    t[j2] += shfl_xor(t[j2], 8);
+    t[j2] += shfl_xor(t[j2], 16);
+  }
+  // ---- root block: lane j holds row j of S and rhs_j, then all-gather inside the group ---------------
+  float srow[NR], rhs = 0.f;
+  {
+    const int jj = j < NR ? j : 0;
+    float br[SD::NRP];
+    ldv<NR>(Hs + jj * SD::RS, br);
+#pragma unroll
+    for (int a2 = 0; a2 < NR; ++a2) srow[a2] = br[a2] - t[a2];
+    rhs = xs[jj] - t[NR];
+  }
+  float S_[NR][NR], xB[NR];
+#pragma unroll
+  for (int a = 0; a < NR; ++a) {
+#pragma unroll
+    for (int a2 = a; a2 < NR; ++a2) S_[a][a2] = shfl(srow[a2], gbase + a);
+    xB[a] = shfl(rhs, gbase + a);
+  }
+  float sinv[NR];
+#pragma unroll
+  for (int a = 0; a < NR; ++a) {
+    float d = S_[a][a];
+#pragma unroll
+    for (int k = 0; k < a; ++k) d -= S_[k][a] * S_[k][a];
+    const float inv = rsqrtf(fmaxf(d, DIAL_MINVAL));
+    sinv[a] = inv;
+#pragma unroll
+    for (int a2 = a + 1; a2 < NR; ++a2) {
+      float v = S_[a][a2];
+#pragma unroll
+      for (int k = 0; k < a; ++k) v -= S_[k][a] * S_[k][a2];
+      S_[a][a2] = v * inv;
+    }
+    float v = xB[a];
+#pragma unroll
+    for (int k = 0; k < a; ++k) v -= S_[k][a] * xB[k];
+    xB[a] = v * inv;
+  }
+#pragma unroll
+  for (int a = NR - 1; a >= 0; --a) {
+    float v = xB[a];
+#pragma unroll
+    for (int a2 = a + 1; a2 < NR; ++a2) v -= S_[a][a2] * xB[a2];
+    xB[a] = v * sinv[a];
+  }
+  // ---- chain back-substitution: x_l = R^-1 (z - W x_B) ----------------------------------------------
+  float xb_j = 0.f;
+#pragma unroll
+  for (int a = 0; a < NR; ++a) xb_j = (j == a) ? xB[a] : xb_j;
+  float xl[NL];
+#pragma unroll
+  for (int p = 0; p < NL; ++p) {
+    float v = (j < NR) ? wv[p] * xb_j : 0.f;
+    v += shfl_xor(v, 1); v += shfl_xor(v, 2); v += shfl_xor(v, 4);
+    xl[p] = shfl(wv[p], gbase + NR) - v;
+  }
+#pragma unroll
+  for (int p = NL - 1; p >= 0; --p) {
+    float v = xl[p];
+#pragma unroll
+    for (int p2 = p + 1; p2 < NL; ++p2) v -= A[p][p2] * xl[p2];
+    xl[p] = v * rinv[p];
+  }
+  // ---- scatter back to the dof lanes (star order) ------------------------------------------------------
+  syncwarp();
+  if (j == 0 && ischain) {
+#pragma unroll
+    for (int p = 0; p < NL; ++p)
+      if (p < len) xs[cb + p] = xl[p];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < NR; ++a) xs[a] = xB[a];
+  }
+  syncwarp();
+  return w.s_chain >= -1 ? xs[w.s_pos] : 0.f;
+}
+
+// efc_force, qfrc_constraint, costs and the gradient in the star layout
+template <int NL, int NR>
+DEV void star_update_constraint(WarpCtx& w, Solver& S) {
+  float fl = (S.l_Jaref < 0.f) ? -S.l_D * S.l_Jaref : 0.f;
+  float fe = (S.e_Jaref < 0.f) ? -S.e_D * S.e_Jaref : 0.f;
+  float qfc = star_mul_JT<NL, NR>(w, fe) + S.l_sign * fl;
+  S.grad = S.Ma - S.qfs - qfc;
+  float g = (S.Ma - S.qfs) * (S.qacc - S.qas);
+  float c = ((S.l_Jaref < 0.f) ? S.l_D * S.l_Jaref * S.l_Jaref : 0.f)
+          + ((S.e_Jaref < 0.f) ? S.e_D * S.e_Jaref * S.e_Jaref : 0.f);
+  float g2 = S.grad * S.grad;
+  warp_sum3(g, c, g2);
+  S.gauss = 0.5f * g;
+  S.prev_cost = S.cost;
+  S.cost = 0.5f * c + S.gauss;
+  S.gradnorm2 = g2;
+}
+
 struct LSPoint { float alpha, cost, d0, d1; };
 
-// evaluate the 1-D piecewise-quadratic cost at NA (<= 3) alphas at once
-template <int NA>
-DEV void ls_points(const Solver& S, float l_jv, float e_jv, const float* qg, const float* al, LSPoint* out) {
+// Per-lane quadratic coefficients of the 1-D cost along the search direction (limit row of the
+// dof lane, pyramid edge row of the edge lane); constant during one line search.
+struct LSRow { float lq0, lq1, lq2, eq0, eq1, eq2; };
+
+// Evaluate the 1-D piecewise-quadratic cost at NA (<= 3) alphas at once.  The bracketing loop of
+// the line search needs only the derivatives d0 / d1: with COST = false the cost sums are left
+// out (a third of the warp reductions); the costs of the points that survive are evaluated once
+// at the end with the same expressions, so the result equals MJX's, which carries them along.
+template <int NA, bool COST>
+DEV void ls_points(const Solver& S, const LSRow& K, float l_jv, float e_jv, const float* qg, const float* al, LSPoint* out) {
   float s[3 * NA];
 #pragma unroll
   for (int i = 0; i < 3 * NA; ++i) s[i] = 0.f;
-  {
-    float q0 = 0.5f * S.l_Jaref * S.l_Jaref * S.l_D, q1 = l_jv * S.l_Jaref * S.l_D, q2 = 0.5f * l_jv * l_jv * S.l_D;
 #pragma unroll
-    for (int i = 0; i < NA; ++i)
-      if (S.l_Jaref + al[i] * l_jv < 0.f) { s[3 * i] += q0; s[3 * i + 1] += q1; s[3 * i + 2] += q2; }
-    q0 = 0.5f * S.e_Jaref * S.e_Jaref * S.e_D; q1 = e_jv * S.e_Jaref * S.e_D; q2 = 0.5f * e_jv * e_jv * S.e_D;
-#pragma unroll
-    for (int i = 0; i < NA; ++i)
-      if (S.e_Jaref + al[i] * e_jv < 0.f) { s[3 * i] += q0; s[3 * i + 1] += q1; s[3 * i + 2] += q2; }
+  for (int i = 0; i < NA; ++i) {
+    if (S.l_Jaref + al[i] * l_jv < 0.f) { if (COST) s[3 * i] += K.lq0; s[3 * i + 1] += K.lq1; s[3 * i + 2] += K.lq2; }
+    if (S.e_Jaref + al[i] * e_jv < 0.f) { if (COST) s[3 * i] += K.eq0; s[3 * i + 1] += K.eq1; s[3 * i + 2] += K.eq2; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int i = 0; i < 3 * NA; ++i) s[i] += shfl_xor(s[i], o);
+    for (int i = 0; i < 3 * NA; ++i)
+      if (COST || (i % 3) != 0) s[i] += shfl_xor(s[i], o);
   }
 #pragma unroll
   for (int i = 0; i < NA; ++i) {
     float t0 = qg[0] + s[3 * i], t1 = qg[1] + s[3 * i + 1], t2 = qg[2] + s[3 * i + 2];
     float a = al[i];
     out[i].alpha = a;
-    out[i].cost = a * a * t2 + a * t1 + t0;
+    out[i].cost = COST ? a * a * t2 + a * t1 + t0 : 0.f;
     out[i].d0 = 2.f * a * t2 + t1;
     out[i].d1 = 2.f * t2 + (t2 == 0.f ? DIAL_MINVAL : 0.f);
   }
 }
 
-template <int MCU>
-DEV void linesearch(WarpCtx& w, Solver& S, const float* Mrow) {
+// MJX solver._linesearch given M.search (mv) and J.search (e_jv) of this lane's rows
+DEV void linesearch_core(WarpCtx& w, Solver& S, float mv, float e_jv) {
   const DevModel& M = *w.M;
   const int nv = M.m.nv;
   const float scale = M.m.meaninertia * (float)(nv > 1 ? nv : 1);
-  float mv = mul_M<MCU>(w, Mrow, S.search);
-  float e_jv = mul_J(w, S.search);
   float l_jv = S.l_sign * S.search;
   float ss = S.search * S.search, sMa = S.search * (S.Ma - S.qfs), sMv = S.search * mv;
   warp_sum3(ss, sMa, sMv);
   float gtol = M.m.tolerance * M.m.ls_tolerance * sqrtf(ss) * scale;
   float qg[3] = {S.gauss, sMa, 0.5f * sMv};
+  LSRow K;
+  K.lq0 = 0.5f * S.l_Jaref * S.l_Jaref * S.l_D; K.lq1 = l_jv * S.l_Jaref * S.l_D; K.lq2 = 0.5f * l_jv * l_jv * S.l_D;
+  K.eq0 = 0.5f * S.e_Jaref * S.e_Jaref * S.e_D; K.eq1 = e_jv * S.e_Jaref * S.e_D; K.eq2 = 0.5f * e_jv * e_jv * S.e_D;
   LSPoint p0, lo, hi;
   float a1[1] = {0.f};
-  ls_points<1>(S, l_jv, e_jv, qg, a1, &p0);
+  ls_points<1, true>(S, K, l_jv, e_jv, qg, a1, &p0);
   a1[0] = p0.alpha - p0.d0 / p0.d1;
-  ls_points<1>(S, l_jv, e_jv, qg, a1, &lo);
+  ls_points<1, false>(S, K, l_jv, e_jv, qg, a1, &lo);
   if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
   bool swap = true;
   for (int it = 0; it < M.m.ls_iterations; ++it) {
@@ -756,7 +1144,7 @@ DEV void linesearch(WarpCtx& w, Solver& S, const float* Mrow) {
     if (done) break;
     LSPoint pt[3];
     float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
-    ls_points<3>(S, l_jv, e_jv, qg, a3, pt);
+    ls_points<3, false>(S, K, l_jv, e_jv, qg, a3, pt);
     const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
     bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
     if (swap_lo_next) lo = lo_next;
@@ -768,6 +1156,13 @@ DEV void linesearch(WarpCtx& w, Solver& S, const float* Mrow) {
     if (swap_hi_mid) hi = mid;
     swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
   }
+  // costs of the two surviving points (same expressions MJX evaluates when it visits them)
+  {
+    LSPoint fin[2];
+    float a2[2] = {lo.alpha, hi.alpha};
+    ls_points<2, true>(S, K, l_jv, e_jv, qg, a2, fin);
+    lo.cost = fin[0].cost; hi.cost = fin[1].cost;
+  }
   bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
   float alpha = (lo.cost < hi.cost) ? lo.alpha : hi.alpha;
   if (!improved) alpha = 0.f;
@@ -777,6 +1172,12 @@ DEV void linesearch(WarpCtx& w, Solver& S, const float* Mrow) {
   S.e_Jaref += alpha * e_jv;
 }
 
+template <int MCU>
+DEV void linesearch(WarpCtx& w, Solver& S, const float* Mrow) {
+  float mv = mul_M<MCU>(w, Mrow, S.search);
+  float e_jv = mul_J(w, S.search);
+  linesearch_core(w, S, mv, e_jv);
+}
 
 // ---------------------------------------------------------------------------------
 // Dense / elliptic-cone solver path (NL < 0): models whose contacts couple two moving bodies
@@ -1256,7 +1657,7 @@ DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float
   }
   syncwarp();
   if (isdof) {
-    V3 ca_ = ld3(cdof + 6 * d), cl_ = ld3(cdof + 6 * d + 3);
+    V3 ca_ = ld3(cdof + CDS * d), cl_ = ld3(cdof + CDS * d + 3);
     V3 rc = ld3(rcom + 3 * M.body_rootidx[m.dof_bodyid[d]]);
     for (int c = 0; c < m.ncon; ++c) {
       if (!cact[c]) continue;
@@ -1589,34 +1990,32 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
     I[4] = ximat[0] * ximat[6] * di[0] + ximat[1] * ximat[7] * di[1] + ximat[2] * ximat[8] * di[2];
     I[5] = ximat[3] * ximat[6] * di[0] + ximat[4] * ximat[7] * di[1] + ximat[5] * ximat[8] * di[2];
     float o2 = dot(off, off);
-    float* ci = cinert + 10 * b;
-    ci[0] = I[0] + mass * (o2 - off.x * off.x);
-    ci[1] = I[1] + mass * (o2 - off.y * off.y);
-    ci[2] = I[2] + mass * (o2 - off.z * off.z);
-    ci[3] = I[3] - mass * off.x * off.y;
-    ci[4] = I[4] - mass * off.x * off.z;
-    ci[5] = I[5] - mass * off.y * off.z;
-    ci[6] = mass * off.x; ci[7] = mass * off.y; ci[8] = mass * off.z; ci[9] = mass;
+    float* ci = cinert + CIS * b;
+    st4(ci, I[0] + mass * (o2 - off.x * off.x), I[1] + mass * (o2 - off.y * off.y), I[2] + mass * (o2 - off.z * off.z),
+        I[3] - mass * off.x * off.y);
+    st4(ci + 4, I[4] - mass * off.x * off.z, I[5] - mass * off.y * off.z, mass * off.x, mass * off.y);
+    st2(ci + 8, mass * off.z, mass);
     if (jid >= 0) {
       int d = m.jnt_dofadr[jid];
       V3 offset = com - anchor;
       if (jtype == JNT_FREE) {
         for (int i = 0; i < 3; ++i) {
-          float* c0 = cdof + 6 * (d + i);
-          c0[0] = c0[1] = c0[2] = 0.f;
-          c0[3] = i == 0 ? 1.f : 0.f; c0[4] = i == 1 ? 1.f : 0.f; c0[5] = i == 2 ? 1.f : 0.f;
+          float* c0 = cdof + CDS * (d + i);
+          st4(c0, 0.f, 0.f, 0.f, i == 0 ? 1.f : 0.f);
+          st2(c0 + 4, i == 1 ? 1.f : 0.f, i == 2 ? 1.f : 0.f);
           V3 ax = v3(xmat[9 * b + i], xmat[9 * b + 3 + i], xmat[9 * b + 6 + i]);
-          float* c1 = cdof + 6 * (d + 3 + i);
-          st3(c1, ax);
-          st3(c1 + 3, cross(ax, offset));
+          V3 cx = cross(ax, offset);
+          float* c1 = cdof + CDS * (d + 3 + i);
+          st4(c1, ax.x, ax.y, ax.z, cx.x);
+          st2(c1 + 4, cx.y, cx.z);
         }
       } else if (jtype == JNT_HINGE) {
-        st3(cdof + 6 * d, axis);
-        st3(cdof + 6 * d + 3, cross(axis, offset));
+        V3 cx = cross(axis, offset);
+        st4(cdof + CDS * d, axis.x, axis.y, axis.z, cx.x);
+        st2(cdof + CDS * d + 4, cx.y, cx.z);
       } else {
-        float* c0 = cdof + 6 * d;
-        c0[0] = c0[1] = c0[2] = 0.f;
-        st3(c0 + 3, axis);
+        st4(cdof + CDS * d, 0.f, 0.f, 0.f, axis.x);
+        st2(cdof + CDS * d + 4, axis.y, axis.z);
       }
     }
   }
@@ -1632,39 +2031,45 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
       if (jtype == JNT_FREE) {
         int d = m.jnt_dofadr[jid];
         for (int k = 0; k < 3; ++k) {
-          float qd = qvel[d + k];
+          float qd = qvel[d + k], cd[6];
+          ld6(cdof + CDS * (d + k), cd);
 #pragma unroll
-          for (int i = 0; i < 6; ++i) { cv[i] += cdof[6 * (d + k) + i] * qd; cdofdot[6 * (d + k) + i] = 0.f; }
+          for (int i = 0; i < 6; ++i) cv[i] += cd[i] * qd;
+          st4(cdofdot + CDS * (d + k), 0.f, 0.f, 0.f, 0.f);
+          st2(cdofdot + CDS * (d + k) + 4, 0.f, 0.f);
         }
         float cvt[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) cvt[i] = cv[i];
         for (int k = 3; k < 6; ++k) {
-          float dd[6];
-          mcross(cvt, cdof + 6 * (d + k), dd);
+          float dd[6], cd[6];
+          ld6(cdof + CDS * (d + k), cd);
+          mcross(cvt, cd, dd);
           float qd = qvel[d + k];
+          st6(cdofdot + CDS * (d + k), dd);
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
-            cdofdot[6 * (d + k) + i] = dd[i];
-            cv[i] += cdof[6 * (d + k) + i] * qd;
+            cv[i] += cd[i] * qd;
             ca[i] += dd[i] * qd;
           }
         }
       } else if (jid >= 0) {
         int d = m.jnt_dofadr[jid];
-        float dd[6];
-        mcross(cv, cdof + 6 * d, dd);
+        float dd[6], cd[6];
+        ld6(cdof + CDS * d, cd);
+        mcross(cv, cd, dd);
         float qd = qvel[d];
+        st6(cdofdot + CDS * d, dd);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          cdofdot[6 * d + i] = dd[i];
-          cv[i] += cdof[6 * d + i] * qd;
+          cv[i] += cd[i] * qd;
           ca[i] += dd[i] * qd;
         }
       }
-      float f1[6], f2[6], f3[6];
-      inert_mul(cinert + 10 * b, ca, f1);
-      inert_mul(cinert + 10 * b, cv, f2);
+      float f1[6], f2[6], f3[6], cib[10];
+      ld10(cinert + CIS * b, cib);
+      inert_mul(cib, ca, f1);
+      inert_mul(cib, cv, f2);
       mcross_force(cv, f2, f3);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
@@ -1684,7 +2089,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
     float* cfs = SM(cfs);
     const int comp = lane & 15, half = lane >> 4;
     const float* src = comp < 10 ? cinert + comp : cfrc + (comp - 10);
-    const int stride = comp < 10 ? 10 : 6;
+    const int stride = comp < 10 ? CIS : 6;
     float* dst = comp < 10 ? crb + comp : cfs + (comp - 10);
     for (int b0 = 1; b0 < nb; b0 += 2) {
       const int bb = b0 + half;
@@ -1713,24 +2118,60 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   const int d = lane;
   const bool isdof = d < nv;
   float myqvel = isdof ? qvel[d] : 0.f;
-  float Mrow[MC], R[MC];
+  float mycdof[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // this lane's cdof row, kept for the contact Jacobian
+  constexpr bool STAR = NL > 0;   // star layout rows (Mr | Mc) instead of compact chain rows
+  constexpr int SNR = STAR ? NR : 1, SNL = STAR ? NL : 1;
+  float Mrow[STAR ? 1 : MC], R[STAR ? 1 : MC];
+  float Mr[SNR], Mc[SNL], Rr[SNR], Rc[SNL];
 #pragma unroll
-  for (int c = 0; c < MCU; ++c) { Mrow[c] = 0.f; R[c] = 0.f; }
+  for (int a = 0; a < SNR; ++a) { Mr[a] = 0.f; Rr[a] = 0.f; }
+#pragma unroll
+  for (int q = 0; q < SNL; ++q) { Mc[q] = 0.f; Rc[q] = 0.f; }
+  if constexpr (!STAR) {
+#pragma unroll
+    for (int c = 0; c < MCU; ++c) { Mrow[c] = 0.f; R[c] = 0.f; }
+  }
   if (isdof) {
     int bi = m.dof_bodyid[d];
     float f[6];
-    inert_mul(SM(crb) + 10 * bi, cdof + 6 * d, f);
+    {
+      float crbb[10];
+      ld10(SM(crb) + CIS * bi, crbb);
+      ld6(cdof + CDS * d, mycdof);
+      inert_mul(crbb, mycdof, f);
+    }
+    if constexpr (STAR) {
+      using SD = StarDims<NL, NR>;
+      // row of M in the star layout: entries towards ancestors are computed (CRB), the others
+      // are the mirror images of other lanes' entries (filled below from the published rows)
+      const float arm = m.dof_armature[d];
+      if (w.s_chain >= 0) {
+        const int att = M.star_att[w.s_chain];
 #pragma unroll
-    for (int c = 0; c < MCU; ++c)
-      if (c < w.nch) Mrow[c] = dot6(f, cdof + 6 * w.chain[c]);
-    Mrow[0] += m.dof_armature[d];
-    if constexpr (NL >= 0) {   // the dense path keeps M in SM(Md) instead
-      float* Mb = SM(Mb);
+        for (int q = 0; q < NL; ++q)
+          if (q <= w.s_depth) { float cd[6]; ld6(cdof + CDS * (w.s_top + q), cd); Mc[q] = dot6(f, cd) + (q == w.s_depth ? arm : 0.f); }
+#pragma unroll
+        for (int a = 0; a < NR; ++a)
+          if (a >= att) { float cd[6]; ld6(cdof + CDS * M.star_root[a], cd); Mr[a] = dot6(f, cd); }
+      } else {
+#pragma unroll
+        for (int a = 0; a < NR; ++a)
+          if (a >= w.s_depth) { float cd[6]; ld6(cdof + CDS * M.star_root[a], cd); Mr[a] = dot6(f, cd) + (a == w.s_depth ? arm : 0.f); }
+      }
+      star_store_row<NL, NR>(SM(Ms) + w.s_pos * SD::RS, Mr, Mc);
+    } else {
 #pragma unroll
       for (int c = 0; c < MCU; ++c)
-        if (c < w.nch) Mb[d * MC + c] = Mrow[c];
+        if (c < w.nch) { float cd[6]; ld6(cdof + CDS * w.chain[c], cd); Mrow[c] = dot6(f, cd); }
+      Mrow[0] += m.dof_armature[d];
+      if constexpr (NL >= 0) {   // the dense path keeps M in SM(Md) instead
+        float* Mb = SM(Mb);
+#pragma unroll
+        for (int c = 0; c < MCU; ++c)
+          if (c < w.nch) Mb[d * MC + c] = Mrow[c];
+      }
     }
-    float bias = dot6(cdof + 6 * d, SM(cfs) + 6 * bi);
+    float bias = dot6(mycdof, SM(cfs) + 6 * bi);
     float act = 0.f;
     int a = M.dof_actuator[d];
     if (a >= 0) {
@@ -1742,6 +2183,20 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
       act = force * m.actuator_gear[a];
     }
     S.qfs = -m.dof_damping[d] * myqvel - bias + act;
+  }
+  if constexpr (STAR) {
+    using SD = StarDims<NL, NR>;
+    float* Ms = SM(Ms);
+    syncwarp();
+    if (w.s_chain >= 0) {          // entries towards deeper dofs of my chain
+#pragma unroll
+      for (int q = 0; q < NL; ++q)
+        if (q > w.s_depth) { Mc[q] = Ms[(w.s_cb + q) * SD::RS + SD::NRP + w.s_depth]; Ms[w.s_pos * SD::RS + SD::NRP + q] = Mc[q]; }
+    } else if (w.s_chain == -1) {  // entries towards deeper root dofs
+#pragma unroll
+      for (int a = 0; a < NR; ++a)
+        if (a < w.s_depth) { Mr[a] = Ms[a * SD::RS + w.s_depth]; Ms[w.s_pos * SD::RS + a] = Mr[a]; }
+    }
   }
 
   float qacc, qacc_int;
@@ -1759,11 +2214,121 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
         if (j == d) Hd[j] += isdof ? m.timestep * m.dof_damping[d] : 1.f;
       qacc_int = dense_factor_solve<NR>(w, Hd, S.qfs + S.qfc);
     }
+  } else if constexpr (STAR) {
+  using SD = StarDims<NL, NR>;
+  // ---- 8. constraint rows in the star layout (lane = dof writes its column of every row) --------
+  float* Js = SM(Js);
+  if (isdof) {
+    V3 ca_ = v3(mycdof[0], mycdof[1], mycdof[2]), cl_ = v3(mycdof[3], mycdof[4], mycdof[5]);
+    V3 rc = ld3(rcom + 3 * M.body_rootidx[m.dof_bodyid[d]]);
+    for (int c = 0; c < m.ncon; ++c) {
+      if (!((w.s_conmask >> c) & 1u)) continue;   // my column is structurally zero in this contact's rows
+      const int k = M.con_pair[c];
+      float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+      const bool moves = (M.body_dofmask[m.geom_bodyid[m.pair_geom2[k]]] >> d) & 1u;
+      if (moves && cdist[c] - (m.pair_margin[k] - m.pair_gap[k]) < 0.f) {
+        V3 p = ld3(cpos + 3 * c);
+        V3 jp = cl_ + cross(ca_, p - rc);
+        float jn = dot(ld3(cframe + 9 * c), jp), j1 = dot(ld3(cframe + 9 * c + 3), jp), j2 = dot(ld3(cframe + 9 * c + 6), jp);
+        float mu0 = m.pair_friction[k][0], mu1 = m.pair_friction[k][1];
+        e0 = jn + mu0 * j1; e1 = jn - mu0 * j1; e2 = jn + mu1 * j2; e3 = jn - mu1 * j2;
+      }
+      float* col = Js + 4 * c * SD::RS + w.s_col;
+      col[0] = e0; col[SD::RS] = e1; col[2 * SD::RS] = e2; col[3 * SD::RS] = e3;
+    }
+    int lj = M.dof_limited[d];
+    if (lj >= 0) {
+      float qv = qpos[m.jnt_qposadr[lj]];
+      float dmin = qv - m.jnt_range[lj][0], dmax = m.jnt_range[lj][1] - qv;
+      float pos = fminf(dmin, dmax) - m.jnt_margin[lj];
+      if (pos < 0.f) {
+        float sign = dmin < dmax ? 1.f : -1.f;
+        float k_, b_, imp;
+        kbi(m.timestep, m.jnt_solref[lj], m.jnt_solimp[lj], pos, k_, b_, imp);
+        float Rr_ = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, DIAL_MINVAL);
+        S.l_sign = sign;
+        S.l_D = 1.f / Rr_;
+        S.l_aref = -b_ * (sign * myqvel) - k_ * imp * pos;
+      }
+    }
+  }
+  float ejv, dummy;
+  star_mul_MJ<NL, NR, false, true>(w, Mr, Mc, myqvel, dummy, ejv);
+  if (lane < M.nedge) {
+    int c = lane >> 2;
+    int k = M.con_pair[c];
+    float pos = cdist[c] - (m.pair_margin[k] - m.pair_gap[k]);
+    if (pos < 0.f) {
+      int b1 = m.geom_bodyid[m.pair_geom1[k]], b2 = m.geom_bodyid[m.pair_geom2[k]];
+      float mu = m.pair_friction[k][0];
+      float t = m.body_invweight0[b1] + m.body_invweight0[b2];
+      float iw = (t + mu * mu * t) * 2.f * mu * mu / m.impratio;
+      float k_, b_, imp;
+      kbi(m.timestep, m.pair_solref[k], m.pair_solimp[k], pos, k_, b_, imp);
+      float Rr_ = fmaxf(iw * (1.f - imp) / imp, DIAL_MINVAL);
+      S.e_D = 1.f / Rr_;
+      S.e_aref = -b_ * ejv - k_ * imp * pos;
+    }
+  }
+  // ---- 9. qacc_smooth and the Newton solve (mjx solver.solve), one factor/solve site ------
+  if (w.midsync) cta_sync();
+  const float scale = m.meaninertia * (float)(nv > 1 ? nv : 1);
+  const float mywarm = isdof ? warm[d] : 0.f;
+  float g = S.qfs;
+#pragma unroll
+  for (int a = 0; a < NR; ++a) Rr[a] = Mr[a];
+#pragma unroll
+  for (int q = 0; q < NL; ++q) Rc[q] = Mc[q];
+  int phase = 0, it = 0;
+  while (true) {
+    float x = star_solve2<NL, NR>(w, Rr, Rc, g);
+    if (phase == 0) {
+      S.qas = x;
+      if (M.nedge == 0 && M.nlimited == 0) { S.qacc = x; break; }
+      float Maw, eJw, eJs;
+      star_mul_MJ<NL, NR, true, true>(w, Mr, Mc, mywarm, Maw, eJw);
+      star_mul_MJ<NL, NR, false, true>(w, Mr, Mc, S.qas, dummy, eJs);
+      eJw -= S.e_aref; eJs -= S.e_aref;
+      float lJw = S.l_sign * mywarm - S.l_aref;
+      float gw = (Maw - S.qfs) * (mywarm - S.qas);
+      float cw = ((lJw < 0.f) ? S.l_D * lJw * lJw : 0.f) + ((eJw < 0.f) ? S.e_D * eJw * eJw : 0.f);
+      float Mas = S.qfs;
+      float lJs = S.l_sign * S.qas - S.l_aref;
+      float cs = ((lJs < 0.f) ? S.l_D * lJs * lJs : 0.f) + ((eJs < 0.f) ? S.e_D * eJs * eJs : 0.f);
+      warp_sum3(gw, cw, cs);
+      const bool usewarm = (0.5f * cw + 0.5f * gw) < (0.5f * cs);
+      S.qacc = usewarm ? mywarm : S.qas;
+      S.Ma = usewarm ? Maw : Mas;
+      S.e_Jaref = usewarm ? eJw : eJs;
+      S.l_Jaref = usewarm ? lJw : lJs;
+      S.cost = INFINITY;
+      S.prev_cost = 0.f;
+    } else {
+      S.search = -x;
+      float mv, e_jv;
+      star_mul_MJ<NL, NR, true, true>(w, Mr, Mc, S.search, mv, e_jv);
+      linesearch_core(w, S, mv, e_jv);
+      ++it;
+    }
+    star_update_constraint<NL, NR>(w, S);
+    bool done = (phase == 1) && (it >= m.iterations);
+    if (m.iterations != 1 || phase == 1) {
+      float improvement = (S.prev_cost - S.cost) / scale;
+      float gradient = sqrtf(S.gradnorm2) / scale;
+      if (m.iterations != 1) done = done || (improvement < m.tolerance) || (gradient < m.tolerance);
+    }
+    if (done) break;
+    phase = 1;
+    star_build_H<NL, NR>(w, S, Mr, Mc, Rr, Rc);
+    g = S.grad;
+  }
+  qacc = S.qacc;
+  qacc_int = qacc;
   } else {
   // ---- 8. constraint rows ----------------------------------------------------------------
   // contact Jacobian, compact along the chain of the contact body's last dof (lane = dof)
   if (isdof) {
-    V3 ca_ = ld3(cdof + 6 * d), cl_ = ld3(cdof + 6 * d + 3);
+    V3 ca_ = v3(mycdof[0], mycdof[1], mycdof[2]), cl_ = v3(mycdof[3], mycdof[4], mycdof[5]);
     int rootb = M.body_rootidx[m.dof_bodyid[d]];
     V3 rc = ld3(rcom + 3 * rootb);
     for (int c = 0; c < m.ncon; ++c) {
@@ -1940,7 +2505,56 @@ DEV BaseKin base_kin(WarpCtx& w, int bid) {
 #include DIAL_CUSTOM_REWARD_FILE
 #endif
 
-DEV float reward_lane0(WarpCtx& w, int step, int& stage) {
+// Per-foot / per-contact terms of the built-in rewards, one lane each (lanes 0..3), summed into
+// lane 0 by two xor-shuffles: [0] gait term (walk envs) or contact bonus (seq-jump), [1] penalty.
+DEV void reward_partials(WarpCtx& w, int step, int stage, float& p0, float& p1) {
+  const DevModel& M = *w.M;
+  const dial_plan_desc& c = w.P->c;
+  const dial_model_desc& m = M.m;
+  const float stepf = (float)step;
+  const int f = w.lane;
+  p0 = 0.f; p1 = 0.f;
+  if (c.env_id == DIAL_ENV_GO2_WALK || c.env_id == DIAL_ENV_H1_WALK || c.env_id == DIAL_ENV_H1_LOCO) {
+    if (f < c.nfeet) {
+      float zt = foot_step(c.gait_duty, c.gait_cadence, c.gait_amplitude, c.gait_phase[f], stepf * c.dt);
+      float z;
+      if (c.env_id == DIAL_ENV_GO2_WALK) {
+        int sid = c.feet_site[f], sb = m.site_bodyid[sid];
+        const float* X = SM(xmat) + 9 * sb;
+        z = SM(xpos)[3 * sb + 2] + X[6] * m.site_pos[sid][0] + X[7] * m.site_pos[sid][1] + X[8] * m.site_pos[sid][2];
+        float e = (zt - z) / 0.05f;
+        p0 = -e * e;
+      } else if (c.env_id == DIAL_ENV_H1_WALK) {
+        z = fminf(SM(cdist)[2 * f], SM(cdist)[2 * f + 1]);
+        p0 = -(zt - z) * (zt - z);
+      } else {   // H1 loco: two capsules (4 contacts) per foot
+        z = fminf(fminf(SM(cdist)[4 * f], SM(cdist)[4 * f + 1]), fminf(SM(cdist)[4 * f + 2], SM(cdist)[4 * f + 3]));
+        p0 = -(zt - z) * (zt - z);
+      }
+    }
+  } else if (c.env_id == DIAL_ENV_GO2_SEQJUMP) {
+    if (f < 4) {
+      const int i = f;
+      float dist = SM(cdist)[i];
+      bool penal = dist <= 0.001f;
+      float px = SM(cpos)[3 * i], py = SM(cpos)[3 * i + 1];
+      for (int j = 0; j < c.n_stage; ++j) {
+        float dx = px - c.contact_targets[j][i][0], dyy = py - c.contact_targets[j][i][1];
+        bool cond = dx * dx + dyy * dyy <= c.contact_radius[j][i] * c.contact_radius[j][i];
+        if (cond && j == stage) p0 += fminf(fmaxf(1.f - dist, 0.f), 1.f);
+        penal = penal && !cond;
+      }
+      p1 = penal ? 1.f : 0.f;
+    }
+  } else {
+    return;   // Allegro / custom: nothing per foot (warp-uniform: no shuffles needed)
+  }
+  // lanes 0..3 -> lane 0 in the fixed order ((0+1)+(2+3)): the same sum on every lane that needs it
+  p0 += shfl_xor(p0, 1); p1 += shfl_xor(p1, 1);
+  p0 += shfl_xor(p0, 2); p1 += shfl_xor(p1, 2);
+}
+
+DEV float reward_lane0(WarpCtx& w, int step, int& stage, float part0, float part1) {
   const DevModel& M = *w.M;
   const dial_plan_desc& c = w.P->c;
   const dial_model_desc& m = M.m;
@@ -1978,24 +2592,7 @@ DEV float reward_lane0(WarpCtx& w, int step, int& stage) {
     float ramp = stepf * c.dt / c.ramp_up_time;
     float vtx = fminf(c.vel_cmd[0] * ramp, c.vel_cmd[0]), vty = fminf(c.vel_cmd[1] * ramp, c.vel_cmd[1]);
     float atz = fminf(c.ang_cmd[2] * ramp, c.ang_cmd[2]);
-    float r_gaits = 0.f;
-    for (int f = 0; f < c.nfeet; ++f) {
-      float zt = foot_step(c.gait_duty, c.gait_cadence, c.gait_amplitude, c.gait_phase[f], stepf * c.dt);
-      float z;
-      if (c.env_id == DIAL_ENV_GO2_WALK) {
-        int sid = c.feet_site[f], sb = m.site_bodyid[sid];
-        const float* X = SM(xmat) + 9 * sb;
-        z = SM(xpos)[3 * sb + 2] + X[6] * m.site_pos[sid][0] + X[7] * m.site_pos[sid][1] + X[8] * m.site_pos[sid][2];
-        float e = (zt - z) / 0.05f;
-        r_gaits -= e * e;
-      } else if (c.env_id == DIAL_ENV_H1_WALK) {
-        z = fminf(SM(cdist)[2 * f], SM(cdist)[2 * f + 1]);
-        r_gaits -= (zt - z) * (zt - z);
-      } else {   // H1 loco: two capsules (4 contacts) per foot
-        z = fminf(fminf(SM(cdist)[4 * f], SM(cdist)[4 * f + 1]), fminf(SM(cdist)[4 * f + 2], SM(cdist)[4 * f + 3]));
-        r_gaits -= (zt - z) * (zt - z);
-      }
-    }
+    const float r_gaits = part0;   // per-foot terms: reward_partials
     float yaw_tar = 0.f + atz * c.dt * stepf;
     float dyaw = quat_yaw(bk.rot) - yaw_tar;
     // atan2(sin d, cos d) == d wrapped to (-pi, pi]
@@ -2028,19 +2625,7 @@ DEV float reward_lane0(WarpCtx& w, int step, int& stage) {
     float r_pos = -dot(dp, dp);
     float dy = quat_yaw(bk.rot) - c.yaw_seq[stage];
     float r_yaw = -dy * dy;
-    float r_contact = 0.f, pen = 0.f;
-    for (int i = 0; i < 4; ++i) {
-      float dist = SM(cdist)[i];
-      bool penal = dist <= 0.001f;
-      float px = SM(cpos)[3 * i], py = SM(cpos)[3 * i + 1];
-      for (int j = 0; j < c.n_stage; ++j) {
-        float dx = px - c.contact_targets[j][i][0], dyy = py - c.contact_targets[j][i][1];
-        bool cond = dx * dx + dyy * dyy <= c.contact_radius[j][i] * c.contact_radius[j][i];
-        if (cond && j == stage) r_contact += fminf(fmaxf(1.f - dist, 0.f), 1.f);
-        penal = penal && !cond;
-      }
-      pen += penal ? 1.f : 0.f;
-    }
+    const float r_contact = part0, pen = part1;   // per-contact terms: reward_partials
     rew = r_pos + r_upright + 0.3f * r_yaw + 0.1f * r_contact - 0.1f * pen + 10.f;
     int ns = (int)floorf((float)(step + 1) * c.dt / c.jump_dt);
     stage = ns < c.n_stage - 1 ? ns : c.n_stage - 1;
@@ -2075,6 +2660,23 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
 #pragma unroll
     for (int i = 0; i < DIAL_MAXCHAIN; ++i)
       if (i < w.nch) w.chain[i] = M.chain_tab[lane][i];
+  }
+  // star layout: lane constants, and the scratch zeroed once (padding slots are never written again)
+  w.s_pos = 0; w.s_col = 0; w.s_cb = 0; w.s_chain = -2; w.s_depth = 0; w.s_top = 0; w.s_conmask = 0u; w.e_cb = 0;
+  if constexpr (NL > 0) {
+    using SD = StarDims<NL, NR>;
+    w.s_cb = SD::NRP; w.e_cb = SD::NRP;
+    if (lane < nv) {
+      w.s_pos = M.s_pos[lane]; w.s_chain = M.s_chain[lane]; w.s_depth = M.s_depth[lane];
+      if (w.s_chain >= 0) { w.s_cb = SD::NRP + w.s_chain * SD::CS; w.s_col = SD::NRP + w.s_depth; w.s_top = M.s_top[w.s_chain]; }
+      else w.s_col = w.s_depth;
+      for (int c = 0; c < m.ncon; ++c)
+        if (w.s_chain < 0 || M.s_con_chain[c] == w.s_chain) w.s_conmask |= 1u << c;
+    }
+    if (lane < M.nedge) { const int cc = M.s_con_chain[lane >> 2]; if (cc >= 0) w.e_cb = SD::NRP + cc * SD::CS; }
+    const int nz = 2 * M.s_npos * SD::RS + M.nedge * SD::RS + M.s_npos + 8;   // Ms, Hs, Js, xs are contiguous
+    for (int i = lane; i < nz; i += 32) SM(Ms)[i] = 0.f;
+    for (int i = lane; i < 32; i += 32) SM(frow)[i] = 0.f;
   }
   // initial state + world body constants
   for (int i = lane; i < nq; i += 32) SM(qpos)[i] = A.qpos0[i];
@@ -2148,8 +2750,9 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     syncwarp();
     for (int f = 0; f < nfr; ++f) physics_step<NL, NR>(w, !fwd_only);
     if (fwd_only) break;
-    float rew = 0.f;
-    if (lane == 0) rew = reward_lane0(w, step, stage);
+    float rew = 0.f, part0, part1;
+    reward_partials(w, step, stage, part0, part1);
+    if (lane == 0) rew = reward_lane0(w, step, stage, part0, part1);
     stage = shfl_i(stage, 0);
     step += 1;
     rsum += rew;
@@ -2161,6 +2764,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     if (A.xpos) for (int i = lane; i < 3 * (nb - 1); i += 32) A.xpos[rt * 3 * (nb - 1) + i] = SM(xpos)[3 + i];
   }
   if (A.rews && lane == 0 && !fwd_only) A.rews[row] = rsum / (float)A.H;
+#ifndef DIAL_NO_XCH
   if (A.xch_world > 1 && lane == 0 && !fwd_only && A.mode == 1) {
     // sample rows go to every rank's mailbox at their GLOBAL index; the mean row (rolled by every
     // rank, bitwise identical) only to the local one
@@ -2172,6 +2776,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     for (int p = 0; p < A.xch_world; ++p)
       if (sample || p == A.xch_rank) A.xch_mbox[p][slot] = val;
   }
+#endif
   if (row == 0) {
     if (A.qpos_out) for (int i = lane; i < nq; i += 32) A.qpos_out[i] = SM(qpos)[i];
     if (A.qvel_out) for (int i = lane; i < nv; i += 32) A.qvel_out[i] = SM(qvel)[i];

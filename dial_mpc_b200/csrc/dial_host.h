@@ -44,6 +44,35 @@ static inline void derive_star(const dial_model_desc& m, DevModel& D) {
   D.star_nroot = nroot; D.star_nchain = nchain;
 }
 
+// which solver instantiation fits the model: 1 = star<3,6>, 2 = star<5,7>, 4 = star<5,6>, 0 = generic tree
+static inline int star_variant(const DevModel& D);
+
+// Star layout tables (see DevModel): only for models that map to a star instantiation and whose
+// contact bodies are each moved by the root chain plus at most one hanging chain.
+static inline void derive_star_layout(const dial_model_desc& m, DevModel& D) {
+  D.s_on = 0;
+  if (D.dense) return;
+  const int v = star_variant(D);
+  if (v != 1 && v != 2 && v != 4) return;
+  const int NL = v == 1 ? 3 : 5, NR = v == 2 ? 7 : 6;
+  D.s_nrp = (NR + 3) & ~3; D.s_cs = (NL + 3) & ~3; D.s_rs = D.s_nrp + D.s_cs;
+  D.s_npos = D.s_nrp + 4 * D.s_cs;
+  for (int i = 0; i < m.nv; ++i) { D.s_pos[i] = 0; D.s_chain[i] = -1; D.s_depth[i] = 0; }
+  for (int a = 0; a < D.star_nroot; ++a) { const int d = D.star_root[a]; D.s_pos[d] = a; D.s_chain[d] = -1; D.s_depth[d] = a; }
+  for (int l = 0; l < D.star_nchain; ++l) {
+    const int len = D.star_len[l], leaf = D.star_leaf[l];
+    const int top = D.chain_tab[leaf][len - 1];
+    if (top + len - 1 != leaf) return;              // chain dofs must be contiguous (depth-first order)
+    D.s_top[l] = top;
+    for (int q = 0; q < len; ++q) { D.s_pos[top + q] = D.s_nrp + l * D.s_cs + q; D.s_chain[top + q] = l; D.s_depth[top + q] = q; }
+  }
+  for (int c = 0; c < m.ncon; ++c) {
+    const int last = D.con_lastdof[c];
+    D.s_con_chain[c] = D.s_chain[last];           // -1: the body hangs off the root chain itself
+  }
+  D.s_on = 1;
+}
+
 static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::string& err) {
   memset(&D, 0, sizeof(D));
   D.m = m;
@@ -182,18 +211,30 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   if (c != m.ncon) { err = "pair_ncon does not sum to ncon"; return false; }
   if (!D.dense) derive_star(m, D);
   D.nedge = D.dense ? 0 : 4 * m.ncon;
+  derive_star_layout(m, D);
   // per-warp slab layout
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   D.o_xpos = take(3 * nb); D.o_xquat = take(4 * nb); D.o_xmat = take(9 * nb); D.o_xipos = take(3 * nb);
-  D.o_cinert = take(10 * nb); D.o_cdof = take(6 * nv); D.o_cdofdot = take(6 * nv);
+  D.o_cinert = take(CIS * nb); D.o_cdof = take(CDS * nv); D.o_cdofdot = take(CDS * nv);
   D.o_cvel = take(6 * nb); D.o_cacc = take(6 * nb); D.o_cfrc = take(6 * nb);
-  // compact-chain M / factor / contact rows and the published solve chains: tree paths only
-  if (!D.dense) { D.o_Mb = take(nv * DIAL_MAXCHAIN); D.o_L = take(nv * DIAL_MAXCHAIN); D.o_J = take(D.nedge * DIAL_MAXCHAIN); }
-  else { D.o_Mb = D.o_L = D.o_J = 0; }
+  // compact-chain M / factor / contact rows and the published solve chains: tree paths only.  The
+  // star layout (Ms, Hs, Js, xs) overlays the same block: a launch runs one solver or the other.
+  if (!D.dense) {
+    const int base = o;
+    D.o_Mb = take(nv * DIAL_MAXCHAIN); D.o_L = take(nv * DIAL_MAXCHAIN); D.o_J = take(D.nedge * DIAL_MAXCHAIN);
+    D.o_xch = take(nv * DIAL_MAXCHAIN);
+    const int generic_end = o;
+    o = base;
+    if (D.s_on) {
+      D.o_Ms = take(D.s_npos * D.s_rs); D.o_Hs = take(D.s_npos * D.s_rs); D.o_Js = take(D.nedge * D.s_rs);
+      D.o_xs = take(D.s_npos + 8);
+    }
+    o = o > generic_end ? o : generic_end;
+  } else { D.o_Mb = D.o_L = D.o_J = D.o_xch = 0; }
   D.o_qpos = take(m.nq); D.o_qvel = take(nv); D.o_warm = take(nv); D.o_ctrl = take(m.nu);
   D.o_vec = take(32); D.o_frow = take(32); D.o_cpos = take(3 * m.ncon); D.o_cframe = take(9 * m.ncon);
-  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_xch = D.dense ? 0 : take(nv * DIAL_MAXCHAIN); D.o_crb = take(10 * nb); D.o_cfs = take(6 * nb);
+  D.o_cdist = take(m.ncon); D.o_rcom = take(3 * 4); D.o_crb = take(CIS * nb); D.o_cfs = take(6 * nb);
   if (D.dense) {
     // Jd: packed columns (jd_stride); Gd: G rows of one contact at a time (6 x nv); hcs (6x6 cone
     // Hessian) overlays vec|frow (64 contiguous floats, idle while H is assembled).
@@ -205,7 +246,6 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
   return true;
 }
 
-// which solver instantiation fits the model: 1 = star<3,6>, 2 = star<5,7>, 0 = generic tree
 static inline int star_variant(const DevModel& D) {
   if (D.dense) return D.m.nv == 22 ? 3 : -1;   // dense path is instantiated for nv = 22 (Allegro)
   if (D.star_nchain >= 1 && D.star_nchain <= 4) {

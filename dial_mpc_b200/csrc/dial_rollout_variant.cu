@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(DIAL_MAXTHREADS, 1) rollout_kernel(const DevMo
     row = A.nrows - 1;  // lock-step CTAs need every warp at the barriers: duplicate the last row (benign)
   }
   if (active) rollout_warp<NL, NR>(sM, sP, slab, A, row, lane);
+#ifndef DIAL_NO_XCH
   if (A.xch_world > 1) {
     // reward exchange epilogue: the rows of this CTA are in every rank's mailbox (peer stores over
     // NVLink); the last CTA of the grid publishes them by raising this rank's flag everywhere
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(DIAL_MAXTHREADS, 1) rollout_kernel(const DevMo
       }
     }
   }
+#endif
 }
 
 #define DIAL_CAT2(a, b) a##b

@@ -7,8 +7,13 @@ the reference, dial_plan.py:92-134 / dial_sim.py:84-123), shifts the plan by the
 with the node spline, runs the annealed ``reverse_once`` scan and publishes joint targets,
 torques and reference positions.  Reference quirks kept on purpose: the
 deploy schedule has no ``sigma_control`` factor (:199-209), the first call runs
-``Ndiffuse_init`` and then ``Ndiffuse`` iterations (:195-212), and the planner state is built
-without ``mjx.forward`` (qacc_warmstart = 0, :45-61,141-155).
+``Ndiffuse_init`` and then ``Ndiffuse`` iterations (:195-212), the planner state is built
+without ``mjx.forward`` (qacc_warmstart = 0, :45-61,141-155), and ``update_mjx_state`` refreshes
+only ``info["step"]`` (:149-155; a seq-jump ``contact_stage`` is advanced by the rollouts).
+
+One planning cycle is ONE CUDA-graph launch (``DeviceLoop(env_step=False)`` -> C ABI
+``dial_mpc_step``): the host writes the state and the time-shifted knots into the bound device
+buffers (one small H2D each), launches, and reads back the knots and the ``xbar`` reference.
 """
 from __future__ import annotations
 
@@ -26,7 +31,7 @@ import yaml
 import dial_mpc_b200.envs as dial_envs
 from dial_mpc_b200 import random as drandom
 from dial_mpc_b200.core.dial_config import DialConfig
-from dial_mpc_b200.core.dial_core import MBDPI
+from dial_mpc_b200.core.dial_core import DeviceLoop, MBDPI
 from dial_mpc_b200.envs.base_env import PipelineState, State
 from dial_mpc_b200.utils.io_utils import get_example_path, load_dataclass_from_dict
 from dial_mpc_b200.utils.spline import interp_matrix
@@ -51,6 +56,7 @@ class MBDPublisher:
         self.rng = drandom.PRNGKey(seed=self.dial_config.seed)
         dev = self.mbdpi.device
         self.Y = torch.zeros(self.dial_config.Hnode + 1, self.mbdpi.nu, device=dev)
+        self._loop = None      # DeviceLoop, created with the first state
         self.ctrl_dt = env_config.dt
         self.timer_period = env_config.dt
         self.n_acts = self.dial_config.Hsample + 1
@@ -94,15 +100,20 @@ class MBDPublisher:
         return State(ps, None, 0.0, 0.0, {}, dict(base.info))
 
     def update_mjx_state(self, state: State, q, qd, t) -> State:
+        """dial_plan.py:149-155: new qpos / qvel, ``info["step"] = int(t / ctrl_dt)``, nothing else."""
         dev = self.mbdpi.device
         f = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32), device=dev)
         ps = PipelineState(f(q), f(qd), state.pipeline_state.qacc_warmstart)
         info = state.info
         info["step"] = int(t / self.ctrl_dt)
-        if hasattr(self.env, "_next_info") and "contact_stage" in info:
-            n = len(info["contact_targets"])
-            info["contact_stage"] = int(min(np.floor(info["step"] * self.env.dt / self.env._config.jump_dt), n - 1))
         return State(ps, None, state.reward, state.done, state.metrics, info)
+
+    def deploy_factors(self, n: int) -> torch.Tensor:
+        """``traj_diffuse_factor ** arange(n)[:, None]`` (dial_plan.py:199-209: no sigma_control),
+        broadcast over the Hnode+1 knots."""
+        cfg, dev = self.dial_config, self.mbdpi.device
+        return ((cfg.traj_diffuse_factor ** torch.arange(n, device=dev, dtype=torch.float32))[:, None]
+                * torch.ones(cfg.Hnode + 1, device=dev)[None, :]).contiguous()
 
     # ---- one planning cycle (body of the reference's `while True`, dial_plan.py:172-229) ------------
     def plan_once(self) -> dict:
@@ -123,17 +134,22 @@ class MBDPublisher:
             self.Y = self.Y * 0.0
         else:
             self.Y = self.shift(self.Y, shift_time)
-        dev = self.mbdpi.device
-        ones = torch.ones(cfg.Hnode + 1, device=dev)
-
-        def deploy_factors(n):   # traj_diffuse_factor ** arange(n)[:, None], broadcast over the nodes
-            return (cfg.traj_diffuse_factor ** torch.arange(n, device=dev, dtype=torch.float32))[:, None] * ones[None, :]
+        if self._loop is None:
+            nmax = max(cfg.Ndiffuse, cfg.Ndiffuse_init)
+            self._loop = DeviceLoop(self.mbdpi, state, self.rng, self.Y, n_diffuse_max=nmax, noise=self.deploy_factors(nmax))
+        loop = self._loop
+        ps = state.pipeline_state
+        loop.set_state(ps.qpos, ps.qvel, ps.qacc_warmstart, step=state.info["step"])
+        loop.buf["Y"].copy_(self.Y)
         if self._first_time:
             self._first_time = False
-            self.rng, self.Y, info = self.mbdpi.reverse_scan(state, self.rng, self.Y, deploy_factors(cfg.Ndiffuse_init))
-        self.rng, self.Y, info = self.mbdpi.reverse_scan(state, self.rng, self.Y, deploy_factors(cfg.Ndiffuse))
+            loop.step(cfg.Ndiffuse_init, env_step=False)
+        loop.step(cfg.Ndiffuse, env_step=False)
+        self.Y = loop.Y.clone()
+        info = loop.info()
         x_targets = info["xbar"][:, 1:, :3]                      # [Hs+1, nbody-2, 3]
-        us = self.mbdpi.node2u_vmap(self.Y).cpu().numpy()         # [Hs+1, nu]
+        us = self.mbdpi.node2u_vmap(self.Y).cpu().numpy()         # [Hs+1, nu]   (D2H: synchronises)
+        self.rng = loop.rng_host()
         joint_targets = np.stack([self.env.act2joint(u) for u in us])
         taus = np.stack([self.env.act2tau(u, state.pipeline_state) for u in us])
         self.acts_shared[: joint_targets.shape[0], :] = joint_targets

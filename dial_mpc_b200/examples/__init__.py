@@ -6,3 +6,9 @@ examples = [
     "allegro_reorient",
     "unitree_h1_loco",
 ]
+# deploy (dial-mpc-plan) configurations of the reference's examples directory
+deploy_examples = [
+    "unitree_go2_trot_deploy",
+    "unitree_go2_seq_jump_deploy",
+    "unitree_h1_loco_deploy",
+]

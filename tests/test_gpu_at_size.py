@@ -113,6 +113,7 @@ def test_reverse_once_at_baseline_size(built, ci):
                outliers=[dict(row=int(rows[i]), err=float(err[i]), oracle_sensitivity=float(sens[i]))
                          for i in np.nonzero(~tight)[0][:20]])
     # per-step quantities of the explicit launch
+    failures = []
     for key, g, on, op, tol, rel in (("rewss", rg[rows], ro, rs, 2e-3, True), ("q", qg[rows], qo, qs, 2e-4, False),
                                       ("qd", qdg[rows], qdo, qds, 1e-2, False), ("xpos", xg[rows], xo, xs, 2e-4, False)):
         bud_k, sens_k = budget(tol, on, op, rel)
@@ -125,8 +126,23 @@ def test_reverse_once_at_baseline_size(built, ci):
         rep[key]["rows_leaving_tolerance"] = int(bad.any(1).sum())
         if bad.any():
             rep[key]["first_divergence_step_min"] = int(np.min([np.argmax(r) for r in bad if r.any()]))
-        assert (e <= bud_k).all(), (key, rep[key])
+            rep[key]["rows"] = [dict(row=int(rows[i]), first_step=int(np.argmax(bad[i])),
+                                     err_by_step=[float(v) for v in e[i].reshape(e.shape[1], -1).max(-1)],
+                                     yardstick_by_step=[float(v) for v in sens_k[i].reshape(e.shape[1], -1).max(-1)])
+                                for i in np.nonzero(bad.any(1))[0][:8]]
+        over = ~(e <= bud_k)
+        rep[key]["elements_over_budget"] = int(over.sum())
+        if over.any():
+            failures.append((key, rep[key]["rows_leaving_tolerance"], rep[key]["err_max"]))
     _report(f"reverse_once_cfg{ci}", rep)
+    if failures:      # keep what is needed to replay the offending rows on the CPU (emulator / oracle)
+        try:
+            np.savez_compressed(os.path.join(ROOT, "gpurun_out", "parity", f"replay_cfg{ci}.npz"), qpos=sq, qvel=sv, warm=sw,
+                                step=step, stage=stage, rows=rows, us=us, gpu_rewss=rg[rows], gpu_q=qg[rows], ora_rewss=ro, ora_q=qo,
+                                yard_rewss=rs, yard_q=qs)
+        except OSError:
+            pass
+    assert not failures, (failures, rep)
     assert (err <= bud).all(), rep
     # the large majority of rows must not need the yardstick at all
     assert tight.mean() >= (0.95 if name != "allegro_reorient" else 0.6), rep

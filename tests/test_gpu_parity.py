@@ -274,27 +274,76 @@ print("GENERIC_OK")
 
 def test_deploy_planner_cycle_over_shared_memory(built):
     """the async planner (deploy/dial_plan.py) attached to the reference's six shm
-    segments: one planning cycle publishes finite joint targets / torques / refs and time-shifts."""
+    segments, two planning cycles 20.5 ms apart, against the ORACLE planner fed with the same
+    Threefry noise (jax.random restatement): joint targets, torques and reference positions
+    published to shm.  Reference: dial_mpc/deploy/dial_plan.py:136-139,172-229."""
+    from scipy.interpolate import InterpolatedUnivariateSpline
     from dial_mpc_b200.core.dial_config import DialConfig
     from dial_mpc_b200.deploy.dial_plan import MBDPublisher
+    from oracle.envs_oracle import OState, make_env
+    from oracle.planner_oracle import PlannerOracle, jax_normal_legacy, jax_split_legacy
     import dial_mpc_b200.envs as E
     cfg = DialConfig(env_name="unitree_go2_walk", Nsample=256, Hsample=16, Hnode=4, Ndiffuse=1, Ndiffuse_init=2,
-                     temp_sample=0.05)
+                     temp_sample=0.05, seed=0)
     ecfg = E.UnitreeGo2EnvConfig(default_vx=0.8, ramp_up_time=1.0)
     env = E.get_environment(cfg.env_name, config=ecfg)
+    o = make_env(cfg.env_name, dict(default_vx=0.8, ramp_up_time=1.0))
+    N, Hs, Hn, nu = cfg.Nsample, cfg.Hsample, cfg.Hnode, 12
+    po = PlannerOracle(o, N, Hs, Hn, cfg.temp_sample, cfg.horizon_diffuse_factor, cfg.traj_diffuse_factor)
+
+    def oracle_cycle(state, rng, Y, n_list):
+        info = None
+        for n in n_list:
+            for i in range(n):
+                sub = jax_split_legacy((int(rng[0]), int(rng[1])))
+                rng, key = sub[0], sub[1]
+                eps = jax_normal_legacy((int(key[0]), int(key[1])), (N, Hn + 1, nu))
+                Y, info = po.reverse_once(state, eps, Y, cfg.traj_diffuse_factor ** i * np.ones(Hn + 1))   # no sigma_control
+        return rng, Y, info
+
+    def published(state, Y, info):
+        us = po.node2u(Y)
+        acts = np.stack([o.act2joint(u) for u in us])
+        taus = np.stack([o.act2tau(u[None], state.qpos, state.qvel)[0] for u in us])
+        return acts, taus, info["xbar"][:, 1:, :3]
+
     pub = MBDPublisher(env, ecfg, cfg, create_shm=True)      # the test plays the simulator's role
     try:
         assert pub.acts_shared.shape == (17, 12) and pub.refs_shared.shape == (17, 12, 3)
         assert pub._shm["state_shm"].size >= 37 * 32
-        out = pub.plan_once()
-        assert np.isfinite(pub.acts_shared).all() and np.isfinite(pub.tau_shared).all()
-        assert np.isfinite(pub.refs_shared).all() and pub.plan_time_shared[0] == 0.0
+        # ---- cycle 1 at t = 0 from the home keyframe: Ndiffuse_init then Ndiffuse iterations ----------
+        pub.plan_once()
+        q0 = np.asarray(pub.default_q, dtype=np.float64)
+        s0 = OState(q0[None], np.zeros((1, 18)), np.zeros((1, 18)), np.array([0]), np.array([0]))   # warm-start 0: no mjx.forward
+        rng, Yo, io = oracle_cycle(s0, (0, cfg.seed), np.zeros((Hn + 1, nu)), [cfg.Ndiffuse_init, cfg.Ndiffuse])
+        acts, taus, refs = published(s0, Yo, io)
+        assert pub.plan_time_shared[0] == 0.0
+        assert np.abs(pub.Y.cpu().numpy() - Yo).max() < 1e-2
+        assert np.abs(pub.acts_shared - acts).max() < 1e-2
+        assert np.abs(pub.tau_shared - taus).max() < 0.5            # kp = 30: 1e-2 rad of target
+        assert np.abs(pub.refs_shared - refs).max() < 5e-3
+        assert np.array_equal(np.asarray(pub.rng, dtype=np.uint32), np.asarray(rng, dtype=np.uint32))
         lo, hi = env.physical_joint_range[:, 0], env.physical_joint_range[:, 1]
         assert (pub.acts_shared >= lo - 1e-5).all() and (pub.acts_shared <= hi + 1e-5).all()
+        # ---- cycle 2: the simulator advanced 20.5 ms (int(t / dt) truncates like the reference) ----------
+        s1, _, _ = o.step(s0, Yo[0][None])
+        pub.state_shared[:19] = s1.qpos[0]
+        pub.state_shared[19:37] = s1.qvel[0]
+        pub.time_shared[0] = 0.0205
         Y_before = pub.Y.clone()
-        pub.time_shared[0] = 0.0205                              # the sim advanced (int(t / dt) truncates like the reference)
-        out2 = pub.plan_once()
+        pub.plan_once()
         assert pub.plan_time_shared[0] == np.float32(0.0205) and pub._state.info["step"] == 1
+        shift_time = float(np.float32(0.0205)) - 0.0
+        Ysh = np.stack([InterpolatedUnivariateSpline(po.step_nodes, Yo[:, a], k=2)(po.step_nodes + shift_time) for a in range(nu)], 1)
+        s1p = OState(s1.qpos.astype(np.float32).astype(np.float64), s1.qvel.astype(np.float32).astype(np.float64),
+                     np.zeros((1, 18)), np.array([1]), np.array([0]))
+        rng2, Yo2, io2 = oracle_cycle(s1p, rng, Ysh, [cfg.Ndiffuse])
+        acts2, taus2, refs2 = published(s1p, Yo2, io2)
+        assert np.abs(pub.Y.cpu().numpy() - Yo2).max() < 2e-2
+        assert np.abs(pub.acts_shared - acts2).max() < 2e-2
+        assert np.abs(pub.tau_shared - taus2).max() < 1.0
+        assert np.abs(pub.refs_shared - refs2).max() < 1e-2
+        assert np.array_equal(np.asarray(pub.rng, dtype=np.uint32), np.asarray(rng2, dtype=np.uint32))
         # shifting by one node period moves node k+1 onto node k (interpolating spline)
         sh = pub.shift(Y_before, pub.mbdpi.node_dt)
         assert torch.allclose(sh[:-1], Y_before[1:], atol=1e-5)
