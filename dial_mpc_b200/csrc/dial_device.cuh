@@ -90,11 +90,14 @@ struct alignas(16) DevModel {
   int32_t s_top[4];                   // first (top) dof of chain l; its dofs are s_top[l] + depth (depth-first order)
   int32_t s_con_chain[DIAL_MAXC];     // chain that moves the contact body (-1: root dofs only)
   int32_t o_Ms, o_Hs, o_Js, o_xs;     // star-layout scratch (overlays Mb / L / J / xch)
+  // the same star at body level (subtree sums): root bodies (deepest first) + one contiguous run of
+  // bodies per hanging chain; sb_on = 0: some body is outside this pattern (welded bodies, ...)
+  int32_t sb_on, sb_nroot, sb_root[4], sb_top[4], sb_len[4], sb_att[4];
   // per-warp shared-memory layout (float offsets)
   int32_t o_xpos, o_xquat, o_xmat, o_xipos, o_cinert, o_cdof, o_cdofdot, o_cvel, o_cacc,
       o_cfrc, o_Mb, o_L, o_J, o_qpos, o_qvel, o_warm, o_ctrl, o_vec, o_frow, o_cpos,
       o_cframe, o_cdist, o_rcom, o_xch, o_crb, o_cfs, o_Md, o_Ld, o_Jd, o_Gd, o_frow2, o_cact, o_hcs, warp_floats;
-  int32_t pad_[2];
+  int32_t pad_[1];
 };
 
 struct alignas(16) DevPlan {
@@ -1082,6 +1085,27 @@ DEV void star_update_constraint(WarpCtx& w, Solver& S) {
 
 struct LSPoint { float alpha, cost, d0, d1; };
 
+// All-reduce of 6 values per lane: reduce-scatter over the lane bits 16 / 8 (each lane keeps half
+// of its values and sends the other half), plain butterflies for the rest, then an all-gather —
+// 17 shuffles + 11 adds instead of 30 + 30.  Every lane ends with the same six sums.
+DEV void warp_allsum6(int lane, float* v) {
+  const bool b16 = (lane & 16) != 0, b8 = (lane & 8) != 0;
+  // xor 16: lanes with bit 16 clear keep (v0, v1, v2), the others (v3, v4, v5)
+  float u0 = b16 ? v[3] : v[0], u1 = b16 ? v[4] : v[1], u2 = b16 ? v[5] : v[2];
+  const float s0 = b16 ? v[0] : v[3], s1 = b16 ? v[1] : v[4], s2 = b16 ? v[2] : v[5];
+  u0 += shfl_xor(s0, 16); u1 += shfl_xor(s1, 16); u2 += shfl_xor(s2, 16);
+  // xor 8: of (u0, u1) keep one; u2 goes on as a plain butterfly
+  float t = b8 ? u1 : u0;
+  const float st = b8 ? u0 : u1;
+  t += shfl_xor(st, 8); u2 += shfl_xor(u2, 8);
+  t += shfl_xor(t, 4); u2 += shfl_xor(u2, 4);
+  t += shfl_xor(t, 2); u2 += shfl_xor(u2, 2);
+  t += shfl_xor(t, 1); u2 += shfl_xor(u2, 1);
+  // t: total of value (b16 ? 3 : 0) + (b8 ? 1 : 0); u2: total of value (b16 ? 5 : 2)
+  v[0] = shfl(t, 0); v[1] = shfl(t, 8); v[3] = shfl(t, 16); v[4] = shfl(t, 24);
+  v[2] = shfl(u2, 0); v[5] = shfl(u2, 16);
+}
+
 // Per-lane quadratic coefficients of the 1-D cost along the search direction (limit row of the
 // dof lane, pyramid edge row of the edge lane); constant during one line search.
 struct LSRow { float lq0, lq1, lq2, eq0, eq1, eq2; };
@@ -1091,7 +1115,7 @@ struct LSRow { float lq0, lq1, lq2, eq0, eq1, eq2; };
 // out (a third of the warp reductions); the costs of the points that survive are evaluated once
 // at the end with the same expressions, so the result equals MJX's, which carries them along.
 template <int NA, bool COST>
-DEV void ls_points(const Solver& S, const LSRow& K, float l_jv, float e_jv, const float* qg, const float* al, LSPoint* out) {
+DEV void ls_points(int lane, const Solver& S, const LSRow& K, float l_jv, float e_jv, const float* qg, const float* al, LSPoint* out) {
   float s[3 * NA];
 #pragma unroll
   for (int i = 0; i < 3 * NA; ++i) s[i] = 0.f;
@@ -1100,11 +1124,21 @@ DEV void ls_points(const Solver& S, const LSRow& K, float l_jv, float e_jv, cons
     if (S.l_Jaref + al[i] * l_jv < 0.f) { if (COST) s[3 * i] += K.lq0; s[3 * i + 1] += K.lq1; s[3 * i + 2] += K.lq2; }
     if (S.e_Jaref + al[i] * e_jv < 0.f) { if (COST) s[3 * i] += K.eq0; s[3 * i + 1] += K.eq1; s[3 * i + 2] += K.eq2; }
   }
+  if constexpr ((NA == 3 && !COST) || (NA == 2 && COST)) {
+    // six sums: transposed reduction
+    float v[6];
+    if constexpr (NA == 3) { v[0] = s[1]; v[1] = s[2]; v[2] = s[4]; v[3] = s[5]; v[4] = s[7]; v[5] = s[8]; }
+    else { v[0] = s[0]; v[1] = s[1]; v[2] = s[2]; v[3] = s[3]; v[4] = s[4]; v[5] = s[5]; }
+    warp_allsum6(lane, v);
+    if constexpr (NA == 3) { s[1] = v[0]; s[2] = v[1]; s[4] = v[2]; s[5] = v[3]; s[7] = v[4]; s[8] = v[5]; }
+    else { s[0] = v[0]; s[1] = v[1]; s[2] = v[2]; s[3] = v[3]; s[4] = v[4]; s[5] = v[5]; }
+  } else {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int i = 0; i < 3 * NA; ++i)
-      if (COST || (i % 3) != 0) s[i] += shfl_xor(s[i], o);
+      for (int i = 0; i < 3 * NA; ++i)
+        if (COST || (i % 3) != 0) s[i] += shfl_xor(s[i], o);
+    }
   }
 #pragma unroll
   for (int i = 0; i < NA; ++i) {
@@ -1132,9 +1166,9 @@ DEV void linesearch_core(WarpCtx& w, Solver& S, float mv, float e_jv) {
   K.eq0 = 0.5f * S.e_Jaref * S.e_Jaref * S.e_D; K.eq1 = e_jv * S.e_Jaref * S.e_D; K.eq2 = 0.5f * e_jv * e_jv * S.e_D;
   LSPoint p0, lo, hi;
   float a1[1] = {0.f};
-  ls_points<1, true>(S, K, l_jv, e_jv, qg, a1, &p0);
+  ls_points<1, true>(w.lane, S, K, l_jv, e_jv, qg, a1, &p0);
   a1[0] = p0.alpha - p0.d0 / p0.d1;
-  ls_points<1, false>(S, K, l_jv, e_jv, qg, a1, &lo);
+  ls_points<1, false>(w.lane, S, K, l_jv, e_jv, qg, a1, &lo);
   if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
   bool swap = true;
   for (int it = 0; it < M.m.ls_iterations; ++it) {
@@ -1144,7 +1178,7 @@ DEV void linesearch_core(WarpCtx& w, Solver& S, float mv, float e_jv) {
     if (done) break;
     LSPoint pt[3];
     float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
-    ls_points<3, false>(S, K, l_jv, e_jv, qg, a3, pt);
+    ls_points<3, false>(w.lane, S, K, l_jv, e_jv, qg, a3, pt);
     const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
     bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
     if (swap_lo_next) lo = lo_next;
@@ -1160,7 +1194,7 @@ DEV void linesearch_core(WarpCtx& w, Solver& S, float mv, float e_jv) {
   {
     LSPoint fin[2];
     float a2[2] = {lo.alpha, hi.alpha};
-    ls_points<2, true>(S, K, l_jv, e_jv, qg, a2, fin);
+    ls_points<2, true>(w.lane, S, K, l_jv, e_jv, qg, a2, fin);
     lo.cost = fin[0].cost; hi.cost = fin[1].cost;
   }
   bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
@@ -1915,7 +1949,11 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   float* qpos = SM(qpos); float* qvel = SM(qvel); float* warm = SM(warm); float* ctrl = SM(ctrl);
   float* cpos = SM(cpos); float* cframe = SM(cframe); float* cdist = SM(cdist); float* rcom = SM(rcom);
 
-  // ---- 1. kinematics (lane = body, level by level) ----------------------------------
+  // ---- 1. kinematics (lane = body) -----------------------------------------------------------
+  // Everything that does not depend on the parent is done for all bodies at once, before and after
+  // the level loop: the transform of the body w.r.t. its parent frame (joint rotation included)
+  //   quat = normalize(pq * qL), pos = ppos + rot(pq, pL), anchor = ppos + rot(pq, aL), axis = rot(pq, axL)
+  // and, afterwards, the rotation matrices and the inertial frame.  The loop only composes.
   const int b = lane;
   const bool isbody = b > 0 && b < nb;
   const int depth = isbody ? m.body_depth[b] : -1;
@@ -1925,44 +1963,60 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   float ximat[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) ximat[i] = 0.f;
+  Q4 qL; qL.w = 1.f; qL.x = qL.y = qL.z = 0.f;
+  V3 pL = v3(0, 0, 0), aL = v3(0, 0, 0), axL = v3(0, 0, 1);
+  if (isbody) {
+    const Q4 bq = ldq(m.body_quat[b]);
+    const V3 bp = ld3(m.body_pos[b]);
+    qL = bq; pL = bp;
+    if (jtype == JNT_HINGE || jtype == JNT_SLIDE) {
+      const int qa = m.jnt_qposadr[jid];
+      const V3 jp = ld3(m.jnt_pos[jid]), ja = ld3(m.jnt_axis[jid]);
+      aL = bp + qrot(bq, jp);
+      axL = qrot(bq, ja);
+      const float dq = qpos[qa] - m.qpos0[qa];
+      if (jtype == JNT_HINGE) {
+        qL = qmul(bq, axisangle(ja, dq));
+        pL = aL - qrot(qL, jp);
+      } else {
+        pL = bp + axL * dq;
+      }
+    }
+  }
+  V3 pos = v3(0, 0, 0);
+  Q4 quat; quat.w = 1.f; quat.x = quat.y = quat.z = 0.f;
   for (int lv = 1; lv <= M.maxdepth; ++lv) {
     if (depth == lv) {
-      int p = m.body_parentid[b];
-      Q4 pq = ldq(xquat + 4 * p);
-      V3 pos = ld3(xpos + 3 * p) + qrot(pq, ld3(m.body_pos[b]));
-      Q4 quat = qmul(pq, ldq(m.body_quat[b]));
       if (jtype == JNT_FREE) {
-        int qa = m.jnt_qposadr[jid];
+        const int qa = m.jnt_qposadr[jid];
         pos = ld3(qpos + qa);
         quat = qnormalize(ldq(qpos + qa + 3));
         stq(qpos + qa + 3, quat);
         anchor = pos;
         axis = v3(0, 0, 1);
-      } else if (jtype == JNT_HINGE || jtype == JNT_SLIDE) {
-        int qa = m.jnt_qposadr[jid];
-        V3 jp = ld3(m.jnt_pos[jid]), ja = ld3(m.jnt_axis[jid]);
-        anchor = qrot(quat, jp) + pos;
-        axis = qrot(quat, ja);
-        float dq = qpos[qa] - m.qpos0[qa];
-        if (jtype == JNT_HINGE) {
-          quat = qmul(quat, axisangle(ja, dq));
-          pos = anchor - qrot(quat, jp);
-        } else {
-          pos = pos + axis * dq;
-        }
+      } else {
+        const int p = m.body_parentid[b];
+        const Q4 pq = ldq(xquat + 4 * p);
+        const V3 pp = ld3(xpos + 3 * p);
+        quat = qmul(pq, qL);
+        pos = pp + qrot(pq, pL);
+        anchor = pp + qrot(pq, aL);
+        axis = qrot(pq, axL);
       }
       quat = qnormalize(quat);
       st3(xpos + 3 * b, pos);
       stq(xquat + 4 * b, quat);
-      float R[9];
-      qmat(quat, R);
-#pragma unroll
-      for (int i = 0; i < 9; ++i) xmat[9 * b + i] = R[i];
-      xip = pos + qrot(quat, ld3(m.body_ipos[b]));
-      st3(xipos + 3 * b, xip);
-      qmat(qmul(quat, ldq(m.body_iquat[b])), ximat);
     }
     syncwarp();
+  }
+  if (isbody) {
+    float R[9];
+    qmat(quat, R);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) xmat[9 * b + i] = R[i];
+    xip = pos + qrot(quat, ld3(m.body_ipos[b]));
+    st3(xipos + 3 * b, xip);
+    qmat(qmul(quat, ldq(m.body_iquat[b])), ximat);
   }
 
   // ---- 2. subtree COM of each tree root --------------------------------------------
@@ -2022,6 +2076,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   syncwarp();
 
   // ---- 4. velocities / accelerations down the tree, local RNE force ---------------------
+  float mycv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, myca[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int lv = 1; lv <= M.maxdepth; ++lv) {
     if (depth == lv) {
       int p = m.body_parentid[b];
@@ -2066,20 +2121,26 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
           ca[i] += dd[i] * qd;
         }
       }
-      float f1[6], f2[6], f3[6], cib[10];
-      ld10(cinert + CIS * b, cib);
-      inert_mul(cib, ca, f1);
-      inert_mul(cib, cv, f2);
-      mcross_force(cv, f2, f3);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         cvel[6 * b + i] = cv[i];
         cacc[6 * b + i] = ca[i];
-        cfrc[6 * b + i] = f1[i] + f3[i];
+        mycv[i] = cv[i]; myca[i] = ca[i];
       }
     }
     syncwarp();
   }
+  // local RNE force of every body at once (needs only the body's own velocity / acceleration)
+  if (isbody) {
+    float f1[6], f2[6], f3[6], cib[10];
+    ld10(cinert + CIS * b, cib);
+    inert_mul(cib, myca, f1);
+    inert_mul(cib, mycv, f2);
+    mcross_force(mycv, f2, f3);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) cfrc[6 * b + i] = f1[i] + f3[i];
+  }
+  syncwarp();
 
   // ---- 5. composite inertia and RNE force of every subtree ---------------------------------
   // Bodies are in depth-first order, so the subtree of b is the index range [b, b + ndesc_b].
@@ -2091,13 +2152,34 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
     const float* src = comp < 10 ? cinert + comp : cfrc + (comp - 10);
     const int stride = comp < 10 ? CIS : 6;
     float* dst = comp < 10 ? crb + comp : cfs + (comp - 10);
-    for (int b0 = 1; b0 < nb; b0 += 2) {
-      const int bb = b0 + half;
-      if (bb < nb) {
+    if (NL > 0 && M.sb_on) {
+      // star models: suffix sums along each hanging chain (half-warp h takes chains h and h + 2),
+      // then the root bodies, deepest first, collect their child root and the chains hanging off them
+      for (int l = half; l < M.star_nchain; l += 2) {
+        const int top = M.sb_top[l];
         float acc = 0.f;
-        const int last = bb + M.body_ndesc[bb];
-        for (int jb = bb; jb <= last; ++jb) acc += src[jb * stride];
-        dst[bb * stride] = acc;
+        for (int k = M.sb_len[l] - 1; k >= 0; --k) { acc += src[(top + k) * stride]; dst[(top + k) * stride] = acc; }
+      }
+      syncwarp();
+      if (half == 0) {
+        float below = 0.f;
+        for (int r = 0; r < M.sb_nroot; ++r) {
+          float acc = src[M.sb_root[r] * stride] + below;
+          for (int l = 0; l < M.star_nchain; ++l)
+            if (M.sb_att[l] == r) acc += dst[M.sb_top[l] * stride];
+          dst[M.sb_root[r] * stride] = acc;
+          below = acc;
+        }
+      }
+    } else {
+      for (int b0 = 1; b0 < nb; b0 += 2) {
+        const int bb = b0 + half;
+        if (bb < nb) {
+          float acc = 0.f;
+          const int last = bb + M.body_ndesc[bb];
+          for (int jb = bb; jb <= last; ++jb) acc += src[jb * stride];
+          dst[bb * stride] = acc;
+        }
       }
     }
   }

@@ -71,6 +71,33 @@ static inline void derive_star_layout(const dial_model_desc& m, DevModel& D) {
     D.s_con_chain[c] = D.s_chain[last];           // -1: the body hangs off the root chain itself
   }
   D.s_on = 1;
+  // body-level star (subtree sums): every non-world body is a root body or lies on one chain run
+  D.sb_on = 0;
+  bool covered[DIAL_MAXB] = {false};
+  D.sb_nroot = 0;
+  for (int a = 0; a < D.star_nroot; ++a) {             // deepest root dof first
+    const int b = m.dof_bodyid[D.star_root[a]];
+    if (D.sb_nroot == 0 || D.sb_root[D.sb_nroot - 1] != b) {
+      if (D.sb_nroot >= 4) return;
+      D.sb_root[D.sb_nroot++] = b;
+      covered[b] = true;
+    }
+  }
+  for (int r = 0; r + 1 < D.sb_nroot; ++r)
+    if (m.body_parentid[D.sb_root[r]] != D.sb_root[r + 1]) return;   // root bodies must form a chain
+  for (int l = 0; l < D.star_nchain; ++l) {
+    const int top = m.dof_bodyid[D.s_top[l]], len = D.star_len[l];
+    for (int q = 0; q < len; ++q) {
+      if (m.dof_bodyid[D.s_top[l] + q] != top + q) return;          // one body per chain dof, contiguous
+      if (q > 0 && m.body_parentid[top + q] != top + q - 1) return;
+      covered[top + q] = true;
+    }
+    D.sb_top[l] = top; D.sb_len[l] = len; D.sb_att[l] = -1;
+    for (int r = 0; r < D.sb_nroot; ++r) if (m.body_parentid[top] == D.sb_root[r]) D.sb_att[l] = r;
+    if (D.sb_att[l] < 0 && m.body_parentid[top] != 0) return;
+  }
+  for (int b = 1; b < m.nbody; ++b) if (!covered[b]) return;
+  D.sb_on = 1;
 }
 
 static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::string& err) {

@@ -484,7 +484,11 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
   // warps, DIAL_NO_MIDSYNC=1 / DIAL_DENSE_LOCKSTEP=2 select the coarser levels.
   A.lockstep = (wpc >= 2 && !getenv("DIAL_NO_LOCKSTEP")) ? 1 : 0;
   if (p->hM.dense && !A.lockstep && A.nrows > wpc * p->num_sms && !getenv("DIAL_NO_DYNAMIC_ROWS")) A.row_counter = p->row_counter;
-  if (A.lockstep && !getenv("DIAL_NO_MIDSYNC")) A.lockstep = 2;  // second barrier before the Newton loop (+1-3 % on the tree paths)
+  // second barrier before the constraint solve: the dense path needs it (and a third per Newton
+  // iteration); on the star paths it stopped paying once the solver shrank (r02: Go2 0.709 -> 0.705 ms,
+  // H1 1.060 -> 1.043 ms without it) — DIAL_MIDSYNC=1 / DIAL_NO_MIDSYNC=1 override
+  const bool mid = getenv("DIAL_MIDSYNC") ? true : (getenv("DIAL_NO_MIDSYNC") ? false : (p->hM.dense || !p->hM.s_on));
+  if (A.lockstep && mid) A.lockstep = 2;
   const char* dl = getenv("DIAL_DENSE_LOCKSTEP");
   if (A.lockstep == 2 && p->hM.dense && !(dl && atoi(dl) == 2)) A.lockstep = 3;
   return launch_rollout(p, A, wpc, st);

@@ -10,6 +10,15 @@
 int forced_variant = -1;
 extern "C" void emul_force_variant(int v) { forced_variant = v; }
 
+// derived-model flags (tests): out = {star variant, s_on, sb_on, warp_floats}
+extern "C" int emul_model_flags(const dial_model_desc* m, int out[4]) {
+  static DevModel D;
+  std::string err;
+  if (!derive_model(*m, D, err)) { fprintf(stderr, "emul: %s\n", err.c_str()); return -1; }
+  out[0] = star_variant(D); out[1] = D.s_on; out[2] = D.sb_on; out[3] = D.warp_floats;
+  return 0;
+}
+
 extern "C" int emul_rollout(const dial_model_desc* m, const dial_plan_desc* c, int mode, int nrows,
                             int H, int step0, int stage0, const float* qpos0, const float* qvel0,
                             const float* warm0, const float* us, const float* eps, const float* Ybar,

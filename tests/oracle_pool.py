@@ -19,13 +19,19 @@ def _rollout_chunk(args):
     name, cfg, qpos, qvel, warm, step, stage, us = args
     from oracle.envs_oracle import OState, make_env
     o = make_env(name, cfg)
-    s = OState(qpos[None], qvel[None], warm[None], np.array([step], dtype=np.int64), np.array([stage], dtype=np.int64))
-    return o.rollout(s, us)
+    s = OState(qpos[None], qvel[None], warm[None], np.array([step], dtype=np.int64), np.array([stage], dtype=np.int64)).tile(us.shape[0])
+    rews, qs, qds, xs, ws, sts = [], [], [], [], [], []
+    for t in range(us.shape[1]):          # OracleEnv.rollout, also keeping qacc_warmstart and the stage
+        s, r, aux = o.step(s, us[:, t])
+        rews.append(r); qs.append(aux["q"]); qds.append(aux["qd"]); xs.append(aux["xpos"])
+        ws.append(s.qacc_warmstart.copy()); sts.append(np.asarray(s.stage).copy())
+    return (np.stack(rews, 1), np.stack(qs, 1), np.stack(qds, 1), np.stack(xs, 1), np.stack(ws, 1), np.stack(sts, 1))
 
 
 def oracle_rollout(name, cfg, qpos, qvel, warm, step, stage, us, procs=None):
-    """o.rollout(state, us) with the rows of `us` split over `procs` processes.
-    Returns (rewss [B,H], q, qd, xpos) like OracleEnv.rollout."""
+    """o.rollout(state, us) with the rows of `us` split over `procs` processes.  Returns
+    (rewss [B,H], q, qd, xpos) like OracleEnv.rollout, then qacc_warmstart [B,H,nv] and the stage
+    [B,H] after every step (what is needed to restart a row from the oracle's state at any step)."""
     us = np.asarray(us, dtype=np.float64)
     B = us.shape[0]
     procs = max(1, min(procs or (os.cpu_count() or 1), B, 32))
@@ -46,20 +52,21 @@ def oracle_rollout(name, cfg, qpos, qvel, warm, step, stage, us, procs=None):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-    return tuple(np.concatenate([p[i] for p in parts], 0) for i in range(4))
+    return tuple(np.concatenate([p[i] for p in parts], 0) for i in range(6))
 
 
 def oracle_with_yardstick(name, cfg, qpos, qvel, warm, step, stage, us, rng, K=3, scale=1e-5, procs=None):
     """Nominal oracle rollout of `us` plus the oracle's own sensitivity to fp32-sized noise, per
     output element: the max over K re-runs with the actions perturbed by `scale`*N(0,1) and — for
     the tree models, which the C port covers — the fp32 build of the C port against the fp64
-    oracle (the oracle's own fp32-vs-fp64 divergence).  Returns (nominal 4-tuple, sens 4-tuple)."""
+    oracle (the oracle's own fp32-vs-fp64 divergence).  Returns (nominal 6-tuple incl. warm-start
+    and stage trajectories, sens 4-tuple)."""
     us = np.asarray(us, dtype=np.float64)
     n = us.shape[0]
     stack = np.concatenate([us] + [us + scale * rng.standard_normal(us.shape) for _ in range(K)], 0)
     out = oracle_rollout(name, cfg, qpos, qvel, warm, step, stage, stack, procs=procs)
     nom = tuple(a[:n] for a in out)
-    sens = [np.zeros_like(a) for a in nom]
+    sens = [np.zeros_like(a) for a in nom[:4]]
     for k in range(K):
         for i in range(4):
             sens[i] = np.maximum(sens[i], np.abs(out[i][(k + 1) * n:(k + 2) * n] - nom[i]))
