@@ -1525,7 +1525,7 @@ DEV LSCoef dense_ls_coef(const Solver& S, const ConeLane& C, float l_jv, const f
 // The bracketing loop needs only d0 / d1; the costs of the surviving points are evaluated once
 // at the end (same expressions), which removes a third of the warp reductions.
 template <int NA, bool COST>
-DEV void dense_ls_points(const Solver& S, const ConeLane& C, const LSCoef& K, float l_jv, const float* cv,
+DEV void dense_ls_points(int lane, const Solver& S, const ConeLane& C, const LSCoef& K, float l_jv, const float* cv,
                          const float* qg, const float* al, LSPoint* out) {
   float s[3 * NA];
 #pragma unroll
@@ -1567,11 +1567,20 @@ DEV void dense_ls_points(const Solver& S, const ConeLane& C, const LSCoef& K, fl
       }
     }
   }
+  if constexpr ((NA == 3 && !COST) || (NA == 2 && COST)) {
+    float v[6];   // six sums: transposed reduction (17 shuffles instead of 30)
+    if constexpr (NA == 3) { v[0] = s[1]; v[1] = s[2]; v[2] = s[4]; v[3] = s[5]; v[4] = s[7]; v[5] = s[8]; }
+    else { v[0] = s[0]; v[1] = s[1]; v[2] = s[2]; v[3] = s[3]; v[4] = s[4]; v[5] = s[5]; }
+    warp_allsum6(lane, v);
+    if constexpr (NA == 3) { s[1] = v[0]; s[2] = v[1]; s[4] = v[2]; s[5] = v[3]; s[7] = v[4]; s[8] = v[5]; }
+    else { s[0] = v[0]; s[1] = v[1]; s[2] = v[2]; s[3] = v[3]; s[4] = v[4]; s[5] = v[5]; }
+  } else {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int i = 0; i < 3 * NA; ++i)
-      if (COST || (i % 3) != 0) s[i] += shfl_xor(s[i], o);
+      for (int i = 0; i < 3 * NA; ++i)
+        if (COST || (i % 3) != 0) s[i] += shfl_xor(s[i], o);
+    }
   }
 #pragma unroll
   for (int i = 0; i < NA; ++i) {
@@ -1599,9 +1608,9 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
   const LSCoef K = dense_ls_coef(S, C, l_jv, cv);
   LSPoint p0, lo, hi;
   float a1[1] = {0.f};
-  dense_ls_points<1, true>(S, C, K, l_jv, cv, qg, a1, &p0);
+  dense_ls_points<1, true>(w.lane, S, C, K, l_jv, cv, qg, a1, &p0);
   a1[0] = p0.alpha - p0.d0 / p0.d1;
-  dense_ls_points<1, false>(S, C, K, l_jv, cv, qg, a1, &lo);
+  dense_ls_points<1, false>(w.lane, S, C, K, l_jv, cv, qg, a1, &lo);
   if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
   bool swap = true;
   // In fp32 the bracket can rarely reach `gtol` (the derivative noise is orders of magnitude above
@@ -1632,7 +1641,7 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
 #endif
     LSPoint pt[3];
     float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
-    dense_ls_points<3, false>(S, C, K, l_jv, cv, qg, a3, pt);
+    dense_ls_points<3, false>(w.lane, S, C, K, l_jv, cv, qg, a3, pt);
     const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
     bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
     if (swap_lo_next) lo = lo_next;
@@ -1648,7 +1657,7 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
   {
     LSPoint fin[2];
     float a2[2] = {lo.alpha, hi.alpha};
-    dense_ls_points<2, true>(S, C, K, l_jv, cv, qg, a2, fin);
+    dense_ls_points<2, true>(w.lane, S, C, K, l_jv, cv, qg, a2, fin);
     lo.cost = fin[0].cost; hi.cost = fin[1].cost;
   }
   bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);

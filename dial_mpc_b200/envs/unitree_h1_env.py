@@ -1,8 +1,8 @@
-"""Unitree H1 walking/jogging environment on the CUDA sampling core.
+"""Unitree H1 environments on the CUDA sampling core.
 
-Same class / config fields / registry name as the reference ``UnitreeH1WalkEnv``
-(dial_mpc/envs/unitree_h1_env.py:25-375).  PushCrate / Loco variants are out of scope
-(SURVEY.md §8f-3)."""
+Same classes / config fields / registry names as the reference ``UnitreeH1WalkEnv``
+(dial_mpc/envs/unitree_h1_env.py:25-375) and ``UnitreeH1LocoEnv`` (:570-902).  The push-crate
+variant (:378-567: box geom, slide joint with frictionloss) is not built."""
 from __future__ import annotations
 
 from dataclasses import dataclass, field

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "c", "dial_port.c")
 HDR = os.path.join(os.path.dirname(HERE), "include", "dial_b200.h")
 OUT = os.path.join(HERE, "_build")
-FLAGS = ["-O3", "-march=x86-64-v2", "-fno-math-errno", "-std=c11", "-shared", "-fPIC"]
+FLAGS = ["-O3", "-march=x86-64-v2", "-fno-math-errno", "-std=c11", "-fopenmp", "-shared", "-fPIC"]
 
 
 def lib_path(real: str) -> str:

@@ -23,6 +23,9 @@
 #if defined(__SSE__)
 #include <xmmintrin.h>
 #endif
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "../../include/dial_b200.h"
 
 #ifndef REAL
@@ -801,50 +804,73 @@ static real reward(const dial_model_desc* m, const dial_plan_desc* c, Work* w, i
  * rewss [nrows,H], q [nrows,H,nq], qd [nrows,H,nv], xpos [nrows,H,nbody-1,3], warm_out [nrows,nv] */
 int port_sizeof_real(void) { return (int)sizeof(real); }
 
+static void rollout_row(const dial_model_desc* m, const dial_plan_desc* c, Work* wp, int row, int H, const double* qpos0,
+                        const double* qvel0, const double* warm0, int step0, int stage0, const double* us, double* rewss,
+                        double* q, double* qd, double* xpos, double* warm_out) {
+  Work* w_ = wp;
+#define w (*w_)
+  const int nq = m->nq, nv = m->nv, nu = m->nu, nb = m->nbody;
+  for (int i = 0; i < nq; ++i) w.qpos[i] = (real)qpos0[i];
+  for (int i = 0; i < nv; ++i) { w.qvel[i] = (real)qvel0[i]; w.warm[i] = (real)warm0[i]; }
+  int step = step0, stage = stage0;
+  for (int t = 0; t < H; ++t) {
+    const double* u = us + ((size_t)row * H + t) * nu;
+    for (int a = 0; a < nu; ++a) {
+      const real an = ((real)u[a] * (real)c->action_scale + 1) * (real)0.5;
+      real jt = (real)c->joint_range[a][0] + (real)c->joint_offset[a] + an * ((real)c->joint_range[a][1] - (real)c->joint_range[a][0]);
+      jt = rclip(jt, (real)c->physical_joint_range[a][0], (real)c->physical_joint_range[a][1]);
+      real ctrl = jt;
+      if (c->leg_control_torque) {
+        const real tau = (real)c->kp[a] * (jt - w.qpos[7 + a]) - (real)c->kd[a] * w.qvel[6 + a];
+        ctrl = rclip(tau, (real)c->joint_torque_range[a][0], (real)c->joint_torque_range[a][1]);
+      }
+      w.ctrl[a] = ctrl;
+    }
+    for (int f = 0; f < c->n_frames; ++f) physics_step(m, &w, 1);
+    const real r = reward(m, c, &w, step, &stage);
+    step += 1;
+    const size_t rt = (size_t)row * H + t;
+    rewss[rt] = (double)r;
+    if (q) for (int i = 0; i < nq; ++i) q[rt * nq + i] = (double)w.qpos[i];
+    if (qd) for (int i = 0; i < nv; ++i) qd[rt * nv + i] = (double)w.qvel[i];
+    if (xpos) for (int b = 1; b < nb; ++b) for (int i = 0; i < 3; ++i) xpos[(rt * (nb - 1) + (b - 1)) * 3 + i] = (double)w.xpos[b][i];
+  }
+  if (warm_out) for (int i = 0; i < nv; ++i) warm_out[(size_t)row * nv + i] = (double)w.warm[i];
+#undef w
+}
+
+/* nthreads: OpenMP threads over the rows (each with its own workspace); <= 1: this thread only */
+int port_rollout_mt(const dial_model_desc* m, const dial_plan_desc* c, int nrows, int H, const double* qpos0,
+                    const double* qvel0, const double* warm0, int step0, int stage0, const double* us, double* rewss,
+                    double* q, double* qd, double* xpos, double* warm_out, int nthreads) {
+  if (m->cone != 0 || m->nv > DIAL_MAXV || 4 * m->ncon + m->nv > MAXE) return -1;
+  if (c->env_id == DIAL_ENV_ALLEGRO || c->env_id == DIAL_ENV_CUSTOM) return -2;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads > 1 ? nthreads : 1)
+#endif
+  {
+    static _Thread_local Work w;
+    derive(m, &w);
+#if defined(__SSE__)
+    /* flush denormals (the GPU build does too: -use_fast_math implies ftz); without it the fp32
+     * build spends most of its time in microcoded denormal arithmetic on some states */
+    const unsigned int csr0 = _mm_getcsr();
+    _mm_setcsr(csr0 | 0x8040u);
+#endif
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 2)
+#endif
+    for (int row = 0; row < nrows; ++row)
+      rollout_row(m, c, &w, row, H, qpos0, qvel0, warm0, step0, stage0, us, rewss, q, qd, xpos, warm_out);
+#if defined(__SSE__)
+    _mm_setcsr(csr0);
+#endif
+  }
+  return 0;
+}
+
 int port_rollout(const dial_model_desc* m, const dial_plan_desc* c, int nrows, int H, const double* qpos0,
                  const double* qvel0, const double* warm0, int step0, int stage0, const double* us, double* rewss,
                  double* q, double* qd, double* xpos, double* warm_out) {
-  if (m->cone != 0 || m->nv > DIAL_MAXV || 4 * m->ncon + m->nv > MAXE) return -1;
-  if (c->env_id == DIAL_ENV_ALLEGRO || c->env_id == DIAL_ENV_CUSTOM) return -2;
-  static _Thread_local Work w;
-  derive(m, &w);
-#if defined(__SSE__)
-  /* flush denormals (the GPU build does too: -use_fast_math implies ftz); without it the fp32
-   * build spends most of its time in microcoded denormal arithmetic on some states */
-  const unsigned int csr0 = _mm_getcsr();
-  _mm_setcsr(csr0 | 0x8040u);
-#endif
-  const int nq = m->nq, nv = m->nv, nu = m->nu, nb = m->nbody;
-  for (int row = 0; row < nrows; ++row) {
-    for (int i = 0; i < nq; ++i) w.qpos[i] = (real)qpos0[i];
-    for (int i = 0; i < nv; ++i) { w.qvel[i] = (real)qvel0[i]; w.warm[i] = (real)warm0[i]; }
-    int step = step0, stage = stage0;
-    for (int t = 0; t < H; ++t) {
-      const double* u = us + ((size_t)row * H + t) * nu;
-      for (int a = 0; a < nu; ++a) {
-        const real an = ((real)u[a] * (real)c->action_scale + 1) * (real)0.5;
-        real jt = (real)c->joint_range[a][0] + (real)c->joint_offset[a] + an * ((real)c->joint_range[a][1] - (real)c->joint_range[a][0]);
-        jt = rclip(jt, (real)c->physical_joint_range[a][0], (real)c->physical_joint_range[a][1]);
-        real ctrl = jt;
-        if (c->leg_control_torque) {
-          const real tau = (real)c->kp[a] * (jt - w.qpos[7 + a]) - (real)c->kd[a] * w.qvel[6 + a];
-          ctrl = rclip(tau, (real)c->joint_torque_range[a][0], (real)c->joint_torque_range[a][1]);
-        }
-        w.ctrl[a] = ctrl;
-      }
-      for (int f = 0; f < c->n_frames; ++f) physics_step(m, &w, 1);
-      const real r = reward(m, c, &w, step, &stage);
-      step += 1;
-      const size_t rt = (size_t)row * H + t;
-      rewss[rt] = (double)r;
-      if (q) for (int i = 0; i < nq; ++i) q[rt * nq + i] = (double)w.qpos[i];
-      if (qd) for (int i = 0; i < nv; ++i) qd[rt * nv + i] = (double)w.qvel[i];
-      if (xpos) for (int b = 1; b < nb; ++b) for (int i = 0; i < 3; ++i) xpos[(rt * (nb - 1) + (b - 1)) * 3 + i] = (double)w.xpos[b][i];
-    }
-    if (warm_out) for (int i = 0; i < nv; ++i) warm_out[(size_t)row * nv + i] = (double)w.warm[i];
-  }
-#if defined(__SSE__)
-  _mm_setcsr(csr0);
-#endif
-  return 0;
+  return port_rollout_mt(m, c, nrows, H, qpos0, qvel0, warm0, step0, stage0, us, rewss, q, qd, xpos, warm_out, 1);
 }

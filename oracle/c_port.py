@@ -36,6 +36,8 @@ def _lib(real: str):
         P = C.c_void_p
         lib.port_rollout.argtypes = [P, P, C.c_int, C.c_int, P, P, P, C.c_int, C.c_int, P, P, P, P, P, P]
         lib.port_rollout.restype = C.c_int
+        lib.port_rollout_mt.argtypes = [P, P, C.c_int, C.c_int, P, P, P, C.c_int, C.c_int, P, P, P, P, P, P, C.c_int]
+        lib.port_rollout_mt.restype = C.c_int
         assert lib.port_sizeof_real() == (4 if real == "float" else 8)
         _LIBS[real] = lib
     return _LIBS[real]
@@ -115,7 +117,7 @@ class CPort:
         self.lib = _lib(real)
         self.md, self.pd = fill_model(env.m), fill_plan(env)
 
-    def rollout(self, s: OState, us, want_traj=True):
+    def rollout(self, s: OState, us, want_traj=True, threads: int = 1):
         us = np.ascontiguousarray(us, dtype=np.float64)
         B, H, nu = us.shape
         m = self.env.m
@@ -127,11 +129,12 @@ class CPort:
         x = np.zeros((B, H, m.nbody - 1, 3)) if want_traj else None
         warm = np.zeros((B, m.nv))
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-        rc = self.lib.port_rollout(C.byref(self.md), C.byref(self.pd), B, H, p(q0), p(v0), p(w0), int(s.step[0]), int(s.stage[0]),
-                                   p(us), p(rew), p(q), p(qd), p(x), p(warm))
+        rc = self.lib.port_rollout_mt(C.byref(self.md), C.byref(self.pd), B, H, p(q0), p(v0), p(w0), int(s.step[0]), int(s.stage[0]),
+                                      p(us), p(rew), p(q), p(qd), p(x), p(warm), int(threads))
         if rc != 0:
             raise RuntimeError(f"port_rollout failed ({rc}): model / env outside the C port's scope")
         return rew, q, qd, x, warm
 
-    def rollout_rews(self, s: OState, us):
-        return self.rollout(s, us, want_traj=False)[0].mean(-1)
+    def rollout_rews(self, s: OState, us, threads: int = 1):
+        """Per-sample mean rewards; ``threads`` OpenMP threads over the rows (the CPU baseline of bench.py)."""
+        return self.rollout(s, us, want_traj=False, threads=threads)[0].mean(-1)

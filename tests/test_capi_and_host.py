@@ -145,3 +145,20 @@ def test_deploy_shm_layout_and_time_shift():
     from scipy.interpolate import InterpolatedUnivariateSpline
     for dt in (0.013, 0.02, 0.055):
         assert np.abs(interp_matrix(nodes, nodes + dt) @ y - InterpolatedUnivariateSpline(nodes, y, k=2)(nodes + dt)).max() < 1e-12
+
+
+def test_end_of_run_dumps_have_the_reference_layout(tmp_path):
+    """dial_core.py:305-323: `*_states.npy` rows [i, qpos, qvel, ctrl]; `*_predictions.npy` holds per
+    control step the xbar of the LAST diffusion iteration over the whole horizon
+    ([n_steps, Hsample+1, nbody-1, 3]; `infos[i]["xbar"][-1]` indexes the scan's iteration axis)."""
+    import numpy as np
+    import torch
+    from dial_mpc_b200.core.dial_core import save_run
+    n_steps, Hs, nq, nv, nu, nb = 7, 16, 19, 18, 12, 14
+    rollout = [torch.cat([torch.tensor([float(t)]), torch.zeros(nq), torch.ones(nv), torch.full((nu,), 2.0)]) for t in range(n_steps)]
+    infos = [torch.full((Hs + 1, nb - 1, 3), float(t)) for t in range(n_steps)]
+    states, preds = save_run(str(tmp_path), rollout, infos, timestamp="t")
+    assert states.shape == (n_steps, 1 + nq + nv + nu) and preds.shape == (n_steps, Hs + 1, nb - 1, 3)
+    assert np.load(tmp_path / "t_states.npy").shape == states.shape
+    assert np.load(tmp_path / "t_predictions.npy").shape == preds.shape
+    assert (states[:, 0] == np.arange(n_steps)).all() and (preds[3] == 3.0).all()
