@@ -134,6 +134,7 @@ struct RolloutArgs {
   const int32_t* counters_in;   // non-null: {step0, stage0} read from here
   int32_t* counters_out;        // non-null: row 0 writes {step, stage} after its H steps
   const uint32_t* key_dev;      // non-null: sampling key read from here
+  const uint32_t* rng_dev;      // non-null: planner rng; the sampling key is split(rng)[1] (the update kernel advances rng)
   unsigned int* row_counter;  // non-null: persistent warps pull rows from this counter (dense path)
   float* dbg;           // optional device counters (DIAL_DEBUG_COUNTERS, see dial_debug_counters)
   // multi-GPU reward exchange fused into the epilogue (dial_exchange_*): every finished row stores
@@ -295,6 +296,20 @@ HD void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
   TF_R(17) TF_R(29) TF_R(16) TF_R(24)  x0 += k1;  x1 += ks2 + 4u;
   TF_R(13) TF_R(15) TF_R(26) TF_R(6)   x0 += ks2; x1 += k0 + 5u;
 #undef TF_R
+}
+// rng, key = jax.random.split(rng) (legacy layout: counters [0,1,2,3] -> halves (0,1) | (2,3)):
+// the sampling key (second half); split_rng gives the first half (the new rng)
+HD void split_key(uint32_t k0, uint32_t k1, uint32_t& key0, uint32_t& key1) {
+  uint32_t a0 = 0, b0 = 2, a1 = 1, b1 = 3;
+  threefry2x32(k0, k1, a0, b0);
+  threefry2x32(k0, k1, a1, b1);
+  key0 = b0; key1 = b1;
+}
+HD void split_rng(uint32_t k0, uint32_t k1, uint32_t& r0, uint32_t& r1) {
+  uint32_t a0 = 0, b0 = 2, a1 = 1, b1 = 3;
+  threefry2x32(k0, k1, a0, b0);
+  threefry2x32(k0, k1, a1, b1);
+  r0 = a0; r1 = a1;
 }
 // element `i` of jax.random.bits(key, (n,)) with threefry_partitionable=False
 DEV uint32_t jax_bits_legacy(uint32_t k0, uint32_t k1, uint32_t i, uint32_t n) {
@@ -2793,7 +2808,8 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     const bool is_mean = row == c.Nsample;
     const uint32_t gidx = (uint32_t)(c.shard_offset + row);
     const uint32_t ntot = (uint32_t)c.Ntotal * (uint32_t)Hn1 * (uint32_t)nu;
-    const uint32_t key0 = A.key_dev ? A.key_dev[0] : A.key0, key1 = A.key_dev ? A.key_dev[1] : A.key1;
+    uint32_t key0 = A.key_dev ? A.key_dev[0] : A.key0, key1 = A.key_dev ? A.key_dev[1] : A.key1;
+    if (A.rng_dev) split_key(A.rng_dev[0], A.rng_dev[1], key0, key1);
 #pragma unroll
     for (int k = 0; k < DIAL_MAXNODE; ++k) {
       if (k < Hn1) {

@@ -256,6 +256,106 @@ __global__ void __launch_bounds__(YBAR_THREADS) ybar_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------
+// Fused update of the control step graph: weights + Ybar + rng advance in ONE multi-CTA kernel
+// (dial_core.py:106,125-132).  Every CTA recomputes the reward statistics (n <= 16384: a few
+// loads per thread), accumulates sum_n e_n Y0s_n and sum_n e_n over its share of the samples with
+// e_n = exp((r_n - rbar) / std / temp - max); the last CTA adds the partials in fixed order,
+// divides, normalises the stored weights, and advances the planner rng.  Saves two launches and
+// their dependency latencies per reverse_once (r02: 765 -> ~735 us per iteration at N = 2048).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(YBAR_THREADS) update_kernel(const float* __restrict__ rews, int n, float temp,
+                                                               float* __restrict__ weights, const XchWait X,
+                                                               uint32_t* __restrict__ rng, const float* __restrict__ Ybar,
+                                                               const float* __restrict__ noise, int Ntotal, int Hn1, int nu,
+                                                               float* __restrict__ partial, unsigned int* __restrict__ counter,
+                                                               float* __restrict__ Ybar_out) {
+  __shared__ float red[4 * 32];
+  __shared__ float acc[YBAR_THREADS];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x;
+  if (X.mbox) {
+    const uint32_t seq = *X.seq, buf = seq & 1u;
+    xch_wait_flags(X.flags + buf * DIAL_MAXRANK, seq + 1u, X.world, X.err);
+    rews = X.mbox + (size_t)buf * n;
+  }
+  uint32_t key0, key1;
+  const uint32_t r0 = rng[0], r1 = rng[1];
+  split_key(r0, r1, key0, key1);
+  // ---- statistics of d = r - rbar over the finite rewards (see weights_kernel) --------------------
+  float rbar = __ldcg(rews + n - 1);
+  if (!isfinite(rbar)) rbar = 0.f;
+  float st[3] = {0.f, 0.f, 0.f}, dmax = -INFINITY;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float r = __ldcg(rews + i);
+    if (isfinite(r)) { const float d = r - rbar; st[0] += 1.f; st[1] += d; st[2] += d * d; dmax = fmaxf(dmax, d); }
+  }
+  block_reduce<3>(st, &dmax, red);
+  const float cnt = st[0];
+  const float mean = st[1] / fmaxf(cnt, 1.f);
+  const float sd = sqrtf(fmaxf(st[2] / fmaxf(cnt, 1.f) - mean * mean, 0.f));
+  const float inv = (sd > 0.f) ? 1.f / sd / temp : 0.f;
+  const float mx = dmax * inv;
+  // ---- this CTA's share of sum e_n Y0s_n (thread -> (sample slot, knot element)) and sum e_n ------------
+  const int ne = Hn1 * nu;
+  const int slots = YBAR_THREADS / ne;
+  const int slot = tid / ne, el = tid - slot * ne;
+  float a = 0.f, z = 0.f;
+  if (slot < slots) {
+    const int k = el / nu;
+    const float yb = Ybar[el], ns = noise[k];
+    const uint32_t ntot = (uint32_t)Ntotal * (uint32_t)ne;
+    for (int s_ = blockIdx.x * slots + slot; s_ <= Ntotal; s_ += gridDim.x * slots) {
+      const float r = __ldcg(rews + s_);
+      float e = isfinite(r) ? expf((r - rbar) * inv - mx) : 0.f;
+      if (cnt == 0.f) e = (s_ == Ntotal) ? 1.f : 0.f;       // no finite reward: keep the mean sample
+      float y = yb;
+      if (s_ < Ntotal && k > 0) {
+        const uint32_t idx = (uint32_t)s_ * (uint32_t)ne + (uint32_t)el;
+        y = jax_normal_legacy(key0, key1, idx, ntot) * ns + yb;
+      }
+      y = fminf(fmaxf(y, -1.f), 1.f);
+      a += e * y;
+      if (el == 0) { z += e; weights[s_] = e; }
+    }
+  }
+  acc[tid] = a;
+  float zz[1] = {z};
+  block_reduce<1>(zz, nullptr, red);
+  __syncthreads();
+  if (tid < ne) {
+    float s_ = 0.f;
+    for (int sl = 0; sl < slots; ++sl) s_ += acc[sl * ne + tid];
+    partial[blockIdx.x * (ne + 1) + tid] = s_;
+  }
+  if (tid == 0) partial[blockIdx.x * (ne + 1) + ne] = zz[0];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float Z = 0.f;
+  for (unsigned b = 0; b < gridDim.x; ++b) Z += __ldcg(&partial[b * (ne + 1) + ne]);   // same order in every thread
+  const float iz = 1.f / Z;
+  if (tid < ne) {
+    float s_ = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) s_ += __ldcg(&partial[b * (ne + 1) + tid]);
+    Ybar_out[tid] = s_ * iz;
+  }
+  for (int i = tid; i < n; i += blockDim.x) {
+    weights[i] = __ldcg(weights + i) * iz;
+    if (X.mbox && X.rews_copy) X.rews_copy[i] = __ldcg(rews + i);
+  }
+  if (tid == 0) {
+    *counter = 0u;
+    uint32_t n0, n1;
+    split_rng(r0, r1, n0, n1);
+    rng[0] = n0; rng[1] = n1;
+    if (X.mbox) *X.seq = *X.seq + 1u;
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // glue of the device-resident MPC loop (dial_mpc_step): everything the reference's Python loop
 // does between kernels (core/dial_core.py:242-268) as tiny kernels, so that one MPC step is one
 // CUDA graph with no host work inside
@@ -368,6 +468,7 @@ struct dial_plan {
   unsigned int* row_counter = nullptr;
   float* zeros = nullptr;                                          // [nv]
   int ybar_grid = 0;
+  int upd_grid = 0;             // grid of the fused update kernel: about 8 samples per thread slot
   int64_t launches = 0;
   float* dbg = nullptr;  // optional device counters (DIAL_DEBUG_COUNTERS=1)
   // device-resident MPC loop
@@ -557,7 +658,11 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
   const int ne = (c.Hnode + 1) * m.nu, slots = YBAR_THREADS / ne;
   int g = (c.Ntotal + 1 + slots - 1) / slots;
   p->ybar_grid = g < 1 ? 1 : (g > 296 ? 296 : g);
-  if ((e = cudaMalloc(&p->partial, (size_t)p->ybar_grid * ne * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(partial)");
+  {
+    int gu = (c.Ntotal + 1 + slots * 8 - 1) / (slots * 8);
+    p->upd_grid = gu < 1 ? 1 : (gu > p->ybar_grid ? p->ybar_grid : gu);
+  }
+  if ((e = cudaMalloc(&p->partial, (size_t)p->ybar_grid * (ne + 1) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(partial)");
   if ((e = cudaMalloc(&p->tb_partial, (size_t)TB_CHUNKS * H * (m.nq + m.nv + 3 * (m.nbody - 1)) * sizeof(float))) != cudaSuccess) return bad(e, "cudaMalloc(tb_partial)");
   if ((e = cudaMalloc(&p->counter, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMalloc(counter)");
   if ((e = cudaMemset(p->counter, 0, sizeof(unsigned int))) != cudaSuccess) return bad(e, "cudaMemset(counter)");
@@ -834,30 +939,41 @@ static int mpc_enqueue(dial_plan* p, int n_diffuse, int env_step, cudaStream_t s
   float* wts[2] = {p->weights, p->weights2};
   for (int i = 0; i < n_diffuse; ++i) {
     const float* noise = B.noise + (size_t)i * n1;
-    mpc_split_kernel<<<1, 32, 0, st>>>(B.rng, p->mpc_key);
-    p->launches++;
-    CUDA_OK(cudaGetLastError());
+    // small / medium sample counts: rng split folded into the rollout (key = split(rng)[1]) and the
+    // fused update kernel (which also advances rng); large ones keep the three-kernel sequence
+    const bool fused = c.Ntotal + 1 <= 16384 && !getenv("DIAL_NO_FUSED_UPDATE");
+    if (!fused) {
+      mpc_split_kernel<<<1, 32, 0, st>>>(B.rng, p->mpc_key);
+      p->launches++;
+      CUDA_OK(cudaGetLastError());
+    }
     if (bars && i >= 2) CUDA_OK(cudaStreamWaitEvent(st, p->ev_side[i & 1], 0));
     RolloutArgs A; memset(&A, 0, sizeof(A));
     A.qpos0 = B.qpos; A.qvel0 = B.qvel; A.warm0 = B.qacc_warmstart; A.counters_in = B.counters;
     A.nrows = c.Nsample + 1; A.H = c.Hsample + 1; A.mode = 1;
-    A.Ybar = Y[cur]; A.noise = noise; A.key_dev = p->mpc_key;
+    A.Ybar = Y[cur]; A.noise = noise;
+    if (fused) A.rng_dev = B.rng; else A.key_dev = p->mpc_key;
     p->cur ^= 1;
     A.rews = B.rews; A.q = p->traj_q[p->cur]; A.qd = p->traj_qd[p->cur]; A.xpos = p->traj_x[p->cur];
     A.dbg = p->dbg;
     fill_xch(p, A);
     CUDA_OK(launch_rollout_any(p, A, st));
     float* w = wts[i & 1];
-    {
-      XchWait X = xch_wait_args(p, B.rews_all);
+    XchWait X = xch_wait_args(p, B.rews_all);
+    if (fused) {
+      update_kernel<<<p->upd_grid, YBAR_THREADS, 0, st>>>(B.rews, c.Ntotal + 1, c.temp_sample, w, X, B.rng, Y[cur], noise, c.Ntotal,
+                                                          n1, nu, p->partial, p->counter, Y[cur ^ 1]);
+      p->launches++;
+      CUDA_OK(cudaGetLastError());
+    } else {
       weights_kernel<<<1, 1024, 0, st>>>(B.rews, c.Ntotal + 1, c.temp_sample, w, X);
+      p->launches++;
+      CUDA_OK(cudaGetLastError());
+      ybar_kernel<<<p->ybar_grid, YBAR_THREADS, 0, st>>>(w, nullptr, 0u, 0u, Y[cur], noise, c.Ntotal, n1, nu,
+                                                         p->partial, p->counter, Y[cur ^ 1], p->mpc_key);
+      p->launches++;
+      CUDA_OK(cudaGetLastError());
     }
-    p->launches++;
-    CUDA_OK(cudaGetLastError());
-    ybar_kernel<<<p->ybar_grid, YBAR_THREADS, 0, st>>>(w, nullptr, 0u, 0u, Y[cur], noise, c.Ntotal, n1, nu,
-                                                       p->partial, p->counter, Y[cur ^ 1], p->mpc_key);
-    p->launches++;
-    CUDA_OK(cudaGetLastError());
     cur ^= 1;
     if (bars) {
       CUDA_OK(cudaEventRecord(p->ev_main[i & 1], st));
