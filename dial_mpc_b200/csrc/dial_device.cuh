@@ -111,6 +111,7 @@ struct RolloutArgs {
   int32_t H;            // env steps per row
   int32_t mode;         // 0: explicit us; 1: planner (Y0s from eps / key); 2: forward only (pipeline_init)
   int32_t lockstep;     // >=1: warps of a CTA re-converge at every env step (shared instruction fetch); 2: and before the Newton loop
+  int32_t sync_every;   // lock-step barrier every this many env steps (>= 1)
   int32_t step0, stage0;
   const float* qpos0;
   const float* qvel0;
@@ -268,7 +269,7 @@ DEV void inert_mul(const float* ci, const float* v, float* r) {
   st3(r, ang); st3(r + 3, vel);
 }
 DEV float dot6(const float* a, const float* b) {
-  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+  return (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (a[3] * b[3] + a[4] * b[4] + a[5] * b[5]);
 }
 
 DEV float warp_sum(float v) {
@@ -840,20 +841,25 @@ DEV void star_mul_MJ(WarpCtx& w, const float* Mr, const float* Mc, float x, floa
   ldv<NL>(xs + w.s_cb, xc);
   float y = 0.f;
   if (WITH_M) {
+  // (independent partial sums: the fp32 pipe has a 4-cycle dependent-issue latency and only
+  // ~3.5 warps per scheduler to hide it)
+  float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll
-  for (int a = 0; a < NR; ++a) y += Mr[a] * xr[a];
+  for (int a = 0; a < NR; ++a) { if (a & 1) y1 += Mr[a] * xr[a]; else y0 += Mr[a] * xr[a]; }
   if (w.s_chain >= 0) {
 #pragma unroll
-    for (int q = 0; q < NL; ++q) y += Mc[q] * xc[q];
+    for (int q = 0; q < NL; ++q) { if (q & 1) y3 += Mc[q] * xc[q]; else y2 += Mc[q] * xc[q]; }
   } else if (w.s_chain == -1) {
     // root dof: the coupling column, sum over every chain slot of M[slot dof][root a] x[slot dof]
     const float* col = Ms + SD::NRP * SD::RS + w.s_col;
     const int nslot = M.star_nchain * SD::CS;
     for (int s0 = 0; s0 < nslot; s0 += 4) {
       F4 xv = ld4(xs + SD::NRP + s0);
-      y += col[(s0 + 0) * SD::RS] * xv.x + col[(s0 + 1) * SD::RS] * xv.y + col[(s0 + 2) * SD::RS] * xv.z + col[(s0 + 3) * SD::RS] * xv.w;
+      y0 += col[(s0 + 0) * SD::RS] * xv.x; y1 += col[(s0 + 1) * SD::RS] * xv.y;
+      y2 += col[(s0 + 2) * SD::RS] * xv.z; y3 += col[(s0 + 3) * SD::RS] * xv.w;
     }
   }
+  y = (y0 + y1) + (y2 + y3);
   }
   Mx = y;
   if (WITH_J) {
@@ -864,10 +870,12 @@ DEV void star_mul_MJ(WarpCtx& w, const float* Mr, const float* Mc, float x, floa
       ldv<NR>(row, jr);
       ldv<NL>(row + SD::NRP, jc);
       ldv<NL>(xs + w.e_cb, xe);
+      float j0 = 0.f, j1 = 0.f, j2 = 0.f;
 #pragma unroll
-      for (int a = 0; a < NR; ++a) j += jr[a] * xr[a];
+      for (int a = 0; a < NR; ++a) { if (a & 1) j1 += jr[a] * xr[a]; else j0 += jr[a] * xr[a]; }
 #pragma unroll
-      for (int q = 0; q < NL; ++q) j += jc[q] * xe[q];
+      for (int q = 0; q < NL; ++q) j2 += jc[q] * xe[q];
+      j = (j0 + j1) + j2;
     }
     Jx = j;
   }
@@ -883,16 +891,16 @@ DEV float star_mul_JT(WarpCtx& w, float f) {
   syncwarp();
   frow[w.lane] = f;
   syncwarp();
-  float y = 0.f;
+  float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;   // independent partial sums (dependent-issue latency)
   const float* col = Js + w.s_col;
   for (int c = 0; c < M.m.ncon; ++c) {
     const F4 fv = ld4(frow + 4 * c);
     if ((w.s_conmask >> c) & 1u) {
       const float* jc = col + 4 * c * SD::RS;
-      y += jc[0] * fv.x + jc[SD::RS] * fv.y + jc[2 * SD::RS] * fv.z + jc[3 * SD::RS] * fv.w;
+      y0 += jc[0] * fv.x; y1 += jc[SD::RS] * fv.y; y2 += jc[2 * SD::RS] * fv.z; y3 += jc[3 * SD::RS] * fv.w;
     }
   }
-  return y;
+  return (y0 + y1) + (y2 + y3);
 }
 
 // H row of this lane: M + active limit + sum over active edges d_e j_e^T j_e
@@ -1685,9 +1693,10 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
   for (int i = 0; i < 6; ++i) C.x[i] += alpha * cv[i];
 }
 
-// sections 8-9 of the physics step for the dense path; returns qacc, leaves S.qfc
+// sections 8-9 of the physics step for the dense path; returns qacc (and qacc_int: the one the
+// integrator uses, = qacc without eulerdamp), leaves S.qfc
 template <int NVD>
-DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float myqvel) {
+DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float myqvel, float& qacc_int) {
   const DevModel& M = *w.M;
   const dial_model_desc& m = M.m;
   const int lane = w.lane, nv = m.nv, d = lane;
@@ -1789,36 +1798,51 @@ DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float
   const float scale = m.meaninertia * (float)(nv > 1 ? nv : 1);
   const float mywarm = isdof ? SM(warm)[d] : 0.f;
   syncwarp();
+  // ONE factor/solve site for the three linear systems of the step (the unrolled register
+  // Cholesky is ~8.6 k SASS instructions per inlined copy: three copies were 45 % of the kernel):
+  //   mode 0: M x = qfrc_smooth            -> qacc_smooth, warm-start choice
+  //   mode 1: H(active set) x = grad       -> Newton direction, line search          (solver.solve)
+  //   mode 2: (M + dt diag(damping)) x = qfrc_smooth + qfrc_constraint               (eulerdamp)
   float Hrow[NVD];
 #pragma unroll
   for (int j = 0; j < NVD; ++j) Hrow[j] = (isdof && j <= d) ? Md[d * nv + j] : (j == d ? 1.f : 0.f);
-  S.qas = dense_factor_solve<NVD>(w, Hrow, S.qfs);
-  {
-    float xw[6], xs[6], cw, cs, f[6], N, T;
-    float Maw = dense_mul_M(w, mywarm);
-    dense_mul_J(w, C, mywarm, xw);
-    dense_mul_J(w, C, S.qas, xs);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { xw[i] -= C.aref[i]; xs[i] -= C.aref[i]; }
-    cone_eval(C, xw, cw, f, N, T);
-    cone_eval(C, xs, cs, f, N, T);
-    float lJw = S.l_sign * mywarm - S.l_aref, lJs = S.l_sign * S.qas - S.l_aref;
-    float gw = (Maw - S.qfs) * (mywarm - S.qas);
-    float tw = ((lJw < 0.f) ? S.l_D * lJw * lJw : 0.f) + 2.f * cw;
-    float ts = ((lJs < 0.f) ? S.l_D * lJs * lJs : 0.f) + 2.f * cs;
-    warp_sum3(gw, tw, ts);
-    const bool usewarm = (0.5f * tw + 0.5f * gw) < (0.5f * ts);
-    S.qacc = usewarm ? mywarm : S.qas;
-    S.Ma = usewarm ? Maw : S.qfs;
-    S.l_Jaref = usewarm ? lJw : lJs;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) C.x[i] = usewarm ? xw[i] : xs[i];
-    S.cost = INFINITY;
-    S.prev_cost = 0.f;
-  }
-  int it = 0;
+  float g = S.qfs;
+  int mode = 0, it = 0;
   bool done = false;
-  while (true) {
+  qacc_int = 0.f;
+  for (;;) {
+    float x = 0.f;
+    if (mode != 1 || !done) x = dense_factor_solve<NVD>(w, Hrow, g);
+    if (mode == 2) { qacc_int = x; break; }
+    if (mode == 0) {
+      S.qas = x;
+      float xw[6], xs[6], cw, cs, f[6], N, T;
+      float Maw = dense_mul_M(w, mywarm);
+      dense_mul_J(w, C, mywarm, xw);
+      dense_mul_J(w, C, S.qas, xs);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { xw[i] -= C.aref[i]; xs[i] -= C.aref[i]; }
+      cone_eval(C, xw, cw, f, N, T);
+      cone_eval(C, xs, cs, f, N, T);
+      float lJw = S.l_sign * mywarm - S.l_aref, lJs = S.l_sign * S.qas - S.l_aref;
+      float gw = (Maw - S.qfs) * (mywarm - S.qas);
+      float tw = ((lJw < 0.f) ? S.l_D * lJw * lJw : 0.f) + 2.f * cw;
+      float ts = ((lJs < 0.f) ? S.l_D * lJs * lJs : 0.f) + 2.f * cs;
+      warp_sum3(gw, tw, ts);
+      const bool usewarm = (0.5f * tw + 0.5f * gw) < (0.5f * ts);
+      S.qacc = usewarm ? mywarm : S.qas;
+      S.Ma = usewarm ? Maw : S.qfs;
+      S.l_Jaref = usewarm ? lJw : lJs;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) C.x[i] = usewarm ? xw[i] : xs[i];
+      S.cost = INFINITY;
+      S.prev_cost = 0.f;
+      mode = 1;
+    } else if (!done) {
+      S.search = -x;
+      dense_linesearch(w, S, C);
+      ++it;
+    }
     if (!done) {
       dense_update_constraint(w, S, C);
       done = it >= m.iterations;
@@ -1831,18 +1855,23 @@ DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float
       // burning iterations x ls_iterations on it (its result is garbage either way, weight 0 later)
       if (!(fabsf(S.cost) <= 3.0e38f)) done = true;
     }
-    if (w.itersync) {
-      // lock-step level 3: the warps of the CTA start every Newton iteration together (shared
-      // instruction fetch inside the solver); a finished warp keeps arriving until all are done
-      if (!cta_sync_or(!done)) break;
-      if (done) continue;
-    } else if (done) {
-      break;
+    // lock-step level 3: the warps of the CTA start every Newton iteration together (shared
+    // instruction fetch inside the solver); a finished warp keeps arriving until all are done
+    const bool any = w.itersync ? cta_sync_or(!done) : !done;
+    if (!any) {
+      if (!m.eulerdamp) { qacc_int = S.qacc; break; }
+      mode = 2;   // implicit joint damping: (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
+#pragma unroll
+      for (int j = 0; j < NVD; ++j) Hrow[j] = (isdof && j <= d) ? Md[d * nv + j] : 0.f;
+#pragma unroll
+      for (int j = 0; j < NVD; ++j)
+        if (j == d) Hrow[j] += isdof ? m.timestep * m.dof_damping[d] : 1.f;
+      g = S.qfs + S.qfc;
+      continue;
     }
+    if (done) continue;
     dense_build_H<NVD>(w, S, C, Hrow);
-    S.search = -dense_factor_solve<NVD>(w, Hrow, S.grad);
-    dense_linesearch(w, S, C);
-    ++it;
+    g = S.grad;
   }
 #ifndef DIAL_HOST_EMUL
   if (w.dbg && lane == 0) { atomicAdd(w.dbg, 1.f); atomicAdd(w.dbg + 1, (float)it); }
@@ -2308,18 +2337,7 @@ DEV void physics_step(WarpCtx& w, bool integrate) {
   float qacc, qacc_int;
   if constexpr (NL < 0) {
     if (w.midsync) cta_sync();   // lock-step CTAs: enter the constraint solve together
-    qacc = dense_constraint_solve<NR>(w, S, Mrow, myqvel);
-    qacc_int = qacc;
-    if (m.eulerdamp) {   // implicit joint damping: (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint)
-      const float* Md_ = SM(Md);
-      float Hd[NR > 0 ? NR : 1];
-#pragma unroll
-      for (int j = 0; j < NR; ++j) Hd[j] = (isdof && j <= d) ? Md_[d * nv + j] : 0.f;
-#pragma unroll
-      for (int j = 0; j < NR; ++j)
-        if (j == d) Hd[j] += isdof ? m.timestep * m.dof_damping[d] : 1.f;
-      qacc_int = dense_factor_solve<NR>(w, Hd, S.qfs + S.qfc);
-    }
+    qacc = dense_constraint_solve<NR>(w, S, Mrow, myqvel, qacc_int);   // also the eulerdamp solve (mode 2)
   } else if constexpr (STAR) {
   using SD = StarDims<NL, NR>;
   // ---- 8. constraint rows in the star layout (lane = dof writes its column of every row) --------
@@ -2831,7 +2849,7 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
   const int H = fwd_only ? 1 : A.H;
   const int nfr = fwd_only ? 1 : c.n_frames;
   for (int t = 0; t < H; ++t) {
-    if (A.lockstep) cta_sync();
+    if (A.lockstep && (A.sync_every <= 1 || t % A.sync_every == 0)) cta_sync();
     // action -> joint target -> torque (base_env.py:37-66)
     if (lane < nu && fwd_only) SM(ctrl)[lane] = 0.f;
     if (lane < nu && !fwd_only) {

@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(YBAR_THREADS) ybar_kernel(const float* __restr
 
 // ---------------------------------------------------------------------------------
 // Fused update of the control step graph: weights + Ybar + rng advance in ONE multi-CTA kernel
-// (dial_core.py:106,125-132).  Every CTA recomputes the reward statistics (n <= 16384: a few
-// loads per thread), accumulates sum_n e_n Y0s_n and sum_n e_n over its share of the samples with
+// (dial_core.py:106,125-132).  Every CTA recomputes the reward statistics (n <= 131072: up to 512
+// L2-resident loads per thread at the 65536-sample config, a few at 2048), accumulates sum_n e_n Y0s_n and sum_n e_n over its share of the samples with
 // e_n = exp((r_n - rbar) / std / temp - max); the last CTA adds the partials in fixed order,
 // divides, normalises the stored weights, and advances the planner rng.  Saves two launches and
 // their dependency latencies per reverse_once (r02: 765 -> ~735 us per iteration at N = 2048).
@@ -590,6 +590,7 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
   // H1 1.060 -> 1.043 ms without it) — DIAL_MIDSYNC=1 / DIAL_NO_MIDSYNC=1 override
   const bool mid = getenv("DIAL_MIDSYNC") ? true : (getenv("DIAL_NO_MIDSYNC") ? false : (p->hM.dense || !p->hM.s_on));
   if (A.lockstep && mid) A.lockstep = 2;
+  { const char* se = getenv("DIAL_SYNC_EVERY"); A.sync_every = se ? atoi(se) : 1; if (A.sync_every < 1) A.sync_every = 1; }
   const char* dl = getenv("DIAL_DENSE_LOCKSTEP");
   if (A.lockstep == 2 && p->hM.dense && !(dl && atoi(dl) == 2)) A.lockstep = 3;
   return launch_rollout(p, A, wpc, st);
@@ -939,9 +940,9 @@ static int mpc_enqueue(dial_plan* p, int n_diffuse, int env_step, cudaStream_t s
   float* wts[2] = {p->weights, p->weights2};
   for (int i = 0; i < n_diffuse; ++i) {
     const float* noise = B.noise + (size_t)i * n1;
-    // small / medium sample counts: rng split folded into the rollout (key = split(rng)[1]) and the
-    // fused update kernel (which also advances rng); large ones keep the three-kernel sequence
-    const bool fused = c.Ntotal + 1 <= 16384 && !getenv("DIAL_NO_FUSED_UPDATE");
+    // rng split folded into the rollout (key = split(rng)[1]) and the fused update kernel (which also
+    // advances rng); beyond 131072 samples the three-kernel sequence is kept
+    const bool fused = c.Ntotal + 1 <= (1 << 17) && !getenv("DIAL_NO_FUSED_UPDATE");
     if (!fused) {
       mpc_split_kernel<<<1, 32, 0, st>>>(B.rng, p->mpc_key);
       p->launches++;
