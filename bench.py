@@ -38,10 +38,26 @@ METRIC = "sample-steps/s (Nsample*Hsample/wall-s) per MPC reverse_once, Go2"
 
 
 def usable_cores() -> int:
+    """Host cores this process may actually use: the affinity mask, capped by the cgroup CPU quota
+    (a GPU slot of a shared box sees all 128 logical CPUs but may be granted far fewer: running 128
+    threads on a 16-CPU quota measures the scheduler, not the code)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(-(-int(q) // int(per)))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = max(1, min(n, -(-q // per)))
+        except Exception:
+            pass
+    return n
 
 
 # --------------------------------------------------------------------------------------------
@@ -53,6 +69,7 @@ def usable_cores() -> int:
 # scheduling over the rows), the softmax update runs once on the gathered rewards.
 # --------------------------------------------------------------------------------------------
 _BARRIER = None     # multiprocessing.Barrier inherited by the forked workers
+LAST_THREADS = 1    # threads (C port) / processes (NumPy oracle) the last cpu_reverse_once ran fastest with
 
 
 def _cpu_worker(args):
@@ -81,9 +98,27 @@ def _cpu_worker(args):
         roll(s, np.zeros((4 * max(threads, 1), 2, env.nu)), threads=threads)   # spin up the OpenMP pool (untimed)
     t_in = 0.0
     best = float("inf")
+    best_threads = threads
     out = None
     if barrier is not None:
         barrier.wait()       # every worker has finished its set-up (NumPy env build, 10 settle steps)
+    if roll is not None and threads > 1:
+        # the logical CPU count of a shared GPU box says little about the CPUs a slot really gets
+        # (hyper-threads, cgroup shares, other tenants): try the thread counts cores, cores/2, ..., cores/16
+        # on the same reverse_once and keep the fastest
+        eps = rng.standard_normal((N, Hn + 1, env.nu))
+        us = pl.node2u(pl.make_Y0s(eps, Y, pl.sigma_control))[rows_lo:rows_hi]
+        th = threads
+        while th >= max(1, threads // 16):
+            for _ in range(n_calls):
+                t0 = time.perf_counter()
+                rews = roll(s, us, threads=th)
+                dt = time.perf_counter() - t0
+                if dt < best:
+                    best, best_threads = dt, th
+            out = rews
+            th //= 2
+        return best, out, best_threads
     for i in range(n_calls):
         eps = rng.standard_normal((N, Hn + 1, env.nu))        # same eps on every worker (same seed)
         Y0s = pl.make_Y0s(eps, Y, pl.sigma_control * b["tdf"] ** (i % b["Ndiffuse"]))
@@ -99,7 +134,7 @@ def _cpu_worker(args):
         out = rews
     # C port: best of the n_calls repetitions of the same reverse_once (thread start-up / scheduler
     # noise of a shared host); NumPy oracle (n_calls = 1): the call itself
-    return (best if kind == "port-c" else t_in), out
+    return (best if kind == "port-c" else t_in), out, best_threads
 
 
 def cpu_reverse_once(ci: int, procs: int, kind: str, n_calls: int = 1, rows_cap=None):
@@ -129,6 +164,8 @@ def cpu_reverse_once(ci: int, procs: int, kind: str, n_calls: int = 1, rows_cap=
         res = pool.map(_cpu_worker, jobs, chunksize=1)
     wall = max(r[0] for r in res)
     rews = np.concatenate([r[1] for r in res])
+    global LAST_THREADS
+    LAST_THREADS = res[0][2] if kind == "port-c" else procs
     t0 = time.perf_counter()                 # the one softmax on the gathered rewards (negligible)
     lp = (rews - rews[-1]) / rews.std() / b["temp"]
     w = np.exp(lp - lp.max())
@@ -166,10 +203,11 @@ def run_reference(args):
         vals.append(v)
         t_all += wall
     value = float(b["N"] * b["Hs"] * args.steps / t_all)
+    used = LAST_THREADS
     what = ("fp32 C port of the per-sample step (oracle/c)" if kind == "port-c" else "fp64 NumPy oracle port")
     sample = (f"one reverse_once of {b['name']} per step: all {b['N']}+1 rows x (Hsample+1)={b['Hs'] + 1} env steps split over "
-              f"{cores} host threads (C port: OpenMP over the rows; NumPy oracle: pinned processes), one softmax; {what}; CPU restatement, "
-              "not reference JAX")
+              f"the host's CPUs (C port: OpenMP over the rows, fastest of {cores}, {cores}/2 ... {cores}/16 threads = {used}; NumPy oracle: pinned "
+              f"processes), one softmax; {what}; CPU restatement, not reference JAX")
     line = dict(impl="reference", metric=METRIC, value=value, unit="sample-steps/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * t_all / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32" if kind == "port-c" else "f64",
@@ -177,7 +215,7 @@ def run_reference(args):
                 config=dict(workload=f"{b['name']} (BASELINE configs[{ci}])", Nsample_per_gpu=b["N"], Nsample_total=b["N"],
                             Hsample=b["Hs"], Hnode=b["Hn"], Ndiffuse=b["Ndiffuse"],
                             step="one reverse_once (metric is per reverse_once)"),
-                cpu_baseline=dict(value=value, unit="sample-steps/s", cores=cores, kind=kind, sample=sample),
+                cpu_baseline=dict(value=value, unit="sample-steps/s", cores=used, logical_cpus=cores, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="sample-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -471,12 +509,13 @@ def run_own(args):
         cap1 = 256 if kind == "port" else None
         v1, wall1, rows1 = cpu_reverse_once(ci, 1, kind, rows_cap=cap1)
         vall, wall, rows = cpu_reverse_once(ci, cores, kind)
-        cpu = dict(value=vall, unit="sample-steps/s", cores=cores, kind=kind,
+        used = LAST_THREADS
+        cpu = dict(value=vall, unit="sample-steps/s", cores=used, logical_cpus=cores, kind=kind,
                    sample=(f"one reverse_once of {b['name']}: all {rows} rows x {b['Hs'] + 1} env steps split over {cores} pinned "
                            f"single-threaded processes; single core: {v1:.1f} sample-steps/s on {rows1} rows; "
                            + ("fp32 C port of the per-sample step" if kind == "port-c" else "fp64 NumPy oracle")
                            + " — CPU restatement, not reference JAX"),
-                   single_core_value=v1, scaling_vs_linear=vall / (v1 * cores), wall_s=wall + wall1)
+                   single_core_value=v1, scaling_vs_linear=vall / (v1 * used), wall_s=wall + wall1)
         if kind == "port-c":               # the NumPy oracle beside it (bounded), for continuity with round 1
             vn, walln, rowsn = cpu_reverse_once(ci, cores, "port")
             cpu["numpy_oracle_value"] = vn

@@ -150,7 +150,7 @@ def test_reverse_once_at_baseline_size(built, ci):
     if over_rows.any():
         from dial_mpc_b200.envs.base_env import PipelineState, State
         plan = env._get_plan()
-        tq, tv, tr = (5e-5, 1e-3, 1e-3) if name != "allegro_reorient" else (1e-3, 5e-2, 5e-3)
+        sh_q, sh_v, sh_r = (5e-5, 1e-3, 1e-3) if name != "allegro_reorient" else (1e-3, 5e-2, 5e-3)
         for i in np.nonzero(over_rows)[0]:
             t = int(first_over[i])
             q0, v0, w0 = (sq, sv, sw) if t == 0 else (qo[i, t - 1], qdo[i, t - 1], wo[i, t - 1])
@@ -161,8 +161,8 @@ def test_reverse_once_at_baseline_size(built, ci):
             ev1 = float((np.abs(ps1.qvel.cpu().numpy() - qdo[i, t]) / (1 + np.abs(qdo[i, t]))).max())
             er1 = float(abs(float(r1) - ro[i, t]) / (1 + abs(ro[i, t])))
             shadow.append(dict(row=int(rows[i]), step=t, q_err=eq1, qvel_relerr=ev1, rew_relerr=er1,
-                               ok=bool(eq1 < tq and ev1 < tv and er1 < tr)))
-        rep["shadowing"] = dict(rows=len(shadow), all_ok=all(sh["ok"] for sh in shadow), tolerances=dict(q=tq, qvel_rel=tv, rew_rel=tr),
+                               ok=bool(eq1 < sh_q and ev1 < sh_v and er1 < sh_r)))
+        rep["shadowing"] = dict(rows=len(shadow), all_ok=all(sh["ok"] for sh in shadow), tolerances=dict(q=sh_q, qvel_rel=sh_v, rew_rel=sh_r),
                                 q_err_max=max(sh["q_err"] for sh in shadow), qvel_relerr_max=max(sh["qvel_relerr"] for sh in shadow),
                                 rew_relerr_max=max(sh["rew_relerr"] for sh in shadow), detail=shadow[:40])
         if rep["shadowing"]["all_ok"]:
