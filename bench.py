@@ -38,26 +38,29 @@ METRIC = "sample-steps/s (Nsample*Hsample/wall-s) per MPC reverse_once, Go2"
 
 
 def usable_cores() -> int:
-    """Host cores this process may actually use: the affinity mask, capped by the cgroup CPU quota
-    (a GPU slot of a shared box sees all 128 logical CPUs but may be granted far fewer: running 128
-    threads on a 16-CPU quota measures the scheduler, not the code)."""
+    """Logical CPUs in this process's affinity mask (the CPU arms then look for the fastest thread
+    count at or below it: hyper-threads and other tenants make the full count a poor choice)."""
     try:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
+    return n
+
+
+def cpu_quota():
+    """cgroup CPU quota in CPUs (None: unlimited).  Reported, not enforced here: CFS throttles per
+    100 ms period, so one reverse_once (< 1 s of CPU) bursts over every core of the box even under
+    a 16-CPU quota (measured: 64 threads = 55x one core); a sustained loop would be held to it."""
     try:
         q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
-        if q != "max":
-            n = max(1, min(n, int(-(-int(q) // int(per)))))
+        return None if q == "max" else int(q) / int(per)
     except Exception:
         try:
             q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
             per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
-            if q > 0:
-                n = max(1, min(n, -(-q // per)))
+            return q / per if q > 0 else None
         except Exception:
-            pass
-    return n
+            return None
 
 
 # --------------------------------------------------------------------------------------------
@@ -215,7 +218,8 @@ def run_reference(args):
                 config=dict(workload=f"{b['name']} (BASELINE configs[{ci}])", Nsample_per_gpu=b["N"], Nsample_total=b["N"],
                             Hsample=b["Hs"], Hnode=b["Hn"], Ndiffuse=b["Ndiffuse"],
                             step="one reverse_once (metric is per reverse_once)"),
-                cpu_baseline=dict(value=value, unit="sample-steps/s", cores=used, logical_cpus=cores, kind=kind, sample=sample),
+                cpu_baseline=dict(value=value, unit="sample-steps/s", cores=used, logical_cpus=cores, cgroup_cpu_quota=cpu_quota(),
+                                  kind=kind, sample=sample),
                 e2e=dict(value=value, unit="sample-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -510,7 +514,7 @@ def run_own(args):
         v1, wall1, rows1 = cpu_reverse_once(ci, 1, kind, rows_cap=cap1)
         vall, wall, rows = cpu_reverse_once(ci, cores, kind)
         used = LAST_THREADS
-        cpu = dict(value=vall, unit="sample-steps/s", cores=used, logical_cpus=cores, kind=kind,
+        cpu = dict(value=vall, unit="sample-steps/s", cores=used, logical_cpus=cores, cgroup_cpu_quota=cpu_quota(), kind=kind,
                    sample=(f"one reverse_once of {b['name']}: all {rows} rows x {b['Hs'] + 1} env steps split over {cores} pinned "
                            f"single-threaded processes; single core: {v1:.1f} sample-steps/s on {rows1} rows; "
                            + ("fp32 C port of the per-sample step" if kind == "port-c" else "fp64 NumPy oracle")
