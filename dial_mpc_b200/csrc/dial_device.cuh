@@ -130,6 +130,7 @@ struct RolloutArgs {
   float* qvel_out;
   float* warm_out;
   float* ctrl_out;
+  float* kin_out;       // [13] x.pos(3), x.rot(4), body-frame xd.vel(3), xd.ang*pi/180(3) of the torso body after row 0's last step, or null
   // device-resident MPC loop (dial_mpc_step): counters / key live in HBM so that a captured CUDA
   // graph can be replayed without patching kernel arguments
   const int32_t* counters_in;   // non-null: {step0, stage0} read from here
@@ -2907,6 +2908,13 @@ DEV void rollout_warp(const DevModel* Mp, const DevPlan* Pp, float* slab, const 
     if (A.qvel_out) for (int i = lane; i < nv; i += 32) A.qvel_out[i] = SM(qvel)[i];
     if (A.warm_out) for (int i = lane; i < nv; i += 32) A.warm_out[i] = SM(warm)[i];
     if (A.ctrl_out) for (int i = lane; i < nu; i += 32) A.ctrl_out[i] = SM(ctrl)[i];
+    if (A.kin_out && lane == 0) {   // what the envs' _get_obs reads of pipeline_state.x / xd (kinematics of the last forward pass)
+      const BaseKin bk = base_kin(w, c.torso_body);
+      A.kin_out[0] = bk.pos.x; A.kin_out[1] = bk.pos.y; A.kin_out[2] = bk.pos.z;
+      A.kin_out[3] = bk.rot.w; A.kin_out[4] = bk.rot.x; A.kin_out[5] = bk.rot.y; A.kin_out[6] = bk.rot.z;
+      A.kin_out[7] = bk.vb.x; A.kin_out[8] = bk.vb.y; A.kin_out[9] = bk.vb.z;
+      A.kin_out[10] = bk.ab.x; A.kin_out[11] = bk.ab.y; A.kin_out[12] = bk.ab.z;
+    }
     if (A.counters_out && lane == 0) { A.counters_out[0] = step; A.counters_out[1] = stage; }
   }
 }

@@ -712,11 +712,17 @@ extern "C" int dial_rollout(dial_plan* p, const dial_state* s, const float* us, 
 
 extern "C" int dial_env_step(dial_plan* p, const dial_state* s, const float* action, float* qpos_out,
                              float* qvel_out, float* warm_out, float* reward, float* ctrl_out, void* stream) {
+  return dial_env_step_kin(p, s, action, qpos_out, qvel_out, warm_out, reward, ctrl_out, nullptr, stream);
+}
+
+extern "C" int dial_env_step_kin(dial_plan* p, const dial_state* s, const float* action, float* qpos_out,
+                                 float* qvel_out, float* warm_out, float* reward, float* ctrl_out, float* kin_out,
+                                 void* stream) {
   if (!p || !s || !action || !qpos_out || !qvel_out || !warm_out || !reward) return fail("dial_env_step: null argument");
   RolloutArgs A; memset(&A, 0, sizeof(A));
   fill_state(A, s);
   A.nrows = 1; A.H = 1; A.mode = 0; A.us = action; A.rewss = reward;
-  A.qpos_out = qpos_out; A.qvel_out = qvel_out; A.warm_out = warm_out; A.ctrl_out = ctrl_out;
+  A.qpos_out = qpos_out; A.qvel_out = qvel_out; A.warm_out = warm_out; A.ctrl_out = ctrl_out; A.kin_out = kin_out;
   CUDA_OK(launch_rollout(p, A, 1, (cudaStream_t)stream));
   return 0;
 }

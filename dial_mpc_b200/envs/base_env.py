@@ -62,6 +62,7 @@ class PipelineState:
     qvel: Any
     qacc_warmstart: Any
     ctrl: Any = None
+    kin: Any = None     # [13] torso x.pos, x.rot, body-frame xd.vel, xd.ang*pi/180 after env.step (for _get_obs)
 
     @property
     def q(self):
@@ -186,11 +187,22 @@ class BaseEnv:
         from dial_mpc_b200 import random as drandom
         rng, _ = drandom.split(rng)
         ps = self._get_plan().pipeline_init(self._init_q)
-        return State(ps, None, 0.0, 0.0, {}, self._init_info(rng))
+        info = self._init_info(rng)
+        return State(ps, self._get_obs(ps, info), 0.0, 0.0, {}, info)
 
     def _next_info(self, info: Dict[str, Any]) -> Dict[str, Any]:
         new = dict(info)
         new["step"] = info["step"] + 1
+        c = self._config
+        if "vel_tar" in info and hasattr(c, "default_vx"):
+            # commanded velocities ramped from the PRE-increment step, fp32 like the reference
+            # (unitree_go2_env.py:151-163, unitree_h1_env.py:208-219; randomize_tasks is not built)
+            f = np.float32
+            ramp = f(info["step"]) * f(self.dt) / f(c.ramp_up_time)
+            vel = np.array([c.default_vx, c.default_vy, 0.0], dtype=f)
+            ang = np.array([0.0, 0.0, c.default_vyaw], dtype=f)
+            new["vel_tar"] = np.minimum(vel * ramp, vel)
+            new["ang_vel_tar"] = np.minimum(ang * ramp, ang)
         return new
 
     def step(self, state: State, action) -> State:
@@ -198,7 +210,49 @@ class BaseEnv:
         ps, reward = self._get_plan().env_step(state, action)
         info = self._next_info(state.info)
         info["rng"], _ = drandom.split(state.info["rng"])
-        return State(ps, None, reward, 0.0, state.metrics, info)
+        # the observation is taken before the info update (unitree_go2_env.py:139)
+        return State(ps, self._get_obs(ps, state.info), reward, self._get_done(ps, state.info), state.metrics, info)
+
+    # -- observation / termination flag (device tensors; not on the sampling path) ---------------
+    _done_height = 0.18      # torso height below which the locomotion envs flag `done`
+
+    @staticmethod
+    def _dev(ps, a):
+        import torch
+        return torch.as_tensor(np.asarray(a, dtype=np.float32), device=ps.qpos.device)
+
+    def _vb_ab(self, ps):
+        """global_to_body_velocity of the torso's xd.vel and xd.ang*pi/180: written by the kernel
+        from the kinematics of the step's forward pass (Brax x / xd are one integration behind
+        qpos); zero at reset (qvel = 0)."""
+        import torch
+        return ps.kin[7:13] if ps.kin is not None else torch.zeros(6, device=ps.qpos.device)
+
+    def _ctrl(self, ps):
+        import torch
+        return ps.ctrl if ps.ctrl is not None else torch.zeros(self.sys.nu, device=ps.qpos.device)
+
+    def _get_obs(self, pipeline_state: PipelineState, info: Dict[str, Any]):
+        """``_get_obs`` of the walk envs (unitree_go2_env.py:263-286, unitree_h1_env.py:323-346):
+        [vel_tar, ang_vel_tar, ctrl, qpos, vb, ab, qvel[6:]]."""
+        import torch
+        ps = pipeline_state
+        return torch.cat([self._dev(ps, info.get("vel_tar", np.zeros(3))), self._dev(ps, info.get("ang_vel_tar", np.zeros(3))),
+                          self._ctrl(ps), ps.qpos, self._vb_ab(ps), ps.qvel[6:]])
+
+    def _get_done(self, pipeline_state: PipelineState, info: Dict[str, Any]):
+        """Termination flag of the locomotion envs (unitree_go2_env.py:241-248, :498-505,
+        unitree_h1_env.py:300-308): torso upside down, a joint outside ``joint_range``, or the torso
+        below ``_done_height``.  The planner never reads it (``reward_alive`` has weight 0)."""
+        import torch
+        ps = pipeline_state
+        if ps.kin is None:
+            return torch.zeros((), device=ps.qpos.device)
+        jr = self._dev(ps, self.joint_range)
+        ja = ps.qpos[7:7 + jr.shape[0]]
+        up_z = 1.0 - 2.0 * (ps.kin[4] ** 2 + ps.kin[5] ** 2)      # dot(rotate(up, rot), up)
+        done = (up_z < 0) | (ja < jr[:, 0]).any() | (ja > jr[:, 1]).any() | (ps.kin[2] < self._done_height)
+        return done.to(torch.float32)
 
 
 def _to_numpy(x):

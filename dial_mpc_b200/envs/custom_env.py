@@ -48,6 +48,16 @@ class CustomRewardEnv(BaseEnv):
             self._library_path = custom.build_library(self.reward_source, model=self.sys.model)
         return self._library_path
 
+    def _get_obs(self, pipeline_state, info):
+        """Default observation of a custom env: [qpos, qvel] (the reference user writes their own;
+        override for anything else — it is not on the sampling path)."""
+        import torch
+        return torch.cat([pipeline_state.qpos, pipeline_state.qvel])
+
+    def _get_done(self, pipeline_state, info):
+        import torch
+        return torch.zeros((), device=pipeline_state.qpos.device)
+
     def user_params(self) -> np.ndarray:
         """Constants for the reward (``ctx->user``)."""
         return np.zeros(0, dtype=np.float32)

@@ -42,6 +42,14 @@ class AllegroReorientEnv(BaseEnv):
     def _init_info(self, rng) -> Dict[str, Any]:
         return {"rng": rng, "ang_vel_tar": self._ang_vel_tar.copy(), "pos_tar": self._pos_tar.copy(), "step": 0}
 
+    def _get_obs(self, pipeline_state, info):
+        import torch
+        return torch.zeros(1, device=pipeline_state.qpos.device)     # manipulation.py:57,97
+
+    def _get_done(self, pipeline_state, info):
+        import torch
+        return torch.full((1,), float(info["step"] >= 100), device=pipeline_state.qpos.device)   # manipulation.py:86-87
+
     def act2joint(self, act):
         """manipulation.py:102-115: the sampling range is shifted by the initial joint pose."""
         act = np.asarray(act, dtype=np.float64)

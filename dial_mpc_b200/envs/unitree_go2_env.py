@@ -149,15 +149,46 @@ class UnitreeGo2SeqJumpEnv(UnitreeGo2Env):
 
     def _init_info(self, rng) -> Dict[str, Any]:
         info = super()._init_info(rng)
-        info.update(last_ctrl=np.zeros(12), contact_stage=0,
+        info.update(last_ctrl=np.zeros(12, dtype=np.float32), contact_stage=0,
                     contact_targets=self._contact_targets,
                     contact_target_radius=self._contact_target_radius,
                     pose_target_sequence=self._pose_target_sequence,
                     yaw_target_sequence=self._yaw_target_sequence)
         return info
 
+    _done_height = 0.1
+
+    def _get_obs(self, pipeline_state, info):
+        """unitree_go2_env.py:523-557: [vel_tar, ang_vel_tar, last_ctrl, torso position error to
+        the stage's pose target, roll, pitch, wrapped yaw error, joint angles, vb, ab, joint
+        velocities]."""
+        import torch
+        ps = pipeline_state
+        w, x, y, z = ps.qpos[3], ps.qpos[4], ps.qpos[5], ps.qpos[6]
+        # brax.math.quat_to_euler
+        ez = torch.atan2(-2 * x * y + 2 * w * z, x * x + w * w - z * z - y * y)
+        ey = torch.asin(torch.clamp(2 * x * z + 2 * w * y, -1.0, 1.0))
+        ex = torch.atan2(-2 * y * z + 2 * w * x, z * z - y * y - x * x + w * w)
+        stage = int(info.get("contact_stage", 0))
+        pos = ps.kin[0:3] if ps.kin is not None else ps.qpos[0:3]
+        dpos = pos - self._dev(ps, info.get("pose_target_sequence", self._pose_target_sequence)[stage])
+        dyaw = ez - float(info.get("yaw_target_sequence", self._yaw_target_sequence)[stage])
+        dyaw = torch.atan2(torch.sin(dyaw), torch.cos(dyaw)).reshape(1)
+        last = info.get("last_ctrl", np.zeros(12))
+        last = last if torch.is_tensor(last) else self._dev(ps, last)
+        return torch.cat([self._dev(ps, info.get("vel_tar", np.zeros(3))), self._dev(ps, info.get("ang_vel_tar", np.zeros(3))), last, dpos,
+                          torch.stack([ex, ey]), dyaw, ps.qpos[7:], self._vb_ab(ps), ps.qvel[6:]])
+
+    def step(self, state, action):
+        new = super().step(state, action)
+        new.info["last_ctrl"] = new.pipeline_state.ctrl          # unitree_go2_env.py:516
+        return new
+
     def _next_info(self, info):
         new = super()._next_info(info)
+        for k in ("vel_tar", "ang_vel_tar"):       # no ramp in this env
+            if k in info:
+                new[k] = info[k]
         n = len(self._contact_targets)
         new["contact_stage"] = int(min(np.floor(np.float32(new["step"]) * np.float32(self.dt)
                                                 / np.float32(self._config.jump_dt)), n - 1))

@@ -103,9 +103,12 @@ class Plan:
         s, keep = self._state(state)
         a = self.f32(action, (self.nu,))
         qo, vo, wo, r, c = self.empty(self.nq), self.empty(self.nv), self.empty(self.nv), self.empty(1), self.empty(self.nu)
-        self._check(self.lib.dial_env_step(self.handle, C.byref(s), _ptr(a), _ptr(qo), _ptr(vo), _ptr(wo), _ptr(r),
-                                           _ptr(c), _stream()))
-        return PipelineState(qo, vo, wo, c), r[0]
+        kin = self.empty(13)
+        self._check(self.lib.dial_env_step_kin(self.handle, C.byref(s), _ptr(a), _ptr(qo), _ptr(vo), _ptr(wo), _ptr(r),
+                                               _ptr(c), _ptr(kin), _stream()))
+        ps = PipelineState(qo, vo, wo, c)
+        ps.kin = kin      # torso x.pos, x.rot, body-frame velocities (what _get_obs reads of x / xd)
+        return ps, r[0]
 
     def rollout(self, state, us, want_traj=True):
         s, keep = self._state(state)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DIAL_ABI_VERSION 5
+#define DIAL_ABI_VERSION 6
 
 /* capacities of the fixed-size device model */
 #define DIAL_MAXB 24   /* bodies incl. world            */
@@ -163,6 +163,14 @@ int dial_rollout(dial_plan* plan, const dial_state* s, const float* us, int B, i
 int dial_env_step(dial_plan* plan, const dial_state* s, const float* action,
                   float* qpos_out, float* qvel_out, float* warm_out, float* reward,
                   float* ctrl_out, void* stream);
+
+/* The same step, also returning what the envs' `_get_obs` (envs/unitree_go2_env.py:263-286,
+ * unitree_h1_env.py:323-346) reads of pipeline_state.x / xd: kin_out [dev][13] = x.pos(3),
+ * x.rot(4) of the torso body, then global_to_body_velocity(xd.vel) (3) and
+ * global_to_body_velocity(xd.ang * pi/180) (3) (nullable). */
+int dial_env_step_kin(dial_plan* plan, const dial_state* s, const float* action,
+                      float* qpos_out, float* qvel_out, float* warm_out, float* reward,
+                      float* ctrl_out, float* kin_out, void* stream);
 
 /* pipeline_init — envs/unitree_go2_env.py:104: mjx.forward at (qpos, qvel=0):
  * normalises the quaternion and produces the initial qacc_warmstart. */

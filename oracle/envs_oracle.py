@@ -140,8 +140,44 @@ class OracleEnv:
         qpos, qvel, warm, d, ctrl = self._physics(s, action)
         rew, stage = self.reward(s, qpos, qvel, d, ctrl)
         ns = OState(qpos, qvel, warm, s.step + 1, stage)
-        aux = dict(q=qpos, qd=qvel, xpos=d.xpos[:, 1:], ctrl=ctrl, data=d)
+        aux = dict(q=qpos, qd=qvel, xpos=d.xpos[:, 1:], ctrl=ctrl, data=d, prev=s)
         return ns, rew, aux
+
+    # -- observation / done of env.step (not on the sampling path) ----------------------------
+    done_height = 0.18
+
+    def info_targets(self, step):
+        """state.info["vel_tar"/"ang_vel_tar"] as the state ENTERING step number `step` carries
+        them: zero after reset, else ramped from the previous (pre-increment) step
+        (unitree_go2_env.py:108-110,156-163)."""
+        step = np.asarray(step, dtype=np.float64)
+        ramp = np.maximum(step - 1.0, 0.0)[:, None] * self.dt / self.ramp_up_time
+        live = (step >= 1)[:, None]
+        return (np.where(live, np.minimum(self.vel_cmd * ramp, self.vel_cmd), 0.0),
+                np.where(live, np.minimum(self.ang_cmd * ramp, self.ang_cmd), 0.0))
+
+    def _vb_ab(self, d):
+        v = mo.brax_views(self.m, d)
+        rot_b = v["x_rot"][:, self.torso]
+        return (inv_rotate(v["xd_vel"][:, self.torso], rot_b),
+                inv_rotate(v["xd_ang"][:, self.torso] * np.pi / 180.0, rot_b), v)
+
+    def observe(self, s: OState, qpos, qvel, d, ctrl, last_ctrl=None):
+        """_get_obs(pipeline_state, state.info) of the walk envs (unitree_go2_env.py:263-286,
+        unitree_h1_env.py:323-346, :850-873) for the step s -> (qpos, qvel, d)."""
+        vel_tar, ang_tar = self.info_targets(s.step)
+        vb, ab, _ = self._vb_ab(d)
+        return np.concatenate([vel_tar, ang_tar, ctrl, qpos, vb, ab, qvel[:, 6:]], -1)
+
+    def done(self, s: OState, qpos, qvel, d):
+        """unitree_go2_env.py:241-248 / unitree_h1_env.py:300-308."""
+        v = mo.brax_views(self.m, d)
+        up = np.array([0.0, 0.0, 1.0])
+        ja = qpos[:, 7:7 + len(self.joint_range)]
+        dn = rotate(up, v["x_rot"][:, self.torso])[:, 2] < 0
+        dn |= np.any(ja < self.joint_range[:, 0], -1) | np.any(ja > self.joint_range[:, 1], -1)
+        dn |= v["x_pos"][:, self.torso, 2] < self.done_height
+        return dn.astype(np.float64)
 
     def rollout(self, s0: OState, us):
         """rollout_us (dial_core.py:36-42) vmapped: us [B,H,nu] ->
@@ -222,6 +258,19 @@ class Go2SeqJumpOracle(Go2WalkOracle):
         self.pose_seq, self.yaw_seq = pose, yaw
         self.joint_range = np.array([[-0.5, 0.5], [0.4, 2.0], [-2.3, -1.3]] * 2
                                     + [[-0.5, 0.5], [0.4, 1.4], [-2.3, -1.3]] * 2)
+
+    done_height = 0.1
+
+    def observe(self, s, qpos, qvel, d, ctrl, last_ctrl=None):
+        """unitree_go2_env.py:523-557 (vel_tar / ang_vel_tar stay zero in this env)."""
+        vb, ab, v = self._vb_ab(d)
+        B = qpos.shape[0]
+        rpy = quat_to_euler(qpos[:, 3:7])
+        dpos = v["x_pos"][:, self.torso] - self.pose_seq[s.stage]
+        dyaw = rpy[:, 2] - self.yaw_seq[s.stage]
+        dyaw = np.arctan2(np.sin(dyaw), np.cos(dyaw))[:, None]
+        last = np.zeros((B, self.nu)) if last_ctrl is None else np.broadcast_to(last_ctrl, (B, self.nu))
+        return np.concatenate([np.zeros((B, 6)), last, dpos, rpy[:, :2], dyaw, qpos[:, 7:], vb, ab, qvel[:, 6:]], -1)
 
     def reward(self, s, qpos, qvel, d, ctrl):
         v = mo.brax_views(self.m, d)

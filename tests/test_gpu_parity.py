@@ -401,3 +401,79 @@ def test_device_loop_graph_equals_eager_loop(built, name):
     torch.cuda.synchronize()
     assert torch.equal(q_before, loop.buf["qpos"]) and torch.equal(c_before, loop.buf["counters"])
     assert torch.isfinite(loop.Y).all()
+
+
+@pytest.mark.parametrize("name", ["unitree_go2_walk", "unitree_go2_seq_jump", "unitree_h1_walk", "unitree_h1_loco",
+                                  "allegro_reorient"])
+def test_env_step_obs_and_done_match_oracle(built, name):
+    """State.obs / State.done of env.reset / env.step against the oracle's restatement of the
+    envs' _get_obs (unitree_go2_env.py:263-286, :523-557, unitree_h1_env.py:323-346, :850-873;
+    manipulation.py:57,86-97): same layout, the info targets of the state ENTERING the step."""
+    from dial_mpc_b200 import random as drandom
+    env, o = make_pair(name)
+    s = o.reset()
+    st = env.reset(drandom.PRNGKey(0))
+    if name == "allegro_reorient":
+        assert tuple(st.obs.shape) == (1,) and float(st.obs[0]) == 0.0
+        st = env.step(st, np.zeros(env.action_size))
+        assert tuple(st.obs.shape) == (1,) and float(st.done[0]) == 0.0 and st.info["step"] == 1
+        return
+    d0 = __import__("oracle.mjx_oracle", fromlist=["forward"]).forward(
+        o.m, s.qpos, s.qvel, np.zeros((1, o.nu)), s.qacc_warmstart)
+    ob0 = o.observe(s, s.qpos, s.qvel, d0, np.zeros((1, o.nu)))[0]
+    assert st.obs.shape[0] == ob0.shape[0]
+    assert np.abs(st.obs.cpu().numpy() - ob0).max() < 1e-5
+    rng = np.random.default_rng(3)
+    last = None
+    for t in range(8):
+        a = np.clip(rng.normal(size=env.action_size) * 0.4, -1, 1)
+        s_prev = s
+        s, r, aux = o.step(s, a[None])
+        ob = o.observe(s_prev, aux["q"], aux["qd"], aux["data"], aux["ctrl"], last_ctrl=last)[0]
+        dn = o.done(s_prev, aux["q"], aux["qd"], aux["data"])[0]
+        last = aux["ctrl"]
+        st = env.step(st, a)
+        og = st.obs.cpu().numpy()
+        assert og.shape == ob.shape
+        tol = 2e-4 + 1e-2 * (np.abs(ob) > 5)          # velocities / torques: the qvel tolerance
+        err = np.abs(og - ob)
+        assert (err <= np.maximum(tol, 2e-3 * (1 + np.abs(ob)))).all(), (t, int(err.argmax()), err.max())
+        assert float(st.done) == dn
+        if "vel_tar" in st.info and name != "unitree_go2_seq_jump":
+            vt, at = o.info_targets(s.step)
+            assert np.abs(np.asarray(st.info["vel_tar"]) - vt[0]).max() < 1e-6
+            assert np.abs(np.asarray(st.info["ang_vel_tar"]) - at[0]).max() < 1e-6
+
+
+@pytest.mark.parametrize("N", [16384, 65536])
+def test_fused_update_equals_unfused_at_multi_gpu_totals(built, N):
+    """The control-step graph's fused update kernel (statistics + weights + weighted knot sum in
+    one launch) at the reward counts an 8-GPU run sees (8 x 2048 and configs[4]'s 65536) against
+    the separate weights / Ybar kernels: same rollouts (bitwise), same knots to rounding."""
+    from dial_mpc_b200 import random as drandom
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import DeviceLoop, MBDPI
+    env, _ = make_pair("unitree_go2_walk")
+    args = DialConfig(env_name="unitree_go2_walk", Nsample=N, Hsample=3, Hnode=1, Ndiffuse=2, Ndiffuse_init=2,
+                      temp_sample=0.05, horizon_diffuse_factor=0.9, traj_diffuse_factor=0.5)
+    out = []
+    for unfused in (False, True):
+        if unfused:
+            os.environ["DIAL_NO_FUSED_UPDATE"] = "1"
+        try:
+            mb = MBDPI(args, env)
+            rng = drandom.PRNGKey(5)
+            rng, r0 = drandom.split(rng)
+            state = env.reset(r0)
+            loop = DeviceLoop(mb, state, rng, torch.zeros(args.Hnode + 1, mb.nu, device="cuda"))
+            for _ in range(3):           # eager, eager, graph replay
+                loop.step(args.Ndiffuse)
+            torch.cuda.synchronize()
+            out.append((loop.Y.clone(), loop.info()["rews"].clone(), loop.state().info["rng"].copy()))
+        finally:
+            os.environ.pop("DIAL_NO_FUSED_UPDATE", None)
+    (Ya, ra, ka), (Yb, rb, kb) = out
+    assert np.array_equal(ka, kb)
+    assert torch.isfinite(Ya).all() and ra.shape[0] == N + 1
+    assert (Ya - Yb).abs().max() < 2e-4
+    assert (ra - rb).abs().max() < 2e-3 * (1 + float(rb.abs().max()))
