@@ -515,8 +515,10 @@ def run_own(args):
         vall, wall, rows = cpu_reverse_once(ci, cores, kind)
         used = LAST_THREADS
         cpu = dict(value=vall, unit="sample-steps/s", cores=used, logical_cpus=cores, cgroup_cpu_quota=cpu_quota(), kind=kind,
-                   sample=(f"one reverse_once of {b['name']}: all {rows} rows x {b['Hs'] + 1} env steps split over {cores} pinned "
-                           f"single-threaded processes; single core: {v1:.1f} sample-steps/s on {rows1} rows; "
+                   sample=(f"one reverse_once of {b['name']}: all {rows} rows x {b['Hs'] + 1} env steps over "
+                           + (f"{used} OpenMP threads of one process (fastest of {cores}, {cores}/2 ... {cores}/16 threads, best of 3)"
+                              if kind == "port-c" else f"{cores} pinned single-threaded processes")
+                           + f"; single core: {v1:.1f} sample-steps/s on {rows1} rows; "
                            + ("fp32 C port of the per-sample step" if kind == "port-c" else "fp64 NumPy oracle")
                            + " — CPU restatement, not reference JAX"),
                    single_core_value=v1, scaling_vs_linear=vall / (v1 * used), wall_s=wall + wall1)

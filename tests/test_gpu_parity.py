@@ -454,7 +454,7 @@ def test_fused_update_equals_unfused_at_multi_gpu_totals(built, N):
     from dial_mpc_b200.core.dial_config import DialConfig
     from dial_mpc_b200.core.dial_core import DeviceLoop, MBDPI
     env, _ = make_pair("unitree_go2_walk")
-    args = DialConfig(env_name="unitree_go2_walk", Nsample=N, Hsample=3, Hnode=1, Ndiffuse=2, Ndiffuse_init=2,
+    args = DialConfig(env_name="unitree_go2_walk", Nsample=N, Hsample=4, Hnode=2, Ndiffuse=2, Ndiffuse_init=2,
                       temp_sample=0.05, horizon_diffuse_factor=0.9, traj_diffuse_factor=0.5)
     out = []
     for unfused in (False, True):
