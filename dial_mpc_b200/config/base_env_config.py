@@ -6,7 +6,7 @@ from dataclasses import dataclass
 @dataclass
 class BaseEnvConfig:
     task_name: str = "default"
-    randomize_tasks: bool = False  # not supported by the fused CUDA rewards (must stay False)
+    randomize_tasks: bool = False  # walk envs: a one-step random command every 500 steps (dial_plan_set_command)
     kp: float = 30.0  # P gain, or a list of P gains for each joint
     kd: float = 1.0  # D gain, or a list of D gains for each joint
     debug: bool = False

@@ -308,6 +308,11 @@ class DeviceLoop:
             noise=(mbdpi.schedule(nmax) if noise is None else f(noise)).contiguous())
         assert tuple(self.buf["noise"].shape) == (nmax, a.Hnode + 1) or self.buf["noise"].shape[0] >= nmax
         self.n_diffuse_max = nmax
+        # randomize_tasks: host mirror of info["step"] / info["rng"] (the env's key chain), from which
+        # the one-step random command the horizon may reach is computed ahead (BaseEnv.command_override)
+        self._rand = bool(state.info.get("randomize_target", False))
+        self._env_info = {"randomize_target": self._rand, "step": int(state.info.get("step", 0)),
+                          "rng": np.asarray(state.info.get("rng", np.zeros(2)), dtype=np.uint32).copy()}
         pl.mpc_bind(self.buf, mbdpi.M_shift.cpu().numpy())
 
     def step(self, n_diffuse: Optional[int] = None, env_step=True) -> None:
@@ -316,7 +321,17 @@ class DeviceLoop:
         n = self.mbdpi.args.Ndiffuse if n_diffuse is None else int(n_diffuse)
         if n > self.n_diffuse_max:
             raise ValueError("n_diffuse exceeds the bound noise schedule")
+        stepping = env_step is True or env_step == 1
+        if self._rand:
+            # the env step (if any) runs at info["step"], the rollouts cover the Hsample+1 steps after it
+            self.plan.set_command(self.mbdpi.env.command_override(
+                self._env_info, self.mbdpi.args.Hsample + (2 if stepping else 1)))
         self.plan.mpc_step(n, env_step)
+        if stepping:
+            self._env_info["step"] += 1
+            if self._rand:
+                from dial_mpc_b200 import random as drandom
+                self._env_info["rng"] = drandom.split(self._env_info["rng"])[0]
 
     def rng_host(self) -> np.ndarray:
         """The planner rng after the steps launched so far (synchronises)."""
@@ -332,6 +347,7 @@ class DeviceLoop:
             self.buf["qacc_warmstart"].copy_(self.plan.f32(qacc_warmstart))
         if step is not None:
             self.buf["counters"][0] = int(step)
+            self._env_info["step"] = int(step)
 
     @property
     def action(self) -> torch.Tensor:

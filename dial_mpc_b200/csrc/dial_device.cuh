@@ -102,7 +102,7 @@ struct alignas(16) DevModel {
 
 struct alignas(16) DevPlan {
   dial_plan_desc c;
-  int32_t pad_[2];
+  int32_t pad_[3];
 };
 
 // arguments of one rollout launch
@@ -2715,8 +2715,11 @@ DEV float reward_lane0(WarpCtx& w, int step, int& stage, float part0, float part
   }
   if (c.env_id == DIAL_ENV_GO2_WALK || c.env_id == DIAL_ENV_H1_WALK || c.env_id == DIAL_ENV_H1_LOCO) {
     float ramp = stepf * c.dt / c.ramp_up_time;
-    float vtx = fminf(c.vel_cmd[0] * ramp, c.vel_cmd[0]), vty = fminf(c.vel_cmd[1] * ramp, c.vel_cmd[1]);
-    float atz = fminf(c.ang_cmd[2] * ramp, c.ang_cmd[2]);
+    // randomize_tasks: a one-step command override (dial_plan_set_command)
+    const float* vel_cmd = step == c.cmd_step ? c.cmd_vel : c.vel_cmd;
+    const float* ang_cmd = step == c.cmd_step ? c.cmd_ang : c.ang_cmd;
+    float vtx = fminf(vel_cmd[0] * ramp, vel_cmd[0]), vty = fminf(vel_cmd[1] * ramp, vel_cmd[1]);
+    float atz = fminf(ang_cmd[2] * ramp, ang_cmd[2]);
     const float r_gaits = part0;   // per-foot terms: reward_partials
     float yaw_tar = 0.f + atz * c.dt * stepf;
     float dyaw = quat_yaw(bk.rot) - yaw_tar;
@@ -2730,7 +2733,7 @@ DEV float reward_lane0(WarpCtx& w, int step, int& stage, float part0, float part
       rew = 0.1f * r_gaits + 0.5f * r_upright + 0.3f * r_yaw + r_vel + r_ang + r_h;
     } else if (c.env_id == DIAL_ENV_H1_LOCO) {
       // unitree_h1_env.py:774-800: all three body-rate components, foot-level and energy terms
-      float atx = fminf(c.ang_cmd[0] * ramp, c.ang_cmd[0]), aty = fminf(c.ang_cmd[1] * ramp, c.ang_cmd[1]);
+      float atx = fminf(ang_cmd[0] * ramp, ang_cmd[0]), aty = fminf(ang_cmd[1] * ramp, ang_cmd[1]);
       float r_ang3 = -((bk.ab.x - atx) * (bk.ab.x - atx) + (bk.ab.y - aty) * (bk.ab.y - aty) + (bk.ab.z - atz) * (bk.ab.z - atz));
       float r_level = 0.f;
       for (int f = 0; f < c.nfeet; ++f) {

@@ -611,6 +611,7 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
   if (p->variant < 0) { g_err = "the dense (elliptic) solver path is instantiated for nv = 22 only"; delete p; return nullptr; }
   memset(&p->hP, 0, sizeof(DevPlan));
   p->hP.c = *cfg;
+  p->hP.c.cmd_step = -1;      // command overrides come through dial_plan_set_command only
   const dial_plan_desc& c = *cfg;
   if (c.Hsample + 1 > DIAL_MAXH || c.Hnode + 1 > DIAL_MAXNODE || c.Hnode < 1 || c.Nsample < 1 || c.Ntotal < c.Nsample ||
       c.n_frames < 1 || (c.Hnode + 1) * model->nu > YBAR_THREADS || c.n_stage > DIAL_MAXSTAGE) {
@@ -707,6 +708,19 @@ extern "C" int dial_rollout(dial_plan* p, const dial_state* s, const float* us, 
   fill_state(A, s);
   A.nrows = B; A.H = H; A.mode = 0; A.us = us; A.rewss = rewss; A.q = q; A.qd = qd; A.xpos = xpos;
   CUDA_OK(launch_rollout_any(p, A, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int dial_plan_set_command(dial_plan* p, int cmd_step, const float* vel, const float* ang, void* stream) {
+  if (!p) return fail("dial_plan_set_command: null plan");
+  if (cmd_step >= 0 && (!vel || !ang)) return fail("dial_plan_set_command: null command");
+  dial_plan_desc& c = p->hP.c;
+  c.cmd_step = cmd_step;
+  for (int i = 0; i < 3; ++i) { c.cmd_vel[i] = cmd_step >= 0 ? vel[i] : 0.f; c.cmd_ang[i] = cmd_step >= 0 ? ang[i] : 0.f; }
+  // 28 bytes from pageable host memory: staged by the driver before the call returns, stream-ordered on the device
+  const size_t off = offsetof(dial_plan_desc, cmd_step);
+  CUDA_OK(cudaMemcpyAsync((char*)p->dP + off, (const char*)&p->hP.c + off, sizeof(int32_t) + 6 * sizeof(float),
+                          cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return 0;
 }
 

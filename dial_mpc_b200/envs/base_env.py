@@ -91,13 +91,15 @@ class State:
 
 class BaseEnv:
     env_id: int = -1
+    supports_randomize_tasks = False     # walk envs: one-step random command every 500 steps
+    COMMAND_PERIOD = 500                 # unitree_go2_env.py:152
 
     def __init__(self, config: BaseEnvConfig):
         assert math.isclose(config.dt % config.timestep, 0.0, abs_tol=1e-9) or \
             math.isclose(config.dt % config.timestep, config.timestep, abs_tol=1e-9), \
             "timestep must be divisible by dt"
-        if config.randomize_tasks:
-            raise NotImplementedError("randomize_tasks=True is not supported by the fused CUDA rewards")
+        if config.randomize_tasks and not self.supports_randomize_tasks:
+            raise NotImplementedError(f"randomize_tasks=True is not supported by {type(self).__name__}")
         self._config = config
         self._n_frames = int(round(config.dt / config.timestep))
         self.sys = self.make_system(config)
@@ -169,6 +171,7 @@ class BaseEnv:
         _capi._set(d.joint_torque_range, np.clip(self.joint_torque_range, -big, big))
         if M_n2u is not None:
             _capi._set(d.M_n2u, M_n2u)
+        d.cmd_step = -1
         self._fill_reward_desc(d)
         return d
 
@@ -190,17 +193,55 @@ class BaseEnv:
         info = self._init_info(rng)
         return State(ps, self._get_obs(ps, info), 0.0, 0.0, {}, info)
 
+    # -- randomize_tasks (unitree_go2_env.py:141-155,298-315; unitree_h1_env.py:198-212,358-375) --
+    def sample_command(self, rng):
+        """``sample_command(rng)`` of the walk envs: uniform vx in [-1.5, 1.5], vy in [-0.5, 0.5],
+        yaw rate in [-1.5, 1.5] from keys 1..3 of ``jax.random.split(rng, 4)``."""
+        from dial_mpc_b200 import random as drandom
+        keys = drandom.split_n(rng, 4)
+        vx = drandom.uniform1(keys[1], -1.5, 1.5)
+        vy = drandom.uniform1(keys[2], -0.5, 0.5)
+        wz = drandom.uniform1(keys[3], -1.5, 1.5)
+        return np.array([vx, vy, 0.0], dtype=np.float32), np.array([0.0, 0.0, wz], dtype=np.float32)
+
+    def command_override(self, info: Dict[str, Any], horizon: int):
+        """(step, vel, ang) of the random command an env step within ``horizon`` steps of
+        ``info["step"]`` uses, or None.  The reference draws it inside ``step`` from
+        ``split(info["rng"])[1]`` whenever ``step % 500 == 0``; ``info["rng"]`` advances by one split
+        per env step, so the key for a future step follows from the current one."""
+        if not info.get("randomize_target", False):
+            return None
+        from dial_mpc_b200 import random as drandom
+        s0 = int(info["step"])
+        hit = -(-s0 // self.COMMAND_PERIOD) * self.COMMAND_PERIOD       # next multiple of the period >= s0
+        if hit >= s0 + max(int(horizon), 1):
+            return None
+        cache = getattr(self, "_cmd_cache", None)
+        tag = (hit, tuple(int(v) for v in np.asarray(info["rng"]).ravel()), s0)
+        if cache is not None and cache[0] == tag:
+            return cache[1]
+        rng = np.asarray(info["rng"], dtype=np.uint32)
+        for _ in range(hit - s0):
+            rng, _unused = drandom.split(rng)
+        vel, ang = self.sample_command(drandom.split(rng)[1])
+        out = (hit, vel, ang)
+        self._cmd_cache = (tag, out)
+        return out
+
     def _next_info(self, info: Dict[str, Any]) -> Dict[str, Any]:
         new = dict(info)
         new["step"] = info["step"] + 1
         c = self._config
         if "vel_tar" in info and hasattr(c, "default_vx"):
             # commanded velocities ramped from the PRE-increment step, fp32 like the reference
-            # (unitree_go2_env.py:151-163, unitree_h1_env.py:208-219; randomize_tasks is not built)
+            # (unitree_go2_env.py:151-163, unitree_h1_env.py:208-219)
             f = np.float32
             ramp = f(info["step"]) * f(self.dt) / f(c.ramp_up_time)
             vel = np.array([c.default_vx, c.default_vy, 0.0], dtype=f)
             ang = np.array([0.0, 0.0, c.default_vyaw], dtype=f)
+            ov = self.command_override(info, 1)
+            if ov is not None:
+                vel, ang = ov[1], ov[2]
             new["vel_tar"] = np.minimum(vel * ramp, vel)
             new["ang_vel_tar"] = np.minimum(ang * ramp, ang)
         return new

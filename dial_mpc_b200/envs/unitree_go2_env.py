@@ -31,6 +31,7 @@ class UnitreeGo2EnvConfig(BaseEnvConfig):
 
 
 class UnitreeGo2Env(BaseEnv):
+    supports_randomize_tasks = True
     env_id = _capi.ENV_IDS["unitree_go2_walk"]
 
     def __init__(self, config: UnitreeGo2EnvConfig):
@@ -111,6 +112,7 @@ def _quat_to_3x3(q):
 
 
 class UnitreeGo2SeqJumpEnv(UnitreeGo2Env):
+    supports_randomize_tasks = False     # would redraw the whole jump sequence at reset (unitree_go2_env.py:383-394): not built
     env_id = _capi.ENV_IDS["unitree_go2_seq_jump"]
 
     def __init__(self, config: UnitreeGo2SeqJumpEnvConfig = None):

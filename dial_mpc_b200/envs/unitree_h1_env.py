@@ -36,6 +36,7 @@ class UnitreeH1WalkEnvConfig(BaseEnvConfig):
 
 
 class UnitreeH1WalkEnv(BaseEnv):
+    supports_randomize_tasks = True
     env_id = _capi.ENV_IDS["unitree_h1_walk"]
 
     def __init__(self, config: UnitreeH1WalkEnvConfig):

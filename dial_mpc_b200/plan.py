@@ -50,6 +50,21 @@ class Plan:
         self.N, self.Ntotal = desc.Nsample, desc.Ntotal
         self.Hs, self.Hn = desc.Hsample, desc.Hnode
         self.exchange_on = False
+        self._cmd = None          # last command override uploaded (randomize_tasks)
+
+    def set_command(self, override) -> None:
+        """``override`` = (step, vel[3], ang[3]) or None: the one-step random command of
+        ``randomize_tasks`` (envs' ``command_override``); uploaded only when it changes."""
+        key = None if override is None else (int(override[0]), tuple(np.float32(override[1]).tolist()),
+                                             tuple(np.float32(override[2]).tolist()))
+        if key == self._cmd:
+            return
+        if key is None:
+            self._check(self.lib.dial_plan_set_command(self.handle, -1, None, None, _stream()))
+        else:
+            v, a = (C.c_float * 3)(*key[1]), (C.c_float * 3)(*key[2])
+            self._check(self.lib.dial_plan_set_command(self.handle, key[0], v, a, _stream()))
+        self._cmd = key
 
     def _check(self, rc: int) -> None:
         if rc != 0:
@@ -83,6 +98,9 @@ class Plan:
         s.qpos, s.qvel, s.qacc_warmstart = qpos.data_ptr(), qvel.data_ptr(), warm.data_ptr()
         s.step = int(state.info.get("step", 0))
         s.stage = int(state.info.get("contact_stage", 0))
+        if state.info.get("randomize_target", False):
+            # every launch that starts from `state` sees the random command its horizon may reach
+            self.set_command(self.env.command_override(state.info, self.Hs + 1))
         return s, (qpos, qvel, warm)
 
     @property

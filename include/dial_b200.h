@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DIAL_ABI_VERSION 6
+#define DIAL_ABI_VERSION 7
 
 /* capacities of the fixed-size device model */
 #define DIAL_MAXB 24   /* bodies incl. world            */
@@ -126,6 +126,11 @@ typedef struct dial_plan_desc {
   /* DIAL_ENV_CUSTOM: constants handed to dial_custom_reward() (ctx->user) */
   int32_t n_user;
   float user[DIAL_MAXUSER];
+  /* randomize_tasks (unitree_go2_env.py:141-155, unitree_h1_env.py:198-212): the env step whose
+   * info["step"] equals cmd_step uses (cmd_vel, cmd_ang) instead of (vel_cmd, ang_cmd); -1 = none.
+   * Set through dial_plan_set_command only (dial_plan_create ignores the value and starts at -1). */
+  int32_t cmd_step;
+  float cmd_vel[3], cmd_ang[3];
 } dial_plan_desc;
 
 /* State handed to the planner: Brax `State.pipeline_state` (qpos, qvel,
@@ -163,6 +168,13 @@ int dial_rollout(dial_plan* plan, const dial_state* s, const float* us, int B, i
 int dial_env_step(dial_plan* plan, const dial_state* s, const float* action,
                   float* qpos_out, float* qvel_out, float* warm_out, float* reward,
                   float* ctrl_out, void* stream);
+
+/* randomize_tasks support: replaces the command of ONE env step (the one whose info["step"]
+ * == cmd_step; pass -1 for none) in every later launch of this plan — the reference draws a
+ * one-step random command whenever step % 500 == 0 (unitree_go2_env.py:141-163), from a key chain
+ * that depends only on the reset key, so the host can compute it ahead of the horizon reaching it.
+ * Stream-ordered (safe between replays of the control-step graph). */
+int dial_plan_set_command(dial_plan* plan, int cmd_step, const float vel[3], const float ang[3], void* stream);
 
 /* The same step, also returning what the envs' `_get_obs` (envs/unitree_go2_env.py:263-286,
  * unitree_h1_env.py:323-346) reads of pipeline_state.x / xd: kin_out [dev][13] = x.pos(3),

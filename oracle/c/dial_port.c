@@ -755,9 +755,12 @@ static real reward(const dial_model_desc* m, const dial_plan_desc* c, Work* w, i
     return r_pos + r_upright + (real)0.3 * (-dy * dy) + (real)0.1 * r_contact - (real)0.1 * pen + 10;
   }
   const real ramp = stepf * dt / (real)c->ramp_up_time;
-  const real vtx = rmin((real)c->vel_cmd[0] * ramp, (real)c->vel_cmd[0]), vty = rmin((real)c->vel_cmd[1] * ramp, (real)c->vel_cmd[1]);
-  const real atx = rmin((real)c->ang_cmd[0] * ramp, (real)c->ang_cmd[0]), aty = rmin((real)c->ang_cmd[1] * ramp, (real)c->ang_cmd[1]);
-  const real atz = rmin((real)c->ang_cmd[2] * ramp, (real)c->ang_cmd[2]);
+  /* randomize_tasks: one-step command override (unitree_go2_env.py:141-163) */
+  const float* vel_cmd = step == c->cmd_step ? c->cmd_vel : c->vel_cmd;
+  const float* ang_cmd = step == c->cmd_step ? c->cmd_ang : c->ang_cmd;
+  const real vtx = rmin((real)vel_cmd[0] * ramp, (real)vel_cmd[0]), vty = rmin((real)vel_cmd[1] * ramp, (real)vel_cmd[1]);
+  const real atx = rmin((real)ang_cmd[0] * ramp, (real)ang_cmd[0]), aty = rmin((real)ang_cmd[1] * ramp, (real)ang_cmd[1]);
+  const real atz = rmin((real)ang_cmd[2] * ramp, (real)ang_cmd[2]);
   real r_gaits = 0;
   for (int f = 0; f < c->nfeet; ++f) {
     const real zt = foot_step((real)c->gait_duty, (real)c->gait_cadence, (real)c->gait_amplitude, (real)c->gait_phase[f], stepf * dt);

@@ -92,6 +92,10 @@ def fill_plan(env: OracleEnv) -> "C.Structure":
     cap._set(d.vel_cmd, getattr(env, "vel_cmd", np.zeros(3)))
     cap._set(d.ang_cmd, getattr(env, "ang_cmd", np.zeros(3)))
     cap._set(d.pos_tar, env.pos_tar)
+    ov = getattr(env, "cmd_override", None)
+    d.cmd_step = -1 if ov is None else int(ov[0])
+    if ov is not None:
+        cap._set(d.cmd_vel, ov[1]); cap._set(d.cmd_ang, ov[2])
     duty, cad, amp = env.GAIT_PARAMS[env.gait]
     d.gait_duty, d.gait_cadence, d.gait_amplitude = float(duty), float(cad), float(amp)
     ph = env.GAIT_PHASE[env.gait]

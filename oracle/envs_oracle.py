@@ -143,6 +143,19 @@ class OracleEnv:
         aux = dict(q=qpos, qd=qvel, xpos=d.xpos[:, 1:], ctrl=ctrl, data=d, prev=s)
         return ns, rew, aux
 
+    # -- randomize_tasks: the one-step command of unitree_go2_env.py:141-155 --------------------
+    cmd_override = None      # (step, vel[3], ang[3]) or None
+
+    def commands(self, step):
+        """(vel_cmd, ang_cmd) [B,3] used by the env step whose info["step"] is `step`."""
+        B = len(step)
+        vel, ang = np.tile(self.vel_cmd, (B, 1)), np.tile(self.ang_cmd, (B, 1))
+        if self.cmd_override is not None:
+            hit = (np.asarray(step) == self.cmd_override[0])[:, None]
+            vel = np.where(hit, np.asarray(self.cmd_override[1], dtype=np.float64), vel)
+            ang = np.where(hit, np.asarray(self.cmd_override[2], dtype=np.float64), ang)
+        return vel, ang
+
     # -- observation / done of env.step (not on the sampling path) ----------------------------
     done_height = 0.18
 
@@ -153,8 +166,9 @@ class OracleEnv:
         step = np.asarray(step, dtype=np.float64)
         ramp = np.maximum(step - 1.0, 0.0)[:, None] * self.dt / self.ramp_up_time
         live = (step >= 1)[:, None]
-        return (np.where(live, np.minimum(self.vel_cmd * ramp, self.vel_cmd), 0.0),
-                np.where(live, np.minimum(self.ang_cmd * ramp, self.ang_cmd), 0.0))
+        vel_cmd, ang_cmd = self.commands(step - 1)
+        return (np.where(live, np.minimum(vel_cmd * ramp, vel_cmd), 0.0),
+                np.where(live, np.minimum(ang_cmd * ramp, ang_cmd), 0.0))
 
     def _vb_ab(self, d):
         v = mo.brax_views(self.m, d)
@@ -220,8 +234,9 @@ class Go2WalkOracle(OracleEnv):
         v = mo.brax_views(self.m, d)
         stepf = s.step.astype(np.float64)
         ramp = stepf[:, None] * self.dt / self.ramp_up_time
-        vel_tar = np.minimum(self.vel_cmd * ramp, self.vel_cmd)
-        ang_tar = np.minimum(self.ang_cmd * ramp, self.ang_cmd)
+        vel_cmd, ang_cmd = self.commands(s.step)
+        vel_tar = np.minimum(vel_cmd * ramp, vel_cmd)
+        ang_tar = np.minimum(ang_cmd * ramp, ang_cmd)
         z_feet = d.site_xpos[:, self.feet_site, 2]
         duty, cad, amp = self.GAIT_PARAMS[self.gait]
         z_tar = get_foot_step(duty, cad, amp, self.GAIT_PHASE[self.gait], stepf * self.dt)
@@ -324,8 +339,9 @@ class H1WalkOracle(OracleEnv):
         v = mo.brax_views(self.m, d)
         stepf = s.step.astype(np.float64)
         ramp = stepf[:, None] * self.dt / self.ramp_up_time
-        vel_tar = np.minimum(self.vel_cmd * ramp, self.vel_cmd)
-        ang_tar = np.minimum(self.ang_cmd * ramp, self.ang_cmd)
+        vel_cmd, ang_cmd = self.commands(s.step)
+        vel_tar = np.minimum(vel_cmd * ramp, vel_cmd)
+        ang_tar = np.minimum(ang_cmd * ramp, ang_cmd)
         duty, cad, amp = self.GAIT_PARAMS[self.gait]
         z_tar = get_foot_step(duty, cad, amp, self.GAIT_PHASE[self.gait], stepf * self.dt)
         z_feet = np.stack([d.con_dist[:, 0:2].min(-1), d.con_dist[:, 2:4].min(-1)], -1)
@@ -367,8 +383,9 @@ class H1LocoOracle(H1WalkOracle):
         v = mo.brax_views(self.m, d)
         stepf = s.step.astype(np.float64)
         ramp = stepf[:, None] * self.dt / self.ramp_up_time
-        vel_tar = np.minimum(self.vel_cmd * ramp, self.vel_cmd)
-        ang_tar = np.minimum(self.ang_cmd * ramp, self.ang_cmd)
+        vel_cmd, ang_cmd = self.commands(s.step)
+        vel_tar = np.minimum(vel_cmd * ramp, vel_cmd)
+        ang_tar = np.minimum(ang_cmd * ramp, ang_cmd)
         duty, cad, amp = self.GAIT_PARAMS[self.gait]
         z_tar = get_foot_step(duty, cad, amp, self.GAIT_PHASE[self.gait], stepf * self.dt)
         z_feet = np.stack([d.con_dist[:, 0:4].min(-1), d.con_dist[:, 4:8].min(-1)], -1)

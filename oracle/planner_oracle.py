@@ -112,9 +112,10 @@ def threefry2x32(key, x0, x1):
 
 
 def jax_random_bits_legacy(key, n):
-    """jax.random bits, threefry_partitionable=False: counters 0..n-1 split in halves."""
+    """jax.random bits, threefry_partitionable=False: counters 0..n-1 split in halves (an odd
+    count is padded with one ZERO counter, jax._src.prng.threefry_2x32)."""
     odd = n % 2
-    cnt = np.arange(n + odd, dtype=np.uint32)
+    cnt = np.concatenate([np.arange(n, dtype=np.uint32), np.zeros(odd, dtype=np.uint32)])
     half = (n + odd) // 2
     a, b = threefry2x32(key, cnt[:half], cnt[half:])
     return np.concatenate([a, b])[:n]
@@ -123,6 +124,25 @@ def jax_random_bits_legacy(key, n):
 def jax_split_legacy(key, num=2):
     bits = jax_random_bits_legacy(key, 2 * num)
     return bits.reshape(num, 2)
+
+
+def jax_uniform_legacy(key, shape, minval, maxval):
+    """jax.random.uniform(key, shape, float32, minval, maxval): mantissa bits -> [1,2) - 1, scaled,
+    clamped from below (jax._src.random._uniform)."""
+    n = int(np.prod(shape))
+    bits = jax_random_bits_legacy(key, n)
+    f = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    lo, hi = np.float32(minval), np.float32(maxval)
+    return np.maximum(lo, f * (hi - lo) + lo).astype(np.float32).reshape(shape)
+
+
+def sample_command_oracle(rng):
+    """sample_command of the walk envs (unitree_go2_env.py:298-315, unitree_h1_env.py:358-375)."""
+    _, k1, k2, k3 = jax_split_legacy(rng, 4)
+    vx = jax_uniform_legacy(k1, (1,), -1.5, 1.5)[0]
+    vy = jax_uniform_legacy(k2, (1,), -0.5, 0.5)[0]
+    wz = jax_uniform_legacy(k3, (1,), -1.5, 1.5)[0]
+    return np.array([vx, vy, 0.0]), np.array([0.0, 0.0, wz])
 
 
 def jax_normal_legacy(key, shape):

@@ -162,3 +162,60 @@ def test_end_of_run_dumps_have_the_reference_layout(tmp_path):
     assert np.load(tmp_path / "t_states.npy").shape == states.shape
     assert np.load(tmp_path / "t_predictions.npy").shape == preds.shape
     assert (states[:, 0] == np.arange(n_steps)).all() and (preds[3] == 3.0).all()
+
+
+def test_host_random_pieces_for_sample_command():
+    """dial_mpc_b200.random: Threefry-2x32 against the Random123 known answers, split_n(key, 2)
+    against the C library's split, uniform1 in range and reproducible."""
+    from dial_mpc_b200 import random as R
+    kat = [((0, 0), (0, 0), (0x6B200159, 0x99BA4EFE)),
+           ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
+           ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0))]
+    for key, ctr, out in kat:
+        y0, y1 = R.threefry2x32(key, [ctr[0]], [ctr[1]])
+        assert (int(y0[0]), int(y1[0])) == out
+    k = R.PRNGKey(11)
+    a, b = R.split(k)
+    s2 = R.split_n(k, 2)
+    assert np.array_equal(s2[0], a) and np.array_equal(s2[1], b)
+    assert R.split_n(k, 4).shape == (4, 2) and len({tuple(r) for r in R.split_n(k, 4)}) == 4
+    u = [R.uniform1(kk, -1.5, 1.5) for kk in R.split_n(k, 64)]
+    assert all(-1.5 <= v < 1.5 for v in u) and np.std(u) > 0.5 and u[0].dtype == np.float32
+    # the oracle's restatement of jax.random.uniform agrees bit for bit
+    from oracle import planner_oracle as J
+    for kk in R.split_n(k, 8):
+        assert R.uniform1(kk, -0.5, 0.5) == J.jax_uniform_legacy(kk, (1,), -0.5, 0.5)[0]
+    assert np.array_equal(R.split_n(k, 4), J.jax_split_legacy(k, 4))
+
+
+def test_command_override_follows_the_env_key_chain():
+    """BaseEnv.command_override: the random command of the next step % 500 == 0 comes from
+    split(R_hit)[1] where R advances by one split per env step (unitree_go2_env.py:127,141-155), so
+    looking ahead from any earlier state gives the same command as arriving there."""
+    import dial_mpc_b200.envs as E
+    from dial_mpc_b200 import random as R
+    cfg = E.get_config("unitree_go2_walk")(randomize_tasks=True)
+    env = E.get_environment("unitree_go2_walk", config=cfg)
+    rng = R.PRNGKey(3)
+    info = {"randomize_target": True, "step": 493, "rng": rng}
+    assert env.command_override(info, 5) is None              # steps 493..497
+    ov = env.command_override(info, 8)                         # reaches step 500
+    assert ov is not None and ov[0] == 500
+    r = rng
+    for _ in range(7):
+        r = R.split(r)[0]
+    at = env.command_override({"randomize_target": True, "step": 500, "rng": r}, 1)
+    assert at[0] == 500 and np.array_equal(at[1], ov[1]) and np.array_equal(at[2], ov[2])
+    vel, ang = env.sample_command(R.split(r)[1])
+    assert np.array_equal(vel, ov[1]) and np.array_equal(ang, ov[2])
+    from oracle.planner_oracle import sample_command_oracle
+    vo, ao = sample_command_oracle(R.split(r)[1])
+    assert np.array_equal(vo.astype(np.float32), vel) and np.array_equal(ao.astype(np.float32), ang)
+    assert -1.5 <= vel[0] < 1.5 and -0.5 <= vel[1] < 0.5 and vel[2] == 0 and ang[0] == ang[1] == 0
+    # info bookkeeping: the step that used the command stores it ramped (ramp >= 1 here)
+    nxt = env._next_info({"randomize_target": True, "step": 500, "rng": r, "vel_tar": np.zeros(3), "ang_vel_tar": np.zeros(3)})
+    ramp = np.float32(500) * np.float32(env.dt) / np.float32(cfg.ramp_up_time)
+    assert np.allclose(nxt["vel_tar"], np.minimum(vel * ramp, vel))
+    assert env.command_override({"randomize_target": False, "step": 500, "rng": r}, 1) is None
+    with pytest.raises(NotImplementedError):
+        E.get_environment("unitree_go2_seq_jump", config=E.get_config("unitree_go2_seq_jump")(randomize_tasks=True))

@@ -120,3 +120,27 @@ def test_emulated_random_states_match_oracle(name):
         assert np.abs(out["q"] - qq).max() < 5e-5
         assert np.abs(out["qd"] - qd).max() < 2e-3 * (1 + np.abs(qd).max() / 10)
         assert np.abs(out["rewss"] - rew).max() < 1e-4 * (1 + np.abs(rew).max())
+
+
+@pytest.mark.parametrize("name", ["unitree_go2_walk", "unitree_h1_loco"])
+def test_emulated_command_override_matches_oracle(name):
+    """randomize_tasks: the env step whose info["step"] equals cmd_step uses the random command
+    (unitree_go2_env.py:141-163); the others keep the default one."""
+    env, o = make_pair(name)
+    s = o.reset()
+    s.step[:] = 497
+    rng = np.random.default_rng(4)
+    H = 6
+    us = np.clip(rng.normal(size=(2, H, env.action_size)) * 0.5, -1, 1)
+    vel, ang = np.array([-1.2, 0.4, 0.0]), np.array([0.0, 0.0, 1.1])
+    base, *_ = o.rollout(s, us)
+    o.cmd_override = (500, vel, ang)
+    rew, q, qd, x = o.rollout(s, us)
+    o.cmd_override = None
+    assert np.abs(rew[:, 3] - base[:, 3]).min() > 1e-2 and np.abs(np.delete(rew - base, 3, axis=1)).max() == 0
+    d = env.plan_desc()
+    d.cmd_step = 500
+    d.cmd_vel[:], d.cmd_ang[:] = list(vel), list(ang)
+    out = emul.rollout(env, d, s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us, step0=497)
+    assert np.abs(out["rewss"] - rew).max() < 1e-3 * (1 + np.abs(rew).max())
+    assert np.abs(out["q"] - q).max() < 1e-4

@@ -477,3 +477,72 @@ def test_fused_update_equals_unfused_at_multi_gpu_totals(built, N):
     assert torch.isfinite(Ya).all() and ra.shape[0] == N + 1
     assert (Ya - Yb).abs().max() < 2e-4
     assert (ra - rb).abs().max() < 2e-3 * (1 + float(rb.abs().max()))
+
+
+def test_randomize_tasks_one_step_command(built):
+    """randomize_tasks=True (unitree_go2_env.py:141-163): the env step at step % 500 == 0 uses a
+    random command drawn from the env's key chain; rollouts whose horizon reaches that step see it
+    too.  CUDA path (dial_plan_set_command) against the oracle with the same override, through
+    env.step, Plan.rollout and the control-step graph."""
+    import dial_mpc_b200.envs as E
+    from dial_mpc_b200 import random as drandom
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import DeviceLoop, MBDPI
+    from oracle.envs_oracle import make_env
+    from oracle.planner_oracle import sample_command_oracle
+    name = "unitree_go2_walk"
+    cfg = dict(ENV_CASES[name])
+    env = E.get_environment(name, config=E.get_config(name)(randomize_tasks=True, **cfg))
+    o = make_env(name, cfg)
+    st = env.reset(drandom.PRNGKey(9))
+    assert st.info["randomize_target"]
+    st.info["step"] = 497
+    s = o.reset()
+    s.step[:] = 497
+    # the command step 500 will use: three splits ahead on the env's key chain
+    r = st.info["rng"]
+    for _ in range(3):
+        r = drandom.split(r)[0]
+    vel, ang = sample_command_oracle(drandom.split(r)[1])
+    o.cmd_override = (500, vel, ang)
+    assert abs(vel[0] - cfg.get("default_vx", 1.0)) > 1e-3
+    # rollouts from step 497 cross step 500
+    rng = np.random.default_rng(6)
+    us = np.clip(rng.normal(size=(8, 7, env.action_size)) * 0.5, -1, 1)
+    rew, q, _, _ = o.rollout(s, us)
+    rg, qg, _, _ = env._get_plan().rollout(st, us)
+    assert np.abs(qg.cpu().numpy() - q).max() < 2e-4
+    assert (np.abs(rg.cpu().numpy() - rew) < 2e-3 * (1 + np.abs(rew))).all()
+    o.cmd_override = None
+    base = o.rollout(s, us)[0]
+    assert np.abs(rew[:, 3] - base[:, 3]).min() > 1e-2            # the override matters at step 500 only
+    o.cmd_override = (500, vel, ang)
+    # env.step across the boundary: rewards and the stored info targets
+    for t in range(5):
+        a = us[0, t]
+        s_prev = s
+        s, r_o, aux = o.step(s, a[None])
+        st = env.step(st, a)
+        assert abs(float(st.reward) - r_o[0]) < 2e-3 * (1 + abs(r_o[0])), t
+        vt, at = o.info_targets(s.step)
+        assert np.abs(np.asarray(st.info["vel_tar"]) - vt[0]).max() < 1e-6, t
+        assert np.abs(np.asarray(st.info["ang_vel_tar"]) - at[0]).max() < 1e-6, t
+    # the control-step graph: same knots as the eager loop when the command changes between replays
+    args = DialConfig(env_name=name, Nsample=128, Hsample=8, Hnode=3, Ndiffuse=2, Ndiffuse_init=2,
+                      temp_sample=0.05, horizon_diffuse_factor=0.9, traj_diffuse_factor=0.5)
+    mb = MBDPI(args, env)
+    st0 = env.reset(drandom.PRNGKey(9))
+    st0.info["step"] = 488
+    prng = drandom.PRNGKey(2)
+    Y0 = torch.zeros(args.Hnode + 1, mb.nu, device="cuda")
+    loop = DeviceLoop(mb, st0, prng, Y0)
+    stE, Y, pr = st0, Y0, prng
+    for t in range(14):              # 488 .. 501: command absent, within the horizon, at the env step, gone
+        stE = env.step(stE, Y[0])
+        Y = mb.shift(Y)
+        pr, Y, info = mb.reverse_scan(stE, pr, Y, mb.schedule(args.Ndiffuse))
+        loop.step(args.Ndiffuse)
+        torch.cuda.synchronize()
+        assert (loop.Y - Y).abs().max() < 5e-3, t
+        assert abs(float(loop.reward) - float(stE.reward)) < 2e-3 * (1 + abs(float(stE.reward))), t
+    assert mb.plan._cmd is None and loop.state().info["step"] == 502
