@@ -91,7 +91,7 @@ class Plan:
     def empty(self, *shape) -> torch.Tensor:
         return torch.empty(shape, dtype=torch.float32, device=self.device)
 
-    def _state(self, state) -> Tuple["_capi.dial_state", tuple]:
+    def _state(self, state, horizon: int = 1) -> Tuple["_capi.dial_state", tuple]:
         ps = state.pipeline_state
         qpos, qvel, warm = self.f32(ps.qpos, (self.nq,)), self.f32(ps.qvel, (self.nv,)), self.f32(ps.qacc_warmstart, (self.nv,))
         s = _capi.dial_state()
@@ -100,7 +100,7 @@ class Plan:
         s.stage = int(state.info.get("contact_stage", 0))
         if state.info.get("randomize_target", False):
             # every launch that starts from `state` sees the random command its horizon may reach
-            self.set_command(self.env.command_override(state.info, self.Hs + 1))
+            self.set_command(self.env.command_override(state.info, horizon))
         return s, (qpos, qvel, warm)
 
     @property
@@ -118,7 +118,7 @@ class Plan:
 
     def env_step(self, state, action):
         from dial_mpc_b200.envs.base_env import PipelineState
-        s, keep = self._state(state)
+        s, keep = self._state(state, 1)
         a = self.f32(action, (self.nu,))
         qo, vo, wo, r, c = self.empty(self.nq), self.empty(self.nv), self.empty(self.nv), self.empty(1), self.empty(self.nu)
         kin = self.empty(13)
@@ -129,7 +129,7 @@ class Plan:
         return ps, r[0]
 
     def rollout(self, state, us, want_traj=True):
-        s, keep = self._state(state)
+        s, keep = self._state(state, int(np.shape(us)[1]))
         us = self.f32(us)
         B, H, nu = us.shape
         assert nu == self.nu
@@ -142,7 +142,7 @@ class Plan:
         return rewss, q, qd, x
 
     def reverse_rollout(self, state, eps, key, Ybar, noise_scale, rews_local):
-        s, keep = self._state(state)
+        s, keep = self._state(state, self.Hs + 1)
         self._check(self.lib.dial_reverse_rollout(self.handle, C.byref(s), _ptr(eps), _key(key), _ptr(Ybar),
                                                   _ptr(noise_scale), _ptr(rews_local), _stream()))
 
