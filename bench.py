@@ -329,6 +329,7 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
     launches0 = mb.plan.launches
     evs = []
     sync_all()
+    xst0 = mb.plan.exchange_status() if (world > 1 and mb.xch) else None
     t_wall0 = time.perf_counter()
     for _ in range(steps):
         flush.zero_()                                   # L2 flush, outside the timed events
@@ -339,6 +340,17 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
         evs.append((e0, e1))
     sync_all()
     t_wall = time.perf_counter() - t_wall0
+    xwait = None
+    if xst0 is not None:
+        # device-measured time this rank's update kernels spent waiting for the slowest peer's flag
+        # (skew between the GPUs + NVLink latency), per reverse_once: min / mean / max over ranks
+        xst1 = mb.plan.exchange_status()
+        w_us = ((xst1["update_wait_ns"] - xst0["update_wait_ns"]) & 0xFFFFFFFF) / 1e3 / (steps * cfg.Ndiffuse)
+        t = torch.tensor([w_us], device=dev, dtype=torch.float64)
+        allw = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allw, t)
+        ws = [float(a.item()) for a in allw]
+        xwait = dict(min=min(ws), mean=sum(ws) / len(ws), max=max(ws))
     launches = mb.plan.launches - launches0
     clocks = sampler.stop(t_wall0, t_wall0 + t_wall) if (sampler is not None and rank == 0) else None
     t_dev = sum(a.elapsed_time(b_) for a, b_ in evs) / 1e3
@@ -447,7 +459,7 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
     out = dict(value=value, ms_per_step=1e3 * t_dev / steps, gpu_launches=int(launches), wall_s_timed_region=t_wall,
                e2e=dict(value=e2e_value, unit="sample-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                         ms_per_step=1e3 * t_e2e / steps),
-               roofline=roofline, phases_us_per_reverse_once=phases, clocks=clocks,
+               roofline=roofline, phases_us_per_reverse_once=phases, exchange_wait_us_per_reverse_once=xwait, clocks=clocks,
                config=dict(workload=f"{b['name']} (BASELINE configs[{ci}])", Nsample_per_gpu=b["N"], Nsample_total=Ntotal,
                            Hsample=b["Hs"], Hnode=b["Hn"], Ndiffuse=b["Ndiffuse"], n_frames=nfr,
                            step=("shift + Ndiffuse x reverse_once (rollout, exchange, update, bars of every iteration) "
@@ -495,7 +507,8 @@ def run_own(args):
         for i in todo:
             st = max(3, min(args.steps, 10 if i != 3 else 4))
             r = measure_config(i, args, rank, world, local, st, 3, fp32_peak_tf=fp32_peak)
-            keep = {k: r[k] for k in ("value", "ms_per_step", "gpu_launches", "e2e", "roofline", "phases_us_per_reverse_once", "config")}
+            keep = {k: r[k] for k in ("value", "ms_per_step", "gpu_launches", "e2e", "roofline", "phases_us_per_reverse_once",
+                                      "exchange_wait_us_per_reverse_once", "config")}
             keep.update(steps=st, warmup=3, unit="sample-steps/s")
             if i == 4 and world == 1:
                 keep["note"] = "ONE 8192-sample shard of configs[4] on one GPU (the full config needs --gpus 8)"
@@ -531,7 +544,8 @@ def run_own(args):
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=head["config"],
                 clocks=head["clocks"], e2e=head["e2e"], gpu_launches=head["gpu_launches"],
                 wall_s_timed_region=head["wall_s_timed_region"], roofline=head["roofline"],
-                phases_us_per_reverse_once=head["phases_us_per_reverse_once"], fp32_peak_tflops_measured=fp32_peak)
+                phases_us_per_reverse_once=head["phases_us_per_reverse_once"],
+                exchange_wait_us_per_reverse_once=head["exchange_wait_us_per_reverse_once"], fp32_peak_tflops_measured=fp32_peak)
     if cpu:
         line["cpu_baseline"] = cpu
     if others:

@@ -105,13 +105,21 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void xch_wait_flags(const uint32_t* flags, uint32_t want, int world, uint32_t* err) {
+// `acc` (nullable): running total of the time this rank spent waiting for its slowest peer, in ns
+// (dial_exchange_status words 4 / 5) — the part of a sharded step that is skew + NVLink latency.
+__device__ __forceinline__ void xch_wait_flags(const uint32_t* flags, uint32_t want, int world, uint32_t* err,
+                                               uint32_t* acc = nullptr) {
   if ((int)threadIdx.x < world) {
     const volatile uint32_t* f = flags + threadIdx.x;
     const unsigned long long t0 = globaltimer_ns();
     while (*f < want) {
       if (globaltimer_ns() - t0 > 4000000000ull) { *err = 1u; break; }
-      __nanosleep(200);
+      __nanosleep(100);
+    }
+    if (acc) {
+      const unsigned long long dt = globaltimer_ns() - t0;
+      const unsigned m = __reduce_max_sync(__activemask(), (unsigned)(dt > 0xffffffffull ? 0xffffffffull : dt));
+      if (threadIdx.x == 0) *acc += m;
     }
     __threadfence_system();
   }
@@ -124,7 +132,7 @@ __global__ void __launch_bounds__(1024) weights_kernel(const float* __restrict__
   const int tid = threadIdx.x;
   if (X.mbox) {
     const uint32_t seq = *X.seq, buf = seq & 1u;
-    xch_wait_flags(X.flags + buf * DIAL_MAXRANK, seq + 1u, X.world, X.err);
+    xch_wait_flags(X.flags + buf * DIAL_MAXRANK, seq + 1u, X.world, X.err, X.err + 2);
     rews = X.mbox + (size_t)buf * n;
     if (X.rews_copy)
       for (int i = tid; i < n; i += blockDim.x) X.rews_copy[i] = __ldcg(rews + i);
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(1024) bars_allreduce_kernel(const BarsXch B) {
       *reinterpret_cast<volatile uint32_t*>(B.flags[p] + buf * DIAL_MAXRANK + B.rank) = seq + 1u;
   }
   __syncthreads();
-  xch_wait_flags(B.flags[B.rank] + buf * DIAL_MAXRANK, seq + 1u, B.world, B.err);
+  xch_wait_flags(B.flags[B.rank] + buf * DIAL_MAXRANK, seq + 1u, B.world, B.err, B.err + 3);
   const float* mine = B.mbox[B.rank] + half;
   for (int i = threadIdx.x; i < B.nbar; i += blockDim.x) {
     float s_ = 0.f;
@@ -260,8 +268,9 @@ __global__ void __launch_bounds__(YBAR_THREADS) ybar_kernel(const float* __restr
 // (dial_core.py:106,125-132).  Every CTA recomputes the reward statistics (n <= 131072: up to 512
 // L2-resident loads per thread at the 65536-sample config, a few at 2048), accumulates sum_n e_n Y0s_n and sum_n e_n over its share of the samples with
 // e_n = exp((r_n - rbar) / std / temp - max); the last CTA adds the partials in fixed order,
-// divides, normalises the stored weights, and advances the planner rng.  Saves two launches and
-// their dependency latencies per reverse_once (r02: 765 -> ~735 us per iteration at N = 2048).
+// divides, normalises the stored weights, and advances the planner rng.  Two graph nodes fewer per
+// reverse_once; measured against the three-kernel sequence it is a wash (3.073 vs 3.068 ms per
+// control step at N = 2048: a launch boundary inside a graph costs about a microsecond).
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(YBAR_THREADS) update_kernel(const float* __restrict__ rews, int n, float temp,
                                                                float* __restrict__ weights, const XchWait X,
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(YBAR_THREADS) update_kernel(const float* __res
   const int tid = threadIdx.x;
   if (X.mbox) {
     const uint32_t seq = *X.seq, buf = seq & 1u;
-    xch_wait_flags(X.flags + buf * DIAL_MAXRANK, seq + 1u, X.world, X.err);
+    xch_wait_flags(X.flags + buf * DIAL_MAXRANK, seq + 1u, X.world, X.err, blockIdx.x == 0 ? X.err + 2 : nullptr);
     rews = X.mbox + (size_t)buf * n;
   }
   uint32_t key0, key1;
@@ -887,10 +896,10 @@ extern "C" int dial_exchange_connect(dial_plan* p, const unsigned char* handles)
   return 0;
 }
 
-extern "C" int dial_exchange_status(dial_plan* p, uint32_t out[4]) {
+extern "C" int dial_exchange_status(dial_plan* p, uint32_t out[6]) {
   if (!p || !out) return fail("dial_exchange_status: null argument");
-  if (!p->xch.on) { out[0] = out[1] = out[2] = out[3] = 0; return 0; }
-  CUDA_OK(cudaMemcpy(out, p->xch.base[p->xch.rank] + p->xch.o_local, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (!p->xch.on) { for (int i = 0; i < 6; ++i) out[i] = 0; return 0; }
+  CUDA_OK(cudaMemcpy(out, p->xch.base[p->xch.rank] + p->xch.o_local, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return 0;
 }
 

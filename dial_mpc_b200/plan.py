@@ -172,9 +172,10 @@ class Plan:
         self.exchange_on = True
 
     def exchange_status(self) -> dict:
-        out = (C.c_uint32 * 4)()
+        out = (C.c_uint32 * 6)()
         self._check(self.lib.dial_exchange_status(self.handle, out))
-        return dict(seq=int(out[0]), done=int(out[1]), error=int(out[2]), bars_seq=int(out[3]))
+        return dict(seq=int(out[0]), done=int(out[1]), error=int(out[2]), bars_seq=int(out[3]),
+                    update_wait_ns=int(out[4]), bars_wait_ns=int(out[5]))
 
     def reverse_trajbar(self, weights, rank, qbar, qdbar, xbar):
         self._check(self.lib.dial_reverse_trajbar(self.handle, _ptr(weights), int(rank), _ptr(qbar), _ptr(qdbar),

@@ -245,10 +245,11 @@ int dial_reverse_trajectories(dial_plan* plan, float* q, float* qd, float* xpos,
  *   3. every rank: dial_exchange_connect(plan, handles[world][64])
  * From then on dial_reverse_rollout publishes, dial_reverse_update(_x) with rews_all == NULL
  * consumes, dial_reverse_trajbar returns the all-rank sums.  dial_exchange_status reads
- * {sequence, CTAs done, error (1 = a wait timed out after ~4 s), bars sequence}. */
+ * {sequence, CTAs done, error (1 = a wait timed out after ~4 s), bars sequence, total ns the
+ * update kernels waited for their slowest peer's flag, the same for the bars kernels}. */
 int dial_exchange_create(dial_plan* plan, int rank, int world, unsigned char handle_out[DIAL_IPC_HANDLE_BYTES]);
 int dial_exchange_connect(dial_plan* plan, const unsigned char* handles);
-int dial_exchange_status(dial_plan* plan, uint32_t out[4]);
+int dial_exchange_status(dial_plan* plan, uint32_t out[6]);
 
 /* ---- Device-resident synchronous MPC loop -------------------------------------------------
  * The reference's main loop (core/dial_core.py:242-268) is, per control step,
