@@ -130,6 +130,8 @@ def _bind(path: str) -> C.CDLL:
     lib.dial_env_step.argtypes = [V, C.POINTER(dial_state), P, P, P, P, P, P, V]
     lib.dial_env_step_kin.argtypes = [V, C.POINTER(dial_state), P, P, P, P, P, P, P, V]
     lib.dial_plan_set_command.argtypes = [V, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), V]
+    F = C.POINTER(C.c_float)
+    lib.dial_plan_set_stages.argtypes = [V, C.c_int, F, F, F, F, V]
     lib.dial_pipeline_init.argtypes = [V, P, P, P, P, V]
     U2 = C.POINTER(C.c_uint32)
     lib.dial_reverse_rollout.argtypes = [V, C.POINTER(dial_state), P, U2, P, P, P, V]
@@ -155,7 +157,7 @@ def _bind(path: str) -> C.CDLL:
     lib.dial_mpc_bind.restype = C.c_int
     lib.dial_mpc_step.argtypes = [V, I, I, V]
     lib.dial_mpc_step.restype = C.c_int
-    for fn in ("dial_rollout", "dial_env_step", "dial_env_step_kin", "dial_plan_set_command", "dial_pipeline_init", "dial_reverse_rollout",
+    for fn in ("dial_rollout", "dial_env_step", "dial_env_step_kin", "dial_plan_set_command", "dial_plan_set_stages", "dial_pipeline_init", "dial_reverse_rollout",
                "dial_reverse_update", "dial_reverse_update_x", "dial_reverse_trajbar", "dial_reverse_trajectories",
                "dial_exchange_create", "dial_exchange_connect", "dial_exchange_status"):
         getattr(lib, fn).restype = C.c_int
@@ -185,7 +187,7 @@ def check(rc: int) -> None:
 
 
 EXPORTS = ["dial_abi_version", "dial_last_error", "dial_sizeof", "dial_plan_create", "dial_plan_destroy", "dial_rollout",
-           "dial_env_step", "dial_env_step_kin", "dial_plan_set_command", "dial_pipeline_init", "dial_reverse_rollout", "dial_reverse_update", "dial_reverse_update_x",
+           "dial_env_step", "dial_env_step_kin", "dial_plan_set_command", "dial_plan_set_stages", "dial_pipeline_init", "dial_reverse_rollout", "dial_reverse_update", "dial_reverse_update_x",
            "dial_exchange_create", "dial_exchange_connect", "dial_exchange_status",
            "dial_reverse_trajbar", "dial_reverse_trajectories", "dial_key_split", "dial_fp32_peak", "dial_launch_count", "dial_debug_counters",
            "dial_solver_variant", "dial_custom_reward_id", "dial_mpc_bind", "dial_mpc_step"]

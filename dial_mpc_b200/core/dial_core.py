@@ -313,6 +313,9 @@ class DeviceLoop:
         self._rand = bool(state.info.get("randomize_target", False))
         self._env_info = {"randomize_target": self._rand, "step": int(state.info.get("step", 0)),
                           "rng": np.asarray(state.info.get("rng", np.zeros(2)), dtype=np.uint32).copy()}
+        if self._rand and hasattr(mbdpi.env, "stage_tables"):
+            # seq-jump: the jump sequence drawn at reset is constant afterwards; one upload at bind time
+            pl.set_stages(mbdpi.env.stage_tables(state.info))
         pl.mpc_bind(self.buf, mbdpi.M_shift.cpu().numpy())
 
     def step(self, n_diffuse: Optional[int] = None, env_step=True) -> None:

@@ -38,6 +38,14 @@ DEV void fast_sincos(float x, float& s, float& c) { __sincosf(x, &s, &c); }
 DEV float fast_cos(float x) { return __cosf(x); }
 #endif
 
+// TEST-ONLY (emulator build with -DDIAL_EMUL_TRACE): iteration counts of the solvers
+#if defined(DIAL_HOST_EMUL) && defined(DIAL_EMUL_TRACE)
+extern "C" void emul_trace(int kind, int val);
+#define DIAL_TRACE(lane, kind, val) do { if ((lane) == 0) emul_trace(kind, val); } while (0)
+#else
+#define DIAL_TRACE(lane, kind, val) do { } while (0)
+#endif
+
 #define DIAL_MAXCHAIN 12   // longest dof ancestor chain (H1: 6 + 5 = 11)
 #define DIAL_MAXLEVEL 28
 #define DIAL_MAXE 32       // contact pyramid edge rows (4 per contact)
@@ -1645,7 +1653,8 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
   LSPoint snap_lo = lo, snap_hi = hi;
   bool snap_swap = swap;
   int snap_it = 0, power = 1, stop_at = M.m.ls_iterations;
-  for (int it = 0; it < stop_at; ++it) {
+  int it = 0;
+  for (; it < stop_at; ++it) {
     bool done = !swap;
     done |= (lo.d0 < 0.f) && (lo.d0 > -gtol);
     done |= (hi.d0 > 0.f) && (hi.d0 < gtol);
@@ -1677,6 +1686,7 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
     if (swap_hi_mid) hi = mid;
     swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
   }
+  DIAL_TRACE(w.lane, 1, it);
   // costs of the two surviving points (mjx carries them along; same expressions, evaluated once)
   {
     LSPoint fin[2];
@@ -1877,6 +1887,7 @@ DEV float dense_constraint_solve(WarpCtx& w, Solver& S, const float* Mrow, float
 #ifndef DIAL_HOST_EMUL
   if (w.dbg && lane == 0) { atomicAdd(w.dbg, 1.f); atomicAdd(w.dbg + 1, (float)it); }
 #endif
+  DIAL_TRACE(lane, 0, it);
   return S.qacc;
 }
 

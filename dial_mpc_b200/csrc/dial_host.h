@@ -5,6 +5,12 @@
 #include <string>
 #include "dial_device.cuh"
 
+// threads per CTA the rollout kernel is compiled for (__launch_bounds__): 512 -> 128 registers per
+// thread, 448 -> 144.  The launch policy never asks for more than DIAL_MAXTHREADS / 32 warps.
+#ifndef DIAL_MAXTHREADS
+#define DIAL_MAXTHREADS 512
+#endif
+
 // Star decomposition: hanging chains = maximal serial chains ending at leaf dofs whose dofs
 // all have <= 1 child; the remaining dofs must form one chain from dof 0 (the root block).
 static inline void derive_star(const dial_model_desc& m, DevModel& D) {

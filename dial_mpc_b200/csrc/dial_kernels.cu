@@ -395,10 +395,15 @@ __global__ void mpc_shift_kernel(const float* __restrict__ Msh, const float* __r
 
 // ---------------------------------------------------------------------------------
 // qbar / qdbar / xbar  (core/dial_core.py:133-135): weighted sums over stored trajectories.
-//   stage 1: grid (H, TB_CHUNKS, 3 arrays), block = 32 columns x 8 row groups -> per-chunk partials
+// A row of a trajectory array is H * ncol contiguous floats, so out[j] = sum_r w_r traj[r][j] with
+// one thread per j reads whole 128-byte lines (consecutive lanes -> consecutive addresses).
+//   stage 1: grid (ceil(max_j / 256), TB_CHUNKS row chunks, 3 arrays): per-chunk partials, rows in
+//            order, 8 independent loads in flight per thread
 //   stage 2: grid H: partials summed in fixed chunk order (bitwise deterministic)
+// The only bandwidth-shaped kernel of the path: rows * H * (nq + nv + 3 (nbody-1)) * 4 bytes read
+// once from L2 / HBM (cfg1: 16 MB, cfg4 shard: 65 MB).
 // ---------------------------------------------------------------------------------
-#define TB_CHUNKS 8
+#define TB_CHUNKS 32
 struct TrajArgs {
   const float* traj[3];
   float* out[3];
@@ -409,45 +414,53 @@ struct TrajArgs {
   float* partial;  // [TB_CHUNKS][H][coltot]
 };
 
-__global__ void __launch_bounds__(256) trajbar_partial_kernel(const TrajArgs T) {
-  __shared__ float red[8][33];
-  const int t = blockIdx.x, chunk = blockIdx.y, arr = blockIdx.z;
-  const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int ncol = T.ncol[arr];
-  const float* __restrict__ traj = T.traj[arr];
+// (32 registers: one CTA fits beside the 448-thread rollout CTA of the next iteration, which the bars overlap)
+__global__ void __launch_bounds__(256, 8) trajbar_partial_kernel(const TrajArgs T) {
+  const int chunk = blockIdx.y, arr = blockIdx.z;
+  const int ncol = arr == 0 ? T.ncol[0] : (arr == 1 ? T.ncol[1] : T.ncol[2]), len = T.H * ncol;
+  const int coloff = arr == 0 ? T.coloff[0] : (arr == 1 ? T.coloff[1] : T.coloff[2]);
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (blockIdx.x * 256 >= len) return;
+  const float* __restrict__ traj = arr == 0 ? T.traj[0] : (arr == 1 ? T.traj[1] : T.traj[2]);
   const int per = (T.nrows + TB_CHUNKS - 1) / TB_CHUNKS;
   const int r0 = chunk * per, r1 = min(T.nrows, r0 + per);
-  for (int c0 = 0; c0 < ncol; c0 += 32) {
-    const int c = c0 + cx;
-    float a = 0.f;
-    if (c < ncol) {
-      for (int r = r0 + g; r < r1; r += 8) {
-        float wgt;
-        if (r == T.mean_row) { if (!T.include_mean) continue; wgt = T.weights[T.mean_weight_index]; }
-        else wgt = T.weights[T.w_offset + r];
-        if (wgt != 0.f) a += wgt * traj[((size_t)r * T.H + t) * ncol + c];   // weight 0: diverged sample (NaN trajectory)
-      }
-    }
-    __syncthreads();
-    red[g][cx] = a;
-    __syncthreads();
-    if (g == 0 && c < ncol) {
-      float s = 0.f;
+  const int jj = j < len ? j : len - 1;
+  float a = 0.f;
+  for (int r = r0; r < r1; r += 8) {
+    float wv[8], xv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += red[i][cx];
-      T.partial[((size_t)chunk * T.H + t) * T.coltot + T.coloff[arr] + c] = s;
+    for (int k = 0; k < 8; ++k) {
+      const int rr = r + k;
+      float wgt = 0.f;
+      if (rr < r1) {
+        if (rr == T.mean_row) wgt = T.include_mean ? T.weights[T.mean_weight_index] : 0.f;
+        else wgt = T.weights[T.w_offset + rr];
+      }
+      wv[k] = wgt;
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)   // weight 0: a diverged sample (NaN trajectory) or a row beyond the chunk: not read
+      xv[k] = (wv[k] != 0.f) ? traj[(size_t)(r + k) * len + jj] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += wv[k] * xv[k];
+  }
+  if (j < len) {
+    const int t = j / ncol, c = j - t * ncol;
+    T.partial[((size_t)chunk * T.H + t) * T.coltot + coloff + c] = a;
   }
 }
 
-__global__ void __launch_bounds__(128) trajbar_final_kernel(const TrajArgs T) {
+__global__ void __launch_bounds__(128, 8) trajbar_final_kernel(const TrajArgs T) {
   const int t = blockIdx.x;
   for (int col = threadIdx.x; col < T.coltot; col += blockDim.x) {
     float s = 0.f;
-#pragma unroll
+#pragma unroll 8
     for (int ch = 0; ch < TB_CHUNKS; ++ch) s += T.partial[((size_t)ch * T.H + t) * T.coltot + col];
-    const int arr = col >= T.coloff[2] ? 2 : (col >= T.coloff[1] ? 1 : 0);
-    if (T.out[arr]) T.out[arr][(size_t)t * T.ncol[arr] + (col - T.coloff[arr])] = s;
+    float* out; int ncol, off;   // (no dynamic indexing of the kernel parameter: it would be copied to the stack)
+    if (col >= T.coloff[2]) { out = T.out[2]; ncol = T.ncol[2]; off = T.coloff[2]; }
+    else if (col >= T.coloff[1]) { out = T.out[1]; ncol = T.ncol[1]; off = T.coloff[1]; }
+    else { out = T.out[0]; ncol = T.ncol[0]; off = T.coloff[0]; }
+    if (out) out[(size_t)t * ncol + (col - off)] = s;
   }
 }
 
@@ -572,19 +585,20 @@ static cudaError_t launch_rollout_any(dial_plan* p, const RolloutArgs& A0, cudaS
     // one CTA per SM holding that SM's share of the rows (any warp count 1..16: the kernel is
     // not specialised on it)
     const int per_sm = (A.nrows + p->num_sms - 1) / p->num_sms;
-    wpc = per_sm < 16 ? per_sm : 16;
+    constexpr int MAXW = DIAL_MAXTHREADS / 32;   // the kernel's __launch_bounds__ (dial_host.h)
+    wpc = per_sm < MAXW ? per_sm : MAXW;
     // more than one wave of rows: balance the waves of one CTA per SM.  Measured at N=8192
     // (56 rows per SM): H1 4 waves of 14 warps 5.57 ms, 16 warps 5.76 ms, two resident 8-warp
     // CTAs 5.91 ms; Go2 3.85 / 3.93 / 3.81 ms.
-    if (per_sm > 16) {
-      const int waves = (per_sm + 15) / 16;
+    if (per_sm > MAXW) {
+      const int waves = (per_sm + MAXW - 1) / MAXW;
       wpc = (per_sm + waves - 1) / waves;
     }
     // respect the 227 KB shared-memory limit of one CTA
     const size_t fixed = sizeof(DevModel) + sizeof(DevPlan), slab = (size_t)p->hM.warp_floats * sizeof(float);
     while (wpc > 1 && fixed + wpc * slab > 227 * 1024) --wpc;
   }
-  if (wpc < 1 || wpc > 16) return cudaErrorInvalidValue;
+  if (wpc < 1 || wpc > DIAL_MAXTHREADS / 32) return cudaErrorInvalidValue;
   // lock-step pays off on both solver paths.  The dense (elliptic) path used to run free with
   // dynamic row assignment because MJX's 50-iteration line searches made its rows heavy-tailed;
   // since the line search stops at the detected cycle, sharing the instruction fetch wins there
@@ -733,6 +747,27 @@ extern "C" int dial_plan_set_command(dial_plan* p, int cmd_step, const float* ve
   return 0;
 }
 
+extern "C" int dial_plan_set_stages(dial_plan* p, int n_stage, const float* pose_seq, const float* yaw_seq,
+                                    const float* contact_targets, const float* contact_radius, void* stream) {
+  if (!p) return fail("dial_plan_set_stages: null plan");
+  if (n_stage < 1 || n_stage > DIAL_MAXSTAGE) return fail("dial_plan_set_stages: n_stage out of range (1..DIAL_MAXSTAGE)");
+  if (!pose_seq || !yaw_seq || !contact_targets || !contact_radius) return fail("dial_plan_set_stages: null table");
+  dial_plan_desc& c = p->hP.c;
+  c.n_stage = n_stage;
+  memset(c.pose_seq, 0, sizeof(c.pose_seq)); memset(c.yaw_seq, 0, sizeof(c.yaw_seq));
+  memset(c.contact_targets, 0, sizeof(c.contact_targets)); memset(c.contact_radius, 0, sizeof(c.contact_radius));
+  memcpy(c.pose_seq, pose_seq, sizeof(float) * 3 * n_stage);
+  memcpy(c.yaw_seq, yaw_seq, sizeof(float) * n_stage);
+  memcpy(c.contact_targets, contact_targets, sizeof(float) * 12 * n_stage);
+  memcpy(c.contact_radius, contact_radius, sizeof(float) * 4 * n_stage);
+  // one stream-ordered copy of [n_stage .. n_user) from the plan's own host mirror (pageable: staged
+  // by the driver before the call returns)
+  const size_t off = offsetof(dial_plan_desc, n_stage), end = offsetof(dial_plan_desc, n_user);
+  CUDA_OK(cudaMemcpyAsync((char*)p->dP + off, (const char*)&p->hP.c + off, end - off, cudaMemcpyHostToDevice,
+                          (cudaStream_t)stream));
+  return 0;
+}
+
 extern "C" int dial_env_step(dial_plan* p, const dial_state* s, const float* action, float* qpos_out,
                              float* qvel_out, float* warm_out, float* reward, float* ctrl_out, void* stream) {
   return dial_env_step_kin(p, s, action, qpos_out, qvel_out, warm_out, reward, ctrl_out, nullptr, stream);
@@ -829,7 +864,8 @@ extern "C" int dial_reverse_trajbar(dial_plan* p, const float* weights, int rank
   T.coltot = m.nq + m.nv + 3 * (m.nbody - 1);
   T.nrows = rows; T.H = H; T.weights = w; T.w_offset = c.shard_offset; T.mean_row = c.Nsample;
   T.mean_weight_index = c.Ntotal; T.include_mean = rank == 0 ? 1 : 0; T.partial = p->tb_partial;
-  trajbar_partial_kernel<<<dim3(H, TB_CHUNKS, 3), 256, 0, st>>>(T);
+  const int maxlen = H * (T.ncol[2] > T.ncol[0] ? T.ncol[2] : T.ncol[0]);   // nq = nv + 1 > nv always
+  trajbar_partial_kernel<<<dim3((maxlen + 255) / 256, TB_CHUNKS, 3), 256, 0, st>>>(T);
   p->launches++;
   CUDA_OK(cudaGetLastError());
   trajbar_final_kernel<<<H, 128, 0, st>>>(T);

@@ -58,9 +58,6 @@ static_assert(sizeof(DevPlan) % 16 == 0, "DevPlan must be a multiple of 16 bytes
 
 // 512 threads, one CTA per SM -> 128 registers per thread; the same binary serves every CTA
 // shape (1..16 warps), so per-sample results do not depend on the launch shape.
-#ifndef DIAL_MAXTHREADS
-#define DIAL_MAXTHREADS 512
-#endif
 template <int NL, int NR>
 __global__ void __launch_bounds__(DIAL_MAXTHREADS, 1) rollout_kernel(const DevModel* __restrict__ gM,
                                                          const DevPlan* __restrict__ gP,

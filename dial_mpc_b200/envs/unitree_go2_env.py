@@ -112,7 +112,7 @@ def _quat_to_3x3(q):
 
 
 class UnitreeGo2SeqJumpEnv(UnitreeGo2Env):
-    supports_randomize_tasks = False     # would redraw the whole jump sequence at reset (unitree_go2_env.py:383-394): not built
+    supports_randomize_tasks = True      # `reset` draws a whole jump sequence (unitree_go2_env.py:383-394, 594-631)
     env_id = _capi.ENV_IDS["unitree_go2_seq_jump"]
 
     def __init__(self, config: UnitreeGo2SeqJumpEnvConfig = None):
@@ -149,13 +149,44 @@ class UnitreeGo2SeqJumpEnv(UnitreeGo2Env):
         return (np.array(targets), np.full((n_steps, 4), foot_place_radius), com_pos.copy(),
                 com_heading.copy())
 
+    N_RANDOM_STAGES = 10    # `n_steps` of the reference's sample_command (+ the start pose = 11 stages)
+
+    def sample_command(self, rng):
+        """unitree_go2_env.py:594-631: a random walk of the COM target (xy steps uniform in
+        +-0.65 m, yaw steps uniform in +-0.5 rad; fp32 running sums like the JAX scan) from
+        ``jax.random.split(rng, 20)``, turned into stage tables by generate_jumping_sequence."""
+        from dial_mpc_b200 import random as drandom
+        n = self.N_RANDOM_STAGES
+        keys = drandom.split_n(rng, 2 * n)
+        pos = np.zeros((n + 1, 3), dtype=np.float32)
+        yaw = np.zeros(n + 1, dtype=np.float32)
+        pos[0] = [0.0, 0.0, 0.27]
+        for i in range(n):
+            pos[i + 1] = pos[i]
+            pos[i + 1, :2] += drandom.uniform(keys[i], 2, -0.65, 0.65)
+            yaw[i + 1] = yaw[i] + drandom.uniform(keys[n + i], 1, -0.5, 0.5)[0]
+        return UnitreeGo2SeqJumpEnv.generate_jumping_sequence(pos, yaw, 0.1)
+
+    def command_override(self, info, horizon):
+        return None     # this env's step draws no per-step command (unitree_go2_env.py:403-521)
+
+    def stage_tables(self, info):
+        """The jump sequence a state carries (reset may have drawn its own): what the plan's stage
+        constants must hold when a kernel is launched from that state."""
+        return (info.get("pose_target_sequence", self._pose_target_sequence),
+                info.get("yaw_target_sequence", self._yaw_target_sequence),
+                info.get("contact_targets", self._contact_targets),
+                info.get("contact_target_radius", self._contact_target_radius))
+
     def _init_info(self, rng) -> Dict[str, Any]:
         info = super()._init_info(rng)
+        tables = (self._contact_targets, self._contact_target_radius, self._pose_target_sequence,
+                  self._yaw_target_sequence)
+        if self._config.randomize_tasks:
+            tables = self.sample_command(rng)
         info.update(last_ctrl=np.zeros(12, dtype=np.float32), contact_stage=0,
-                    contact_targets=self._contact_targets,
-                    contact_target_radius=self._contact_target_radius,
-                    pose_target_sequence=self._pose_target_sequence,
-                    yaw_target_sequence=self._yaw_target_sequence)
+                    contact_targets=tables[0], contact_target_radius=tables[1],
+                    pose_target_sequence=tables[2], yaw_target_sequence=tables[3])
         return info
 
     _done_height = 0.1
@@ -191,7 +222,7 @@ class UnitreeGo2SeqJumpEnv(UnitreeGo2Env):
         for k in ("vel_tar", "ang_vel_tar"):       # no ramp in this env
             if k in info:
                 new[k] = info[k]
-        n = len(self._contact_targets)
+        n = len(info.get("contact_targets", self._contact_targets))
         new["contact_stage"] = int(min(np.floor(np.float32(new["step"]) * np.float32(self.dt)
                                                 / np.float32(self._config.jump_dt)), n - 1))
         return new

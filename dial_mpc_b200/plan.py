@@ -51,6 +51,7 @@ class Plan:
         self.Hs, self.Hn = desc.Hsample, desc.Hnode
         self.exchange_on = False
         self._cmd = None          # last command override uploaded (randomize_tasks)
+        self._stages = None       # identity of the last stage tables uploaded (seq-jump randomize_tasks)
 
     def set_command(self, override) -> None:
         """``override`` = (step, vel[3], ang[3]) or None: the one-step random command of
@@ -65,6 +66,21 @@ class Plan:
             v, a = (C.c_float * 3)(*key[1]), (C.c_float * 3)(*key[2])
             self._check(self.lib.dial_plan_set_command(self.handle, key[0], v, a, _stream()))
         self._cmd = key
+
+    def set_stages(self, tables) -> None:
+        """``tables`` = (pose [n,3], yaw [n], contact_targets [n,4,3], contact_radius [n,4]): the jump
+        sequence of the state a launch starts from (seq-jump ``randomize_tasks``: drawn at reset);
+        uploaded only when it differs from what the plan holds."""
+        pose, yaw, tgt, rad = (np.ascontiguousarray(t, dtype=np.float32) for t in tables)
+        key = (pose.tobytes(), yaw.tobytes(), tgt.tobytes(), rad.tobytes())
+        if key == self._stages:
+            return
+        n = int(pose.shape[0])
+        assert yaw.shape == (n,) and tgt.shape == (n, 4, 3) and rad.shape == (n, 4)
+        F = C.POINTER(C.c_float)
+        self._check(self.lib.dial_plan_set_stages(self.handle, n, pose.ctypes.data_as(F), yaw.ctypes.data_as(F),
+                                                  tgt.ctypes.data_as(F), rad.ctypes.data_as(F), _stream()))
+        self._stages = key
 
     def _check(self, rc: int) -> None:
         if rc != 0:
@@ -101,6 +117,8 @@ class Plan:
         if state.info.get("randomize_target", False):
             # every launch that starts from `state` sees the random command its horizon may reach
             self.set_command(self.env.command_override(state.info, horizon))
+            if hasattr(self.env, "stage_tables"):
+                self.set_stages(self.env.stage_tables(state.info))
         return s, (qpos, qvel, warm)
 
     @property

@@ -63,3 +63,17 @@ def uniform1(key, minval: float, maxval: float) -> np.float32:
     f = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32)[0] - np.float32(1.0)
     lo, hi = np.float32(minval), np.float32(maxval)
     return np.maximum(lo, f * (hi - lo) + lo)
+
+
+def uniform(key, n: int, minval: float, maxval: float) -> np.ndarray:
+    """jax.random.uniform(key, (n,), minval=, maxval=) in the legacy counter layout: counters
+    0..n-1 (an odd count padded with one zero), first half paired with second half."""
+    m = n + (n & 1)
+    c = np.arange(m, dtype=np.uint32)
+    if n & 1:
+        c[-1] = 0
+    y0, y1 = threefry2x32(key, c[:m // 2], c[m // 2:])
+    bits = np.concatenate([y0, y1])[:n]
+    f = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    lo, hi = np.float32(minval), np.float32(maxval)
+    return np.maximum(lo, f * (hi - lo) + lo)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DIAL_ABI_VERSION 7
+#define DIAL_ABI_VERSION 8
 
 /* capacities of the fixed-size device model */
 #define DIAL_MAXB 24   /* bodies incl. world            */
@@ -39,7 +39,7 @@ extern "C" {
 #define DIAL_MAXS 8    /* sites                         */
 #define DIAL_MAXNODE 8 /* Hnode+1                       */
 #define DIAL_MAXH 64   /* Hsample+1                     */
-#define DIAL_MAXSTAGE 8
+#define DIAL_MAXSTAGE 12
 #define DIAL_MAXUSER 64 /* user constants of a custom reward */
 #define DIAL_MAXRANK 8  /* GPUs of one NVLink domain sharing the samples */
 #define DIAL_IPC_HANDLE_BYTES 64
@@ -175,6 +175,14 @@ int dial_env_step(dial_plan* plan, const dial_state* s, const float* action,
  * that depends only on the reset key, so the host can compute it ahead of the horizon reaching it.
  * Stream-ordered (safe between replays of the control-step graph). */
 int dial_plan_set_command(dial_plan* plan, int cmd_step, const float vel[3], const float ang[3], void* stream);
+
+/* randomize_tasks of UnitreeGo2SeqJumpEnv (unitree_go2_env.py:383-394, 594-631): `reset` draws a
+ * whole jump sequence (11 stages) instead of using the configured one.  Replaces the stage tables
+ * of the plan (n_stage <= DIAL_MAXSTAGE; pose [n][3], yaw [n], contact_targets [n][4][3],
+ * contact_radius [n][4], host pointers) for every later launch.  Stream-ordered like
+ * dial_plan_set_command. */
+int dial_plan_set_stages(dial_plan* plan, int n_stage, const float* pose_seq, const float* yaw_seq,
+                         const float* contact_targets, const float* contact_radius, void* stream);
 
 /* The same step, also returning what the envs' `_get_obs` (envs/unitree_go2_env.py:263-286,
  * unitree_h1_env.py:323-346) reads of pipeline_state.x / xd: kin_out [dev][13] = x.pos(3),

@@ -145,6 +145,22 @@ def sample_command_oracle(rng):
     return np.array([vx, vy, 0.0]), np.array([0.0, 0.0, wz])
 
 
+def sample_jump_sequence_oracle(rng, n_steps=10):
+    """UnitreeGo2SeqJumpEnv.sample_command (unitree_go2_env.py:594-631): 2 n_steps keys from
+    jax.random.split; the COM target walks by uniform(+-0.65) in x, y and the heading by
+    uniform(+-0.5), both as fp32 running sums (lax.scan carries float32).  Returns (com_pos
+    [n_steps+1, 3], com_yaw [n_steps+1]) — the inputs of generate_jumping_sequence."""
+    keys = jax_split_legacy(rng, 2 * n_steps)
+    pos = [np.array([0.0, 0.0, 0.27], dtype=np.float32)]
+    yaw = [np.float32(0.0)]
+    for i in range(n_steps):
+        nxt = pos[-1].copy()
+        nxt[:2] = nxt[:2] + jax_uniform_legacy(keys[i], (2,), -0.65, 0.65)
+        pos.append(nxt)
+        yaw.append(np.float32(yaw[-1] + jax_uniform_legacy(keys[n_steps + i], (1,), -0.5, 0.5)[0]))
+    return np.array(pos), np.array(yaw)
+
+
 def jax_normal_legacy(key, shape):
     """jax.random.normal(key, shape, float32): sqrt(2)*erfinv(uniform(-1+ulp, 1))."""
     n = int(np.prod(shape))

@@ -21,19 +21,20 @@ for _ in range(10):
     st = env.step(st, torch.zeros(mb.nu, device=mb.device))
 Y = torch.zeros(cfg.Hnode + 1, mb.nu, device=mb.device)
 key = drandom.PRNGKey(1)
+noise = mb.sigma_control * float(os.environ.get("DIAL_PROF_NOISE", "1"))   # 0: identical rows (no divergence between warps)
 for i in range(K):
-    mb.plan.reverse_rollout(st, None, key, Y, mb.sigma_control, mb._rews_local)
+    mb.plan.reverse_rollout(st, None, key, Y, noise, mb._rews_local)
 torch.cuda.synchronize()
 if "--time" in sys.argv:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 20 if ci != 3 else 5
     e0.record()
     for i in range(reps):
-        mb.plan.reverse_rollout(st, None, key, Y, mb.sigma_control, mb._rews_local)
+        mb.plan.reverse_rollout(st, None, key, Y, noise, mb._rews_local)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(f"cfg{ci} {b['name']} N={cfg.Nsample} Hs={cfg.Hsample} WPC={os.environ.get('DIAL_WPC', 'auto')}: rollout kernel {ms:.4f} ms "
+    print(f"cfg{ci} {b['name']} N={cfg.Nsample} Hs={cfg.Hsample} WPC={os.environ.get('DIAL_WPC', 'auto')} noise x{os.environ.get('DIAL_PROF_NOISE', '1')}: rollout kernel {ms:.4f} ms "
           f"-> {cfg.Nsample * cfg.Hsample / ms * 1e3:.4e} sample-steps/s  rews {float(mb._rews_local.mean()):.5f}")
 else:
     print("done", float(mb._rews_local.mean()))

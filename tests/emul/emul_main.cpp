@@ -5,6 +5,16 @@
 #include <vector>
 #include <string>
 #include <stdio.h>
+#ifdef DIAL_EMUL_TRACE
+static std::vector<int> g_trace;
+extern "C" void emul_trace(int kind, int val) { g_trace.push_back(kind); g_trace.push_back(val); }
+extern "C" int emul_trace_take(int* out, int cap) {
+  int n = (int)g_trace.size() < cap ? (int)g_trace.size() : cap;
+  for (int i = 0; i < n; ++i) out[i] = g_trace[i];
+  g_trace.clear();
+  return n;
+}
+#endif
 #include "../../dial_mpc_b200/csrc/dial_host.h"
 
 int forced_variant = -1;

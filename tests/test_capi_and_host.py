@@ -9,6 +9,7 @@ import pytest
 import yaml
 
 from dial_mpc_b200 import _capi
+from tests.conftest import ENV_CASES
 
 
 def test_library_exports_every_declared_symbol(built):
@@ -217,5 +218,56 @@ def test_command_override_follows_the_env_key_chain():
     ramp = np.float32(500) * np.float32(env.dt) / np.float32(cfg.ramp_up_time)
     assert np.allclose(nxt["vel_tar"], np.minimum(vel * ramp, vel))
     assert env.command_override({"randomize_target": False, "step": 500, "rng": r}, 1) is None
-    with pytest.raises(NotImplementedError):
-        E.get_environment("unitree_go2_seq_jump", config=E.get_config("unitree_go2_seq_jump")(randomize_tasks=True))
+
+
+def test_seq_jump_random_sequence_matches_oracle():
+    """randomize_tasks of UnitreeGo2SeqJumpEnv (unitree_go2_env.py:383-394, 594-631): reset draws an
+    11-stage jump sequence.  Host sampler against the oracle's restatement of jax.random, the stage
+    tables against the oracle env built from the same sequence, and a rollout across a stage change
+    through the kernel logic (warp emulator) with those tables."""
+    import dial_mpc_b200.envs as E
+    from dial_mpc_b200 import _capi, random as R
+    from oracle import planner_oracle as J
+    from oracle.envs_oracle import make_env
+    from tests.emul import emul
+    k = R.PRNGKey(5)
+    for kk in R.split_n(k, 6):
+        assert np.array_equal(R.uniform(kk, 2, -0.65, 0.65), J.jax_uniform_legacy(kk, (2,), -0.65, 0.65))
+        assert R.uniform(kk, 1, -0.5, 0.5)[0] == R.uniform1(kk, -0.5, 0.5)
+        assert np.array_equal(R.uniform(kk, 5, 0.0, 1.0), J.jax_uniform_legacy(kk, (5,), 0.0, 1.0))
+    name = "unitree_go2_seq_jump"
+    cfg = dict(ENV_CASES[name])
+    env = E.get_environment(name, config=E.get_config(name)(randomize_tasks=True, **{
+        kk: (np.array(v) if isinstance(v, list) else v) for kk, v in cfg.items()}))
+    rng = R.split(k)[0]
+    info = env._init_info(rng)
+    assert info["randomize_target"] and info["contact_targets"].shape == (11, 4, 3)
+    com_pos, com_yaw = J.sample_jump_sequence_oracle(rng)
+    assert com_pos.shape == (11, 3) and np.abs(np.diff(com_pos[:, :2], axis=0)).max() < 0.65 and (com_pos[:, 2] == np.float32(0.27)).all()
+    assert np.abs(np.diff(com_yaw)).max() < 0.5 and np.abs(np.diff(com_yaw)).min() > 0
+    o = make_env(name, dict(cfg, pose_target_sequence=com_pos, yaw_target_sequence=com_yaw))
+    assert np.abs(info["pose_target_sequence"] - com_pos).max() == 0 and np.abs(info["yaw_target_sequence"] - com_yaw).max() == 0
+    assert np.abs(info["contact_targets"] - o.contact_targets).max() < 1e-6
+    assert np.abs(info["contact_target_radius"] - o.contact_radius).max() == 0
+    assert env.command_override(info, 1000) is None
+    # a different key gives a different sequence; the configured one is untouched
+    assert np.abs(env._init_info(R.split(rng)[0])["pose_target_sequence"] - com_pos).max() > 1e-2
+    assert len(env._contact_targets) == 5
+    # stage bookkeeping runs over the drawn sequence (11 stages), not the configured 5
+    nxt = env._next_info(dict(info, step=399, vel_tar=np.zeros(3), ang_vel_tar=np.zeros(3)))
+    assert nxt["contact_stage"] == 8
+    # kernel logic with the drawn tables: rollout across the stage change at step 50
+    d = env.plan_desc()
+    pose, yaw, tgt, rad = env.stage_tables(info)
+    d.n_stage = 11
+    _capi._set(d.pose_seq, pose); _capi._set(d.yaw_seq, yaw); _capi._set(d.contact_targets, tgt); _capi._set(d.contact_radius, rad)
+    s = o.reset()
+    s.step[:] = 46
+    us = np.clip(np.random.default_rng(2).normal(size=(2, 8, 12)) * 0.5, -1, 1)
+    rew, q, qd, x = o.rollout(s, us)
+    out = emul.rollout(env, d, s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us, step0=46, stage0=0)
+    assert np.abs(out["q"] - q).max() < 1e-4
+    assert np.abs(out["rewss"] - rew).max() < 1e-3 * (1 + np.abs(rew).max())
+    # ... and they matter: the configured sequence gives other rewards after the stage change
+    base = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us, step0=46, stage0=0)
+    assert np.abs(base["rewss"][:, 5:] - out["rewss"][:, 5:]).max() > 1e-3

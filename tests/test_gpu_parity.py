@@ -553,3 +553,75 @@ def test_randomize_tasks_one_step_command(built):
         loop.set_state(ps.qpos, ps.qvel, ps.qacc_warmstart)
         loop.buf["Y"].copy_(Y)
     assert mb.plan._cmd is None and loop.state().info["step"] == 502
+
+
+def test_seq_jump_randomize_tasks_draws_the_sequence_at_reset(built):
+    """randomize_tasks=True of UnitreeGo2SeqJumpEnv (unitree_go2_env.py:383-394, 594-631): reset draws
+    an 11-stage jump sequence; every launch from such a state runs with its tables
+    (dial_plan_set_stages).  CUDA rollouts / env steps against the oracle env built from the oracle's
+    own restatement of the sampler, across a stage change; a state with the configured sequence on
+    the same plan switches the tables back."""
+    import dial_mpc_b200.envs as E
+    from dial_mpc_b200 import random as drandom
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import DeviceLoop, MBDPI
+    from oracle.envs_oracle import make_env
+    from oracle.planner_oracle import sample_jump_sequence_oracle
+    name = "unitree_go2_seq_jump"
+    cfg = {k: (np.array(v) if isinstance(v, list) else v) for k, v in ENV_CASES[name].items()}
+    env = E.get_environment(name, config=E.get_config(name)(randomize_tasks=True, **cfg))
+    key = drandom.PRNGKey(21)
+    st = env.reset(key)
+    assert st.info["randomize_target"] and st.info["contact_targets"].shape == (11, 4, 3)
+    com_pos, com_yaw = sample_jump_sequence_oracle(drandom.split(key)[0])
+    o = make_env(name, dict(ENV_CASES[name], pose_target_sequence=com_pos, yaw_target_sequence=com_yaw))
+    assert np.abs(st.info["contact_targets"] - o.contact_targets).max() < 1e-6
+    s = o.reset()
+    s.step[:] = 46
+    st.info["step"] = 46
+    rng = np.random.default_rng(8)
+    us = np.clip(rng.normal(size=(8, 9, env.action_size)) * 0.5, -1, 1)
+    rew, q, _, _ = o.rollout(s, us)
+    plan = env._get_plan()
+    rg, qg, _, _ = plan.rollout(st, us)
+    assert np.abs(qg.cpu().numpy() - q).max() < 2e-4
+    assert (np.abs(rg.cpu().numpy() - rew) < 2e-3 * (1 + np.abs(rew))).all()
+    # the configured 5-stage sequence gives other rewards once the stage has changed (step 50)
+    env0 = E.get_environment(name, config=E.get_config(name)(**cfg))
+    o0 = make_env(name, dict(ENV_CASES[name]))
+    st0 = env0.reset(key)
+    st0.info["step"] = 46
+    r0, _, _, _ = o0.rollout(s, us)
+    assert np.abs(r0[:, 5:] - rew[:, 5:]).max() > 1e-3
+    # ... also on the SAME plan: a launch from a state that carries the configured tables
+    # switches them back (and forth)
+    st_cfg = type(st)(st.pipeline_state, st.obs, st.reward, st.done, st.metrics,
+                      dict(st.info, **{k2: st0.info[k2] for k2 in ("contact_targets", "contact_target_radius",
+                                                                "pose_target_sequence", "yaw_target_sequence")}))
+    rb, _, _, _ = plan.rollout(st_cfg, us)
+    assert (np.abs(rb.cpu().numpy() - r0) < 2e-3 * (1 + np.abs(r0))).all()
+    rg2, _, _, _ = plan.rollout(st, us)
+    assert torch.equal(rg2, rg)
+    # env.step across the stage change: rewards, stage counter, observation
+    for t in range(6):
+        a = us[0, t]
+        s, r_o, aux = o.step(s, a[None])
+        st = env.step(st, a)
+        assert abs(float(st.reward) - r_o[0]) < 2e-3 * (1 + abs(r_o[0])), t
+        assert st.info["contact_stage"] == int(s.stage[0]), t
+    assert st.info["contact_stage"] == 1 and st.info["contact_targets"].shape == (11, 4, 3)
+    # the control-step graph binds the drawn sequence: same knots as the eager loop
+    args = DialConfig(env_name=name, Nsample=128, Hsample=8, Hnode=3, Ndiffuse=2, Ndiffuse_init=2,
+                      temp_sample=0.05, horizon_diffuse_factor=0.9, traj_diffuse_factor=0.5)
+    mb = MBDPI(args, env)
+    mb.plan.set_stages(env.stage_tables(st0.info))      # start from the "wrong" tables on purpose
+    prng = drandom.PRNGKey(2)
+    Y0 = torch.zeros(args.Hnode + 1, mb.nu, device="cuda")
+    loop = DeviceLoop(mb, st, prng, Y0)
+    stE = env.step(st, Y0[0])
+    Y = mb.shift(Y0)
+    pr, Y, info = mb.reverse_scan(stE, prng, Y, mb.schedule(args.Ndiffuse))
+    loop.step(args.Ndiffuse)
+    torch.cuda.synchronize()
+    assert (loop.Y - Y).abs().max() < 5e-3
+    assert abs(float(loop.reward) - float(stE.reward)) < 2e-3 * (1 + abs(float(stE.reward)))
