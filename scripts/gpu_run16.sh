@@ -16,8 +16,9 @@ for CFG in 1 2; do
   t DIAL_WPC=7
   t DIAL_WPC=1
 done
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -p no:cacheprovider -k "seq_jump_randomize or randomize_tasks_one" > gpurun_out/tests16.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -p no:cacheprovider -k "seq_jump_randomize or randomize_tasks_one or update_stage or golden or device_loop" > gpurun_out/tests16.log 2>&1
 tail -25 gpurun_out/tests16.log | cut -c1-300
+python bench.py --steps 20 --warmup 5 --only --no-cpu-baseline > gpurun_out/b16.json 2> gpurun_out/b16.err; tail -c 1500 gpurun_out/b16.json
 CFG=3
 t X=base
 t DIAL_PROF_NOISE=0
