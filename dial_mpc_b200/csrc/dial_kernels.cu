@@ -209,6 +209,23 @@ __global__ void __launch_bounds__(1024) bars_allreduce_kernel(const BarsXch B) {
   if (threadIdx.x == 0) *B.seq = seq + 1u;
 }
 
+// sum_b col[b * stride], b = 0..count-1, in that order, with 16 independent L2 loads in flight (the
+// last-CTA reductions of ybar_kernel / update_kernel: a plain loop pays one L2 round trip per term)
+__device__ __forceinline__ float ordered_column_sum(const float* __restrict__ col, int stride, unsigned count, bool on) {
+  float tot = 0.f;
+  if (!on) return tot;
+  unsigned b = 0;
+  for (; b + 16 <= count; b += 16) {
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = __ldcg(col + (size_t)(b + k) * stride);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tot += v[k];
+  }
+  for (; b < count; ++b) tot += __ldcg(col + (size_t)b * stride);
+  return tot;
+}
+
 // ---------------------------------------------------------------------------------
 // Ybar = sum_n w_n * Y0s_n  (core/dial_core.py:129-132), Y0s regenerated
 // ---------------------------------------------------------------------------------
@@ -254,11 +271,7 @@ __global__ void __launch_bounds__(YBAR_THREADS) ybar_kernel(const float* __restr
   if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   __syncthreads();
   if (is_last) {
-    if (threadIdx.x < ne) {
-      float s = 0.f;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partial[b * ne + threadIdx.x]);
-      Ybar_out[threadIdx.x] = s;
-    }
+    if (threadIdx.x < ne) Ybar_out[threadIdx.x] = ordered_column_sum(partial + threadIdx.x, ne, gridDim.x, true);
     if (threadIdx.x == 0) *counter = 0u;
   }
 }
@@ -343,14 +356,15 @@ __global__ void __launch_bounds__(YBAR_THREADS) update_kernel(const float* __res
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  float Z = 0.f;
-  for (unsigned b = 0; b < gridDim.x; ++b) Z += __ldcg(&partial[b * (ne + 1) + ne]);   // same order in every thread
-  const float iz = 1.f / Z;
-  if (tid < ne) {
-    float s_ = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) s_ += __ldcg(&partial[b * (ne + 1) + tid]);
-    Ybar_out[tid] = s_ * iz;
-  }
+  // one thread per column of the partials (columns 0..ne-1: sum e Y0s, column ne: sum e), one pass,
+  // 16 L2 loads in flight, added in CTA order (bitwise deterministic)
+  __shared__ float zsh;
+  float tot = ordered_column_sum(partial + tid, ne + 1, gridDim.x, tid <= ne);
+  if (tid == ne) zsh = tot;
+  if (ne == (int)blockDim.x && tid == 0) zsh = ordered_column_sum(partial + ne, ne + 1, gridDim.x, true);
+  __syncthreads();
+  const float iz = 1.f / zsh;
+  if (tid < ne) Ybar_out[tid] = tot * iz;
   for (int i = tid; i < n; i += blockDim.x) {
     weights[i] = __ldcg(weights + i) * iz;
     if (X.mbox && X.rews_copy) X.rews_copy[i] = __ldcg(rews + i);
