@@ -326,7 +326,6 @@ __global__ void __launch_bounds__(YBAR_THREADS) update_kernel(const float* __res
     const int k = el / nu;
     const float yb = Ybar[el], ns = noise[k];
     const uint32_t ntot = (uint32_t)Ntotal * (uint32_t)ne;
-#pragma unroll 4   // independent Threefry / erfinv chains in flight; the accumulation order is unchanged
     for (int s_ = blockIdx.x * slots + slot; s_ <= Ntotal; s_ += gridDim.x * slots) {
       const float r = __ldcg(rews + s_);
       float e = isfinite(r) ? expf((r - rbar) * inv - mx) : 0.f;

@@ -4,6 +4,9 @@ set -x
 mkdir -p gpurun_out
 (time timeout 600 python -m pytest tests -m gpu -x -q --tb=short -p no:cacheprovider) > gpurun_out/final_tests.log 2>&1
 tail -6 gpurun_out/final_tests.log | cut -c1-300
+M=$(python -c "import sys; sys.path.insert(0,'scripts'); import rollout_counts as r; print(r.METRICS)")
+for i in 0 1 2 3 4; do timeout 200 ncu --metrics $M --clock-control none -k regex:rollout_kernel --launch-skip 11 -c 1 --csv --log-file gpurun_out/counts_cfg$i.csv python scripts/prof_cfg.py $i 3 > /dev/null 2>&1; done
+python scripts/rollout_counts.py gpurun_out/counts_cfg0.csv gpurun_out/counts_cfg1.csv gpurun_out/counts_cfg2.csv gpurun_out/counts_cfg3.csv gpurun_out/counts_cfg4.csv; cp profiles/rollout_counts.json gpurun_out/rollout_counts.json
 timeout 500 python bench.py --steps 20 --warmup 5 > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; tail -c 600 gpurun_out/final_bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/final_reference.json 2> gpurun_out/final_reference.err; tail -c 600 gpurun_out/final_reference.json
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"rollout|update|trajbar|shift|weights|ybar|split|bars" -c 300 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 2 --warmup 1 --only --no-cpu-baseline > gpurun_out/final_ncu_list.log 2>&1
