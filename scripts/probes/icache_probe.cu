@@ -3,7 +3,11 @@
 // The design of the rollout kernel (one CTA per SM, warps in lock-step) rests on the answer.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o icache_probe icache_probe.cu && ./icache_probe
 // Body: SEGS segments of 256 independent-chain FFMAs (4 accumulators: not latency-bound), entered through a
-// jump table so that a warp can start at any segment; KB = SEGS * 256 * 16 / 1024.
+// jump table so that a warp can start at any segment; KB = SEGS * 256 * 16 / 1024.  "scattered": warp w enters
+// the first pass at segment 7 w SEGS/16 and keeps that distance to the others afterwards; `sync` > 0: a CTA
+// barrier in front of every sync-th segment (lock-step at that period).  One JSON line per run; results and
+// reading: profiles/r02_icache_probe.{md,json,jsonl}.  (The 16 KB body — four segments, one jump-table
+// dispatch per 1024 instructions — is slower than the 32 KB one for reasons of its own and is left out there.)
 #include <cstdio>
 #include <cuda_runtime.h>
 

@@ -41,3 +41,23 @@ def test_c_port_rejects_models_outside_its_scope(built_port):
     o = make_env("allegro_reorient", ENV_CFG["allegro_reorient"])
     with pytest.raises(NotImplementedError):
         CPort(o)
+
+
+def test_bench_reference_arm_prints_the_contract_line(built_port):
+    """`bench.py --impl reference` (the driver's reference arm: the CPU restatement on the host cores, no
+    GPU involved): one JSON line with the contract's keys, on the smallest BASELINE config."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "0",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, cwd=root, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "sample-steps/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1 and line["vs_baseline"] is None
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port-c", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "configs[0]" in line["config"]["workload"]
