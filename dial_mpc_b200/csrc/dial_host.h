@@ -10,6 +10,13 @@
 #ifndef DIAL_MAXTHREADS
 #define DIAL_MAXTHREADS 512
 #endif
+// number of dofs the dense (elliptic-cone) solver is instantiated for: its matrix rows live in registers,
+// unrolled at compile time.  The stock library carries nv = 22 (Allegro hand + ball); a custom build
+// (dial_mpc_b200.custom) is compiled for the dof count of its own model.
+#ifndef DIAL_DENSE_NV
+#define DIAL_DENSE_NV 22
+#endif
+static_assert(DIAL_DENSE_NV >= 1 && DIAL_DENSE_NV <= 32, "the dense solver keeps one matrix row per lane");
 
 // Star decomposition: hanging chains = maximal serial chains ending at leaf dofs whose dofs
 // all have <= 1 child; the remaining dofs must form one chain from dof 0 (the root block).
@@ -280,7 +287,7 @@ static inline bool derive_model(const dial_model_desc& m, DevModel& D, std::stri
 }
 
 static inline int star_variant(const DevModel& D) {
-  if (D.dense) return D.m.nv == 22 ? 3 : -1;   // dense path is instantiated for nv = 22 (Allegro)
+  if (D.dense) return D.m.nv == DIAL_DENSE_NV ? 3 : -1;   // dense path: one instantiation per library build
   if (D.star_nchain >= 1 && D.star_nchain <= 4) {
     int maxchain = 0;
     for (int i = 0; i < D.m.nv; ++i) maxchain = D.dof_nchain[i] > maxchain ? D.dof_nchain[i] : maxchain;

@@ -16,6 +16,8 @@
 #include <vector>
 #include <new>
 #include "dial_host.h"
+#define DIAL_STR2(x) #x
+#define DIAL_STR(x) DIAL_STR2(x)
 
 static thread_local std::string g_err;
 static int fail(const std::string& s) { g_err = s; return -1; }
@@ -645,7 +647,7 @@ extern "C" dial_plan* dial_plan_create(const dial_model_desc* model, const dial_
       p->num_sms = sms;
   }
   p->variant = (getenv("DIAL_FORCE_GENERIC_TREE") && !p->hM.dense) ? 0 : star_variant(p->hM);
-  if (p->variant < 0) { g_err = "the dense (elliptic) solver path is instantiated for nv = 22 only"; delete p; return nullptr; }
+  if (p->variant < 0) { g_err = "this build instantiates the dense (elliptic) solver path for nv = " DIAL_STR(DIAL_DENSE_NV) " only (custom builds: dial_mpc_b200.custom compiles it for the model's nv)"; delete p; return nullptr; }
   memset(&p->hP, 0, sizeof(DevPlan));
   p->hP.c = *cfg;
   p->hP.c.cmd_step = -1;      // command overrides come through dial_plan_set_command only
@@ -1126,13 +1128,11 @@ extern "C" int dial_solver_variant(const dial_model_desc* model) {
   std::string err;
   int v = -1;
   if (!derive_model(*model, *D, err)) g_err = err;
-  else if ((v = star_variant(*D)) < 0) g_err = "the dense (elliptic) solver path is instantiated for nv = 22 only";
+  else if ((v = star_variant(*D)) < 0) g_err = "this build instantiates the dense (elliptic) solver path for nv = " DIAL_STR(DIAL_DENSE_NV) " only (custom builds: dial_mpc_b200.custom compiles it for the model's nv)";
   delete D;
   return v;
 }
 
-#define DIAL_STR2(x) #x
-#define DIAL_STR(x) DIAL_STR2(x)
 extern "C" const char* dial_custom_reward_id(void) {
 #if defined(DIAL_CUSTOM_REWARD_FILE) && defined(DIAL_CUSTOM_REWARD_ID)
   return DIAL_STR(DIAL_CUSTOM_REWARD_ID);

@@ -1,5 +1,5 @@
 // dial_rollout_variant.cu — the rollout kernel of ONE solver variant (-DDIAL_VARIANT=v):
-//   1 star<3,6> (quadruped)   2 star<5,7> (humanoid)   3 dense<22> (elliptic cones)
+//   1 star<3,6> (quadruped)   2 star<5,7> (humanoid)   3 dense<DIAL_DENSE_NV> (elliptic cones; 22 in the stock build)
 //   4 star<5,6>               0 generic tree (level-scheduled compact Cholesky)
 // Compiled once per variant so that the instantiations build in parallel (each is ~200 KB of
 // straight-line SASS); exports one launcher, dial_launch_rollout_v<v>.
@@ -22,7 +22,7 @@
 #define DIAL_V_NR 7
 #elif DIAL_VARIANT == 3
 #define DIAL_V_NL -1
-#define DIAL_V_NR 22
+#define DIAL_V_NR DIAL_DENSE_NV
 #elif DIAL_VARIANT == 4
 #define DIAL_V_NL 5
 #define DIAL_V_NR 6

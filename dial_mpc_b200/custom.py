@@ -34,26 +34,46 @@ def _sources(reward_path: str):
          reward_path]
 
 
-def reward_id(reward_path: str, variant: int) -> str:
+def _tag(variant: int, dense_nv: Optional[int]) -> str:
+    """Build key of a solver instantiation: the variant, plus the dof count for the dense solver
+    (variant 3 is compiled per nv: -DDIAL_DENSE_NV; the stock library carries nv = 22)."""
+    return f"v{variant}" + (f"n{dense_nv}" if variant == 3 and dense_nv not in (None, 22) else "")
+
+
+def reward_id(reward_path: str, variant: int, dense_nv: Optional[int] = None) -> str:
     h = hashlib.sha256()
     for s in _sources(reward_path):
         h.update(open(s, "rb").read())
-    h.update((" ".join(NVCC_FLAGS) + f" variant={variant}").encode())
+    h.update((" ".join(NVCC_FLAGS) + f" variant={_tag(variant, dense_nv)[1:]}").encode())
     return h.hexdigest()[:16]
 
 
-def library_path(reward_path: str, variant: int) -> str:
+def library_path(reward_path: str, variant: int, dense_nv: Optional[int] = None) -> str:
     stem = os.path.splitext(os.path.basename(reward_path))[0]
-    return os.path.join(CACHE_DIR, f"libdial_b200_{stem}_v{variant}_{reward_id(reward_path, variant)}.so")
+    return os.path.join(CACHE_DIR, f"libdial_b200_{stem}_{_tag(variant, dense_nv)}_{reward_id(reward_path, variant, dense_nv)}.so")
 
 
 def solver_variant(model) -> int:
-    """Solver instantiation a compiled model maps to (host logic of the stock library)."""
+    """Solver instantiation a compiled model maps to (host logic of the stock library).  Models on the
+    dense (elliptic-cone) path map to variant 3 whatever their dof count: a custom build instantiates
+    the dense solver for the model's own nv (``dense_nv``)."""
     md = _capi.fill_model_desc(model)
+    if dense_nv(model) is not None:
+        return 3
     v = _capi.lib().dial_solver_variant(md)
     if v < 0:
         raise RuntimeError(f"model not supported: {_capi.lib().dial_last_error().decode()}")
     return v
+
+
+def dense_nv(model) -> Optional[int]:
+    """nv of a model that needs the dense solver path (elliptic friction cones), else None."""
+    md = _capi.fill_model_desc(model)
+    if int(md.cone) != 1:
+        return None
+    if not 1 <= int(md.nv) <= 32:
+        raise RuntimeError("the dense solver keeps one matrix row per lane: nv <= 32")
+    return int(md.nv)
 
 
 def build_library(reward_path: str, model=None, variant: Optional[int] = None, force: bool = False,
@@ -66,7 +86,8 @@ def build_library(reward_path: str, model=None, variant: Optional[int] = None, f
         if model is None:
             raise ValueError("pass the compiled model (or the solver variant) the library is for")
         variant = solver_variant(model)
-    out = library_path(reward_path, variant)
+    nvd = dense_nv(model) if (model is not None and variant == 3) else None
+    out = library_path(reward_path, variant, nvd)
     if os.path.exists(out) and not force:
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -75,9 +96,9 @@ def build_library(reward_path: str, model=None, variant: Optional[int] = None, f
     os.makedirs(CACHE_DIR, exist_ok=True)
     tmp = out + f".tmp{os.getpid()}"
     cmd = [nvcc] + NVCC_FLAGS + [f'-DDIAL_CUSTOM_REWARD_FILE="{reward_path}"',
-                                 f"-DDIAL_CUSTOM_REWARD_ID={reward_id(reward_path, variant)}",
-                                 f"-DDIAL_ONLY_VARIANT={variant}", "-o", tmp,
-                                 os.path.join(CSRC, "dial_kernels.cu")]
+                                 f"-DDIAL_CUSTOM_REWARD_ID={reward_id(reward_path, variant, nvd)}",
+                                 f"-DDIAL_ONLY_VARIANT={variant}"] + ([f"-DDIAL_DENSE_NV={nvd}"] if nvd else []) + [
+                                 "-o", tmp, os.path.join(CSRC, "dial_kernels.cu")]
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -89,7 +110,7 @@ def build_library(reward_path: str, model=None, variant: Optional[int] = None, f
     # superseded builds of the same reward (older kernel or reward sources) are dropped
     import glob
     stem = os.path.splitext(os.path.basename(reward_path))[0]
-    for old in glob.glob(os.path.join(CACHE_DIR, f"libdial_b200_{stem}_v{variant}_*.so")):
+    for old in glob.glob(os.path.join(CACHE_DIR, f"libdial_b200_{stem}_{_tag(variant, nvd)}_*.so")):
         if old != out:
             try:
                 os.remove(old)

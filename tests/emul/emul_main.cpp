@@ -52,7 +52,7 @@ extern "C" int emul_rollout(const dial_model_desc* m, const dial_plan_desc* c, i
     emul::run_warp([&](int lane) {
       if (variant == 1) rollout_warp<3, 6>(&D, &P, slab.data(), A, row, lane);
       else if (variant == 2) rollout_warp<5, 7>(&D, &P, slab.data(), A, row, lane);
-      else if (variant == 3) rollout_warp<-1, 22>(&D, &P, slab.data(), A, row, lane);
+      else if (variant == 3) rollout_warp<-1, DIAL_DENSE_NV>(&D, &P, slab.data(), A, row, lane);
       else if (variant == 4) rollout_warp<5, 6>(&D, &P, slab.data(), A, row, lane);
       else rollout_warp<0, 0>(&D, &P, slab.data(), A, row, lane);
     });

@@ -171,3 +171,62 @@ def test_emulated_dense_path_random_states():
         assert np.abs(out["rewss"] - rew).max() < 1e-3 * (1 + np.abs(rew).max())
         active += int(np.abs(out["qd"] - qd).max() > 1e-4)   # contact-rich trials show fp32 noise
     assert active >= 1
+
+
+def test_line_search_stall_on_first_fingertip_contact():
+    """Characterisation of the restated solver (scripts/ls_stall_trace.py): when the falling ball
+    first meets a fingertip, the second Newton direction overshoots a cone-zone boundary (cost at alpha = 1
+    an order of magnitude above the cost at 0, minimum near alpha = 0.1), MJX's bracketing line search
+    returns "no improvement", the solver stops far from convergence, and the force-based eulerdamp
+    integration kicks the 10 g ball.  The kernels follow the oracle through this (bit-identical line-search
+    state); what is pinned here is that the behaviour comes from the algorithm, not from rounding."""
+    from oracle import mjx_oracle as mo
+    env, o = make_pair("allegro_reorient")
+    s = o.reset()
+    m = o.m
+    jr = np.asarray(o.joint_range)
+    hold = 2 * (-jr[:, 0] / (jr[:, 1] - jr[:, 0])) - 1      # joint targets = reset pose
+    scale = m.meaninertia * max(1, m.nv)
+    qpos, qvel, warm = s.qpos.copy(), s.qvel.copy(), s.qacc_warmstart.copy()
+    ctrl = o.act2joint(hold[None])
+    seen = None
+    for sub in range(12):
+        d = mo.forward(m, qpos, qvel, ctrl, warm)
+        g = np.linalg.norm((np.einsum("nvw,nw->nv", d.M, d.qacc) - d.qfrc_smooth - d.qfrc_constraint)[0]) / scale
+        if (d.con_dist[0] < 0).any():
+            seen = (sub, g, int(d.solver_niter[0]), qpos.copy(), qvel.copy(), warm.copy())
+            break
+        assert g < 1e-8                                   # free flight: nothing to solve
+        qpos, qvel, warm, _ = mo.step(m, qpos, qvel, ctrl, warm)
+    assert seen is not None, "the ball never reached a fingertip"
+    sub, g, niter, qpos, qvel, warm = seen
+    assert niter < m.iterations and g > 1.0               # stopped early, |grad| / scale 1e8 above the tolerance
+    # the stall itself: second Newton direction, true cost along it, and what the line search makes of it
+    d = mo.forward(m, qpos, qvel, ctrl, warm)
+    M, J, D, aref, qs, qa = d.M, d.efc_J, d.efc_D, d.efc_aref, d.qfrc_smooth, d.qacc_smooth
+    wc = mo._ctx_create(m, M, J, D, aref, qs, qa, warm, grad=False)
+    sc = mo._ctx_create(m, M, J, D, aref, qs, qa, qa, grad=False)
+    ctx = mo._ctx_create(m, M, J, D, aref, qs, qa, np.where((wc.cost < sc.cost)[:, None], warm, qa))
+    mo._linesearch(m, ctx, M, J, D, qs)
+    assert ctx.ls_alpha[0] > 0.5                           # first iteration: a normal Newton step
+    mo._update_constraint(m, ctx, J, D, qs, qa)
+    mo._update_gradient(m, ctx, M, J, D, qs)
+    ctx.search = -ctx.Mgrad
+    assert ctx.search[0] @ ctx.grad[0] < 0                 # a descent direction ...
+
+    def cost_at(alpha):
+        c = mo._Ctx()
+        c.qacc = ctx.qacc + alpha * ctx.search
+        c.Jaref = np.einsum("nrv,nv->nr", J, c.qacc) - aref
+        c.Ma = np.einsum("nvw,nw->nv", M, c.qacc)
+        c.cost, c.prev_cost = np.zeros(1), np.zeros(1)
+        mo._update_constraint(m, c, J, D, qs, qa)
+        return c.cost[0]
+    c0, c01, c1 = cost_at(0.0), cost_at(0.1), cost_at(1.0)
+    assert c01 < c0 < c1 and c1 > 5 * c0                   # ... that improves for small steps and overshoots at alpha = 1
+    mo._linesearch(m, ctx, M, J, D, qs)
+    assert ctx.ls_alpha[0] == 0.0                          # MJX's bracket rule gives up: no step, solver stops
+    # consequence: the next substep integrates the forces of the unconverged point
+    v0 = qvel[0, :3].copy()
+    _, qvel1, _, _ = mo.step(m, qpos, qvel, ctrl, warm)
+    assert np.linalg.norm(qvel1[0, :3] - v0) > 0.5         # > 0.5 m/s in one 5 ms substep on a 10 g ball

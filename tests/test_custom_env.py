@@ -143,3 +143,123 @@ def test_gpu_custom_env_matches_oracle(pair, built):
     ok = np.abs(r - info_o["rews"]) < 2e-3 * (1 + np.abs(info_o["rews"]))
     assert ok.mean() > 0.97, (ok.mean(), np.abs(r - info_o["rews"]).max())
     assert np.abs(Y.cpu().numpy() - Yo).max() < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# a custom env on the DENSE solver path (elliptic cones) with its own dof count: the stock library
+# instantiates the dense solver for nv = 22, the custom build for the model at hand (-DDIAL_DENSE_NV)
+# ---------------------------------------------------------------------------------------------
+def _pincher_reward_np(c):
+    """NumPy twin of examples/custom_env/pincher_reward.cuh."""
+    u = c["user"]
+    w = c["xd_ang"][:, 1]
+    r_spin = -((w[:, 2] - u[1]) ** 2 + w[:, 0] ** 2 + w[:, 1] ** 2)
+    p = c["xpos"][:, 1]
+    r_pos = -(p[:, 0] ** 2 + p[:, 1] ** 2 + (p[:, 2] - u[0]) ** 2)
+    r_joint = -np.sum((c["qpos"][:, 7:11] - u[3:7]) ** 2, -1)
+    dmin = np.minimum(1.0, c["contact_dist"].min(-1))
+    return 0.05 * r_spin + 50.0 * r_pos + u[2] * r_joint - 2.0 * np.maximum(dmin, 0.0)
+
+
+@pytest.fixture(scope="module")
+def pincher():
+    if EX not in sys.path:
+        sys.path.insert(0, EX)
+    pe = importlib.import_module("pincher_env")
+    import dial_mpc_b200.envs as E
+    from oracle.envs_oracle import CustomRewardOracle
+    cfg = pe.PincherEnvConfig()
+    env = E.get_environment("pincher_spin", config=cfg)
+    tmp = tempfile.NamedTemporaryFile(suffix=".json", delete=False)
+    tmp.close()
+    env.sys.model.save(tmp.name)
+    o = CustomRewardOracle(tmp.name, _pincher_reward_np, user=env.user_params(), joint_range=env.joint_range,
+                           dt=cfg.dt, timestep=cfg.timestep, leg_control="position")
+    yield env, o
+    os.unlink(tmp.name)
+
+
+def _pincher_actions(rng, B, H):
+    """Random finger targets biased towards closing, so that the tips reach the ball (contacts in all
+    cone zones: sticking on the floor, sliding under the tips) within a few env steps."""
+    return np.clip(rng.normal(size=(B, H, 4)) * 0.4 - 0.1, -1, 1)
+
+
+def test_dense_custom_env_dimensions_and_variant(pincher):
+    from dial_mpc_b200 import _capi, custom
+    env, o = pincher
+    m = env.sys
+    assert (m.nq, m.nv, m.nu, m.nbody) == (11, 10, 4, 7) and env._n_frames == 4
+    assert custom.dense_nv(env.sys.model) == 10 and custom.solver_variant(env.sys.model) == 3
+    assert "_v3n10_" in custom.library_path(env.reward_source, 3, 10)
+    assert "_v3_" in custom.library_path(env.reward_source, 3, 22)          # the stock instantiation keeps its name
+    d = env.plan_desc(Nsample=8, Hsample=10, Hnode=4)
+    assert d.env_id == _capi.ENV_IDS["custom"] and d.n_user == 7 and d.n_frames == 4 and d.leg_control_torque == 0
+    np.testing.assert_allclose(env._init_q, o.init_q)
+    assert o.m.elliptic and o.m.ncon == 8
+
+
+def test_dense_custom_env_in_emulator_matches_oracle(pincher):
+    """The device code instantiated for nv = 10 (g++ -DDIAL_DENSE_NV=10) + the custom reward against the
+    oracle: 4 substeps per env step, elliptic cones, fingertips closing on the ball."""
+    from tests.emul import emul
+    env, o = pincher
+    s = o.reset()
+    rng = np.random.default_rng(7)
+    us = _pincher_actions(rng, 3, 6)
+    rew, q, qd, x = o.rollout(s, us)
+    out = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us,
+                       defines=("DIAL_DENSE_NV=10",))
+    # ball position and finger joints tightly; the ball's quaternion loosely: MJX's line search can stall on a
+    # fresh pinch (DESIGN.md 2) and the unconverged forces then spin the 50 g ball up to 1e3 rad/s, which
+    # amplifies fp32 rounding in its orientation (the oracle and the kernel stall at the same substeps)
+    sel = [0, 1, 2, 7, 8, 9, 10]
+    assert np.abs(out["q"][..., sel] - q[..., sel]).max() < 5e-4
+    assert np.abs(out["q"][..., 3:7] - q[..., 3:7]).max() < 5e-3
+    assert np.abs(out["xpos"] - x).max() < 5e-4
+    assert np.abs(out["rewss"] - rew).max() < 2e-3 * (1 + np.abs(rew).max())
+    assert np.abs(rew).max() > 1e-3
+    # the fingers did reach the ball: it moved at some point of some rollout
+    assert np.abs(q[:, :, :3] - s.qpos[0][:3]).max() > 2e-3
+
+
+def test_dense_custom_library_builds_for_its_own_nv(pincher, built):
+    """nvcc cross-compiles the dense solver for nv = 10 into the custom build; the stock library (nv = 22)
+    refuses the model with a message that says so."""
+    import ctypes as C
+    from dial_mpc_b200 import _capi, custom
+    env, _ = pincher
+    md = _capi.fill_model_desc(env.sys.model)
+    stock = _capi.lib()
+    assert stock.dial_solver_variant(md) < 0 and b"nv = 22" in stock.dial_last_error()
+    path = env.library_path
+    assert os.path.exists(path) and "_v3n10_" in path
+    lib = _capi.lib(path)
+    assert lib.dial_solver_variant(md) == 3
+    assert lib.dial_custom_reward_id().decode() == custom.reward_id(env.reward_source, 3, 10)
+    for sym in _capi.EXPORTS:
+        assert hasattr(lib, sym)
+
+
+@pytest.mark.gpu
+def test_gpu_dense_custom_env_matches_oracle(pincher, built):
+    import torch
+    from dial_mpc_b200.core.dial_config import DialConfig
+    from dial_mpc_b200.core.dial_core import MBDPI
+    from dial_mpc_b200 import random as drandom
+    env, o = pincher
+    s = o.reset()
+    state = env.reset(drandom.PRNGKey(0))
+    np.testing.assert_allclose(state.pipeline_state.qpos.cpu().numpy(), s.qpos[0], atol=1e-6)
+    N, Hs, Hn = 64, 8, 4
+    args = DialConfig(env_name="pincher_spin", Nsample=N, Hsample=Hs, Hnode=Hn, Ndiffuse=1, temp_sample=0.05,
+                      horizon_diffuse_factor=1.0, traj_diffuse_factor=0.5)
+    mb = MBDPI(args, env)
+    us = _pincher_actions(np.random.default_rng(9), 12, Hs + 1).astype(np.float32)
+    rewss, ps = mb.rollout_us_vmap(state, us)
+    rew, q, qd, x = o.rollout(s, us.astype(np.float64))
+    okr = np.abs(rewss.cpu().numpy() - rew) < 2e-3 * (1 + np.abs(rew))
+    assert okr.mean() > 0.95, (okr.mean(), np.abs(rewss.cpu().numpy() - rew).max())
+    # the planner runs on this build (weights / Ybar finite, mean row last)
+    _, Y, info = mb.reverse_once(state, drandom.PRNGKey(3), torch.zeros(Hn + 1, 4, device="cuda"), mb.sigma_control)
+    assert torch.isfinite(Y).all() and torch.isfinite(info["rews"]).all() and info["rews"].shape == (N + 1,)
