@@ -241,12 +241,100 @@ def test_dense_custom_library_builds_for_its_own_nv(pincher, built):
         assert hasattr(lib, sym)
 
 
+def _pincher_single_step_setup(n_traj, n_step, seed):
+    """(env, oracle) with ONE physics substep per env step and mid-rollout states of the oracle: fingers
+    closing on the ball, contacts in every cone zone, including the substeps on which the solver stalls."""
+    if EX not in sys.path:
+        sys.path.insert(0, EX)
+    pe = importlib.import_module("pincher_env")
+    import dial_mpc_b200.envs as E
+    from oracle.envs_oracle import CustomRewardOracle
+    cfg = pe.PincherEnvConfig(dt=0.005, timestep=0.005)
+    env = E.get_environment("pincher_spin", config=cfg)
+    assert env._n_frames == 1
+    tmp = tempfile.NamedTemporaryFile(suffix=".json", delete=False)
+    tmp.close()
+    env.sys.model.save(tmp.name)
+    o = CustomRewardOracle(tmp.name, _pincher_reward_np, user=env.user_params(), joint_range=env.joint_range,
+                           dt=cfg.dt, timestep=cfg.timestep, leg_control="position")
+    os.unlink(tmp.name)
+    rng = np.random.default_rng(seed)
+    s = o.reset().tile(n_traj)
+    Q, V, W, A = [], [], [], []
+    a = _pincher_actions(rng, n_traj, 1)[:, 0]
+    for t in range(n_step):
+        if t % 4 == 0:
+            a = _pincher_actions(rng, n_traj, 1)[:, 0]              # a new finger target every 20 ms
+        Q.append(s.qpos.copy()); V.append(s.qvel.copy()); W.append(s.qacc_warmstart.copy()); A.append(a.copy())
+        s, _, _ = o.step(s, a)
+    Q, V, W, A = (np.concatenate(x, 0) for x in (Q, V, W, A))
+    from oracle.envs_oracle import OState
+    st = OState(Q, V, W, np.zeros(len(Q), dtype=np.int64), np.zeros(len(Q), dtype=np.int64))
+    ns, _, aux = o.step(st, A)
+    active = (aux["data"].con_dist < 0).any(-1)
+    return env, o, (Q, V, W, A), ns, active
+
+
+def _single_step_report(eq, ev, ea, active):
+    eq, ev, ea = np.array(eq), np.array(ev), np.array(ea)
+    return dict(states=len(eq), in_contact=int(active.sum()), qpos_err_max=float(eq.max()), qvel_relerr_max=float(ev.max()),
+                qacc_relerr_max=float(ea.max()), qacc_within_1e4=float((ea.max(1) <= 1e-4).mean()))
+
+
+# One mjx.step from identical (qpos, qvel, ctrl, qacc_warmstart): positions, velocities (relative to 1 + |v|) and
+# the solver output qacc (relative to 1 + |qacc|).  Calibrated on the emulator (the same fp32 device code; 48 / 96
+# states): qpos 5e-5, qvel 8e-4 on every state; qacc within 1e-4 on 82-96 % of the states and 1-8 % off on the
+# rest — the substeps on which MJX's line search stalls (DESIGN.md 2): whether the last bracket point "improved"
+# is decided by a cost difference at rounding level, fp32 and fp64 then return different iterates of an
+# unconverged solve (the integrated velocities still agree: dt * qacc is small against them).
+_PINCHER_TOL = dict(q=5e-4, v=5e-3, a_max=0.3, frac_1e4=0.6, frac_5e3=0.8)
+
+
+def _check_single_steps(rep, ea):
+    t = _PINCHER_TOL
+    ea = np.array(ea).max(1)
+    rep = dict(rep, qacc_within_5e3=float((ea <= 5e-3).mean()))
+    assert rep["qpos_err_max"] < t["q"] and rep["qvel_relerr_max"] < t["v"], rep
+    assert rep["qacc_relerr_max"] < t["a_max"] and rep["qacc_within_1e4"] >= t["frac_1e4"] and rep["qacc_within_5e3"] >= t["frac_5e3"], rep
+
+
+def test_dense_custom_env_single_steps_in_emulator():
+    from tests.emul import emul
+    env, o, (Q, V, W, A), ns, active = _pincher_single_step_setup(4, 12, 5)
+    assert active.sum() >= 10                                          # contacts are exercised
+    eq, ev, ea = [], [], []
+    for i in range(len(Q)):
+        out = emul.rollout(env, env.plan_desc(), Q[i], V[i], W[i], us=A[i][None, None, :], defines=("DIAL_DENSE_NV=10",))
+        eq.append(np.abs(out["qpos_out"] - ns.qpos[i]))
+        ev.append(np.abs(out["qvel_out"] - ns.qvel[i]) / (1 + np.abs(ns.qvel[i])))
+        ea.append(np.abs(out["warm_out"] - ns.qacc_warmstart[i]) / (1 + np.abs(ns.qacc_warmstart[i])))
+    _check_single_steps(_single_step_report(eq, ev, ea, active), ea)
+
+
 @pytest.mark.gpu
 def test_gpu_dense_custom_env_matches_oracle(pincher, built):
+    """The custom build (dense solver instantiated for nv = 10 + the pincher reward) on the GPU: single physics
+    steps from >= 100 oracle states (rollouts themselves are chaotic on this scene: MJX's line search stalls on
+    fresh pinches and the unconverged forces kick the ball, DESIGN.md 2 — the kernels stall on the same substeps,
+    which is what stepping from identical states shows), the first env step of a batch of rollouts, and the
+    planner end to end."""
     import torch
     from dial_mpc_b200.core.dial_config import DialConfig
     from dial_mpc_b200.core.dial_core import MBDPI
     from dial_mpc_b200 import random as drandom
+    from dial_mpc_b200.envs.base_env import PipelineState, State
+    env1, o1, (Q, V, W, A), ns, active = _pincher_single_step_setup(8, 16, 11)
+    assert len(Q) >= 100 and active.sum() >= 30
+    plan = env1._get_plan()
+    eq, ev, ea = [], [], []
+    for i in range(len(Q)):
+        st = State(PipelineState(plan.f32(Q[i]), plan.f32(V[i]), plan.f32(W[i])), None, 0.0, 0.0, {}, {"step": 0})
+        ps, _ = plan.env_step(st, A[i])
+        eq.append(np.abs(ps.qpos.cpu().numpy() - ns.qpos[i]))
+        ev.append(np.abs(ps.qvel.cpu().numpy() - ns.qvel[i]) / (1 + np.abs(ns.qvel[i])))
+        ea.append(np.abs(ps.qacc_warmstart.cpu().numpy() - ns.qacc_warmstart[i]) / (1 + np.abs(ns.qacc_warmstart[i])))
+    _check_single_steps(_single_step_report(eq, ev, ea, active), ea)
+    # rollouts through the 4-substep env: the first env step of every row (before anything can amplify)
     env, o = pincher
     s = o.reset()
     state = env.reset(drandom.PRNGKey(0))
@@ -258,8 +346,9 @@ def test_gpu_dense_custom_env_matches_oracle(pincher, built):
     us = _pincher_actions(np.random.default_rng(9), 12, Hs + 1).astype(np.float32)
     rewss, ps = mb.rollout_us_vmap(state, us)
     rew, q, qd, x = o.rollout(s, us.astype(np.float64))
-    okr = np.abs(rewss.cpu().numpy() - rew) < 2e-3 * (1 + np.abs(rew))
-    assert okr.mean() > 0.95, (okr.mean(), np.abs(rewss.cpu().numpy() - rew).max())
+    rg = rewss.cpu().numpy()
+    assert np.isfinite(rg).all()
+    assert (np.abs(rg[:, 0] - rew[:, 0]) < 2e-3 * (1 + np.abs(rew[:, 0]))).all()
     # the planner runs on this build (weights / Ybar finite, mean row last)
     _, Y, info = mb.reverse_once(state, drandom.PRNGKey(3), torch.zeros(Hn + 1, 4, device="cuda"), mb.sigma_control)
     assert torch.isfinite(Y).all() and torch.isfinite(info["rews"]).all() and info["rews"].shape == (N + 1,)
