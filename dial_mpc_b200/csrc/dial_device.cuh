@@ -1117,6 +1117,21 @@ DEV void star_update_constraint(WarpCtx& w, Solver& S) {
 
 struct LSPoint { float alpha, cost, d0, d1; };
 
+// Bracket update of the line search.  Default: MJX's rule (solver._linesearch) — lo / hi move to their Newton
+// successor whenever they are on the wrong side (lo.d0 > 0) OR the successor's derivative is larger, whichever
+// its sign.  On a step that crosses a cone-zone boundary this can throw away a valid bracket, the search then
+// returns "no improvement" and the solver stops unconverged.  -DDIAL_ROBUST_LS (opt-in, custom /
+// experimental builds: scripts/build_exp.py, dial_mpc_b200.custom) keeps the bracket: a successor is accepted
+// only while it stays on the same side of the minimum.  A documented deviation from the reference, like the
+// NaN guards; the stock library is built without it.
+#ifdef DIAL_ROBUST_LS
+#define DIAL_LS_SWAP_LO(lo, nx) (((lo).d0 < (nx).d0) && ((nx).d0 < 0.f))
+#define DIAL_LS_SWAP_HI(hi, nx) (((hi).d0 > (nx).d0) && ((nx).d0 > 0.f))
+#else
+#define DIAL_LS_SWAP_LO(lo, nx) (((lo).d0 > 0.f) || ((lo).d0 < (nx).d0))
+#define DIAL_LS_SWAP_HI(hi, nx) (((hi).d0 < 0.f) || ((hi).d0 > (nx).d0))
+#endif
+
 // All-reduce of 6 values per lane: reduce-scatter over the lane bits 16 / 8 (each lane keeps half
 // of its values and sends the other half), plain butterflies for the rest, then an all-gather —
 // 17 shuffles + 11 adds instead of 30 + 30.  Every lane ends with the same six sums.
@@ -1212,11 +1227,11 @@ DEV void linesearch_core(WarpCtx& w, Solver& S, float mv, float e_jv) {
     float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
     ls_points<3, false>(w.lane, S, K, l_jv, e_jv, qg, a3, pt);
     const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
-    bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
+    bool swap_lo_next = DIAL_LS_SWAP_LO(lo, lo_next);
     if (swap_lo_next) lo = lo_next;
     bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
     if (swap_lo_mid) lo = mid;
-    bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
+    bool swap_hi_next = DIAL_LS_SWAP_HI(hi, hi_next);
     if (swap_hi_next) hi = hi_next;
     bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
     if (swap_hi_mid) hi = mid;
@@ -1676,11 +1691,11 @@ DEV void dense_linesearch(WarpCtx& w, Solver& S, ConeLane& C) {
     float a3[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
     dense_ls_points<3, false>(w.lane, S, C, K, l_jv, cv, qg, a3, pt);
     const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
-    bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
+    bool swap_lo_next = DIAL_LS_SWAP_LO(lo, lo_next);
     if (swap_lo_next) lo = lo_next;
     bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
     if (swap_lo_mid) lo = mid;
-    bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
+    bool swap_hi_next = DIAL_LS_SWAP_HI(hi, hi_next);
     if (swap_hi_next) hi = hi_next;
     bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
     if (swap_hi_mid) hi = mid;

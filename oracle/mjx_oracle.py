@@ -648,6 +648,11 @@ def _ctx_create(m, M, J, D, aref, qfrc_smooth, qacc_smooth, qacc, grad=True):
     return ctx
 
 
+# False: MJX's bracket rule (the reference).  True: the checker of the -DDIAL_ROBUST_LS builds of the kernels
+# (a bracket that only narrows); set by the tests that compare those builds.
+LS_NARROWING = False
+
+
 def _linesearch(m: OModel, ctx, M, J, D, qfrc_smooth):
     B = ctx.qacc.shape[0]
     scale = m.meaninertia * max(1, m.nv)
@@ -723,11 +728,17 @@ def _linesearch(m: OModel, ctx, M, J, D, qfrc_smooth):
         lo_next = point(lo[:, 0] - lo[:, 2] / lo[:, 3])
         hi_next = point(hi[:, 0] - hi[:, 2] / hi[:, 3])
         mid = point(0.5 * (lo[:, 0] + hi[:, 0]))
-        swap_lo_next = (lo[:, 2] > 0) | (lo[:, 2] < lo_next[:, 2])
+        if LS_NARROWING:
+            swap_lo_next = (lo[:, 2] < lo_next[:, 2]) & (lo_next[:, 2] < 0)
+        else:
+            swap_lo_next = (lo[:, 2] > 0) | (lo[:, 2] < lo_next[:, 2])
         nlo = sel(swap_lo_next, lo_next, lo)
         swap_lo_mid = (mid[:, 2] < 0) & (nlo[:, 2] < mid[:, 2])
         nlo = sel(swap_lo_mid, mid, nlo)
-        swap_hi_next = (hi[:, 2] < 0) | (hi[:, 2] > hi_next[:, 2])
+        if LS_NARROWING:
+            swap_hi_next = (hi[:, 2] > hi_next[:, 2]) & (hi_next[:, 2] > 0)
+        else:
+            swap_hi_next = (hi[:, 2] < 0) | (hi[:, 2] > hi_next[:, 2])
         nhi = sel(swap_hi_next, hi_next, hi)
         swap_hi_mid = (mid[:, 2] > 0) & (nhi[:, 2] > mid[:, 2])
         nhi = sel(swap_hi_mid, mid, nhi)

@@ -29,13 +29,11 @@ def variant(narrowing: bool, iterate_forces: bool):
     successors only when the successor is still on the same side of the minimum (derivative of the same sign,
     closer to zero), and / or (iterate_forces) an Euler step whose implicit-damping solve sees M qacc."""
     src = open(mo.__file__).read()
-    a = "swap_lo_next = (lo[:, 2] > 0) | (lo[:, 2] < lo_next[:, 2])"
-    b = "swap_hi_next = (hi[:, 2] < 0) | (hi[:, 2] > hi_next[:, 2])"
+    a = "LS_NARROWING = False"
     c = "(d.qfrc_smooth + d.qfrc_constraint)[..., None]"
-    assert a in src and b in src and c in src
+    assert a in src and c in src
     if narrowing:
-        src = src.replace(a, "swap_lo_next = (lo[:, 2] < lo_next[:, 2]) & (lo_next[:, 2] < 0)")
-        src = src.replace(b, "swap_hi_next = (hi[:, 2] > hi_next[:, 2]) & (hi_next[:, 2] > 0)")
+        src = src.replace(a, "LS_NARROWING = True")
     if iterate_forces:
         src = src.replace(c, 'np.einsum("nvw,nw->nv", d.M, d.qacc)[..., None]')
     mod = types.ModuleType("mjx_oracle_variant")

@@ -230,3 +230,31 @@ def test_line_search_stall_on_first_fingertip_contact():
     v0 = qvel[0, :3].copy()
     _, qvel1, _, _ = mo.step(m, qpos, qvel, ctrl, warm)
     assert np.linalg.norm(qvel1[0, :3] - v0) > 0.5         # > 0.5 m/s in one 5 ms substep on a 10 g ball
+
+
+def test_robust_line_search_build_keeps_the_ball_and_matches_its_oracle():
+    """-DDIAL_ROBUST_LS (opt-in builds; a documented deviation from MJX's bracket rule): the device
+    code with the narrowing bracket against the oracle with the same rule (LS_NARROWING), through the first
+    fingertip contact of the hold action — where the reference rule stalls and kicks the ball (test above), this
+    one converges and the ball settles on the fingertips."""
+    from oracle import mjx_oracle as mo
+    from tests.emul import emul
+    env, o = make_pair("allegro_reorient")
+    s = o.reset()
+    jr = np.asarray(o.joint_range)
+    hold = 2 * (-jr[:, 0] / (jr[:, 1] - jr[:, 0])) - 1
+    us = np.repeat(hold[None, None], 5, axis=1)                       # 5 env steps = 20 substeps: contact at step 2
+    mo.LS_NARROWING = True
+    try:
+        rew, q, qd, x = o.rollout(s, us)
+    finally:
+        mo.LS_NARROWING = False
+    assert np.linalg.norm(qd[0, :, :3], axis=-1).max() < 0.6          # no kick (the reference rule: 1.6 m/s)
+    assert q[0, -1, 2] > 0.12                                         # the ball rests on the fingertips
+    out = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us, defines=("DIAL_ROBUST_LS",))
+    assert np.abs(out["q"] - q).max() < 5e-4
+    assert np.abs(out["rewss"] - rew).max() < 2e-3 * (1 + np.abs(rew).max())
+    # and the stock rule does kick it, in the oracle and in the device code alike
+    rew0, q0, qd0, _ = o.rollout(s, us)
+    out0 = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us)
+    assert np.linalg.norm(qd0[0, :, :3], axis=-1).max() > 1.0 and np.linalg.norm(out0["qd"][0, :, :3], axis=-1).max() > 1.0
