@@ -279,6 +279,28 @@ def _load_json(*path):
         return {}
 
 
+def issue_roofline(warp_inst_per_step, rows, steps_per_row, t_kernel, sm_mhz, n_sm, probe):
+    """Achieved warp instructions per clock and SM (= ncu sm__inst_executed.avg.per_cycle_elapsed) against what
+    an SM delivers from code that does not fit its instruction cache: every resident warp receives one
+    instruction per `cpi` cycles (profiles/r02_icache_probe.md), so the ceiling is resident warps / cpi —
+    14 warps per SM at N = 2048, 1 at N = 128 (the launch policy puts ceil(rows / SMs) <= 16 warps on an SM)."""
+    if not (warp_inst_per_step and sm_mhz and t_kernel > 0):
+        return None
+    ipc = warp_inst_per_step * rows * steps_per_row / (t_kernel * float(sm_mhz) * 1e6 * n_sm)
+    per_sm = -(-rows // n_sm)
+    waves = -(-per_sm // 16)
+    wpc = -(-per_sm // waves)                                  # warps per CTA of the launch policy
+    resident = min(rows, n_sm * wpc) / n_sm                    # average over all SMs, like `ipc`
+    cpi = (probe.get("cycles_per_instr_per_warp_128KB") or {}).get("14")
+    # (below 8 warps per SM the probe's two builds disagree, 2.9 vs 5.7 cycles for a lone warp: no ceiling is claimed)
+    ceiling = resident / cpi if (cpi and resident >= 8) else None
+    return dict(warp_inst_per_physics_step=warp_inst_per_step, ipc_per_sm=ipc, resident_warps_per_sm=resident,
+                cycles_per_instr_per_warp_streaming=cpi, ipc_ceiling_streaming_code=ceiling,
+                frac=(ipc / ceiling) if ceiling else None, sm_clock_mhz=float(sm_mhz), sms=n_sm,
+                source="instruction count: ncu smsp__inst_executed.sum (profiles/rollout_counts.json); ceiling: "
+                       "scripts/probes/icache_probe.cu on this pool's B200 (profiles/r02_icache_probe.json)")
+
+
 def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, full=True, fp32_peak_tf=None):
     """Time config ci on this process group.  Returns the JSON fields of the config (rank 0: all
     of them; other ranks: partial).  full=False skips the clocks / cpu arms (secondary blocks)."""
@@ -463,17 +485,15 @@ def measure_config(ci, args, rank, world, local, steps, warmup, sampler=None, fu
     # instruction caches (~136 KB per env step vs 32 KB), and a B200 SM issues at most `ipc_ceiling` warp
     # instructions per clock from such code — measured with independent FFMA chains (no data stalls at
     # all) by scripts/probes/icache_probe.cu, numbers committed under profiles/r02_icache_probe.json.
-    wip = prof.get("warp_inst_per_physics_step")
-    fe = _load_json("profiles", "r02_icache_probe.json")
-    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz")
-    if wip and sm_mhz:
-        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        ipc = wip * rows * H * nfr / (t_kernel * float(sm_mhz) * 1e6 * n_sm)      # = ncu sm__inst_executed.avg.per_cycle_elapsed
-        ceil_ = fe.get("ipc_ceiling_14_warps_streaming")
-        roofline["issue"] = dict(warp_inst_per_physics_step=wip, ipc_per_sm=ipc, ipc_ceiling_streaming_code=ceil_,
-                                 frac=(ipc / ceil_) if ceil_ else None, sm_clock_mhz=float(sm_mhz), sms=n_sm,
-                                 source="instruction count: ncu smsp__inst_executed.sum (profiles/rollout_counts.json); ceiling: "
-                                        "scripts/probes/icache_probe.cu on this pool's B200 (profiles/r02_icache_probe.json)")
+    try:
+        issue = issue_roofline(prof.get("warp_inst_per_physics_step"), rows, H * nfr, t_kernel,
+                               (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz"),
+                               torch.cuda.get_device_properties(dev).multi_processor_count,
+                               _load_json("profiles", "r02_icache_probe.json"))
+    except Exception as e:      # an explanatory block must never cost the bench line
+        issue = dict(error=repr(e))
+    if issue:
+        roofline["issue"] = issue
     out = dict(value=value, ms_per_step=1e3 * t_dev / steps, gpu_launches=int(launches), wall_s_timed_region=t_wall,
                e2e=dict(value=e2e_value, unit="sample-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                         ms_per_step=1e3 * t_e2e / steps),

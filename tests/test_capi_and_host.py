@@ -271,3 +271,22 @@ def test_seq_jump_random_sequence_matches_oracle():
     # ... and they matter: the configured sequence gives other rewards after the stage change
     base = emul.rollout(env, env.plan_desc(), s.qpos[0], s.qvel[0], s.qacc_warmstart[0], us=us, step0=46, stage0=0)
     assert np.abs(base["rewss"][:, 5:] - out["rewss"][:, 5:]).max() > 1e-3
+
+
+def test_bench_issue_roofline_block():
+    """bench.py's `roofline.issue`: achieved IPC per SM from ncu's instruction count and the kernel time, ceiling =
+    resident warps / measured cycles per instruction of a warp streaming non-resident code."""
+    import json
+    import os
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = json.load(open(os.path.join(root, "profiles", "r02_icache_probe.json")))
+    r = bench.issue_roofline(8494, 2049, 26, 0.691e-3, 1965.0, 148, probe)
+    assert abs(r["ipc_per_sm"] - 2.25) < 0.01 and abs(r["resident_warps_per_sm"] - 2049 / 148) < 1e-9
+    assert 0.9 < r["frac"] < 1.0 and abs(r["ipc_ceiling_streaming_code"] - 13.84 / 5.841) < 0.01
+    r4 = bench.issue_roofline(8644, 8193, 26, 2.730e-3, 1965.0, 148, probe)           # 4 waves of 14 warps
+    assert r4["resident_warps_per_sm"] == 14 and 0.9 < r4["frac"] < 1.0
+    r0 = bench.issue_roofline(8775, 129, 17, 0.345e-3, 1965.0, 148, probe)            # one warp per SM: no ceiling claimed
+    assert r0["ipc_ceiling_streaming_code"] is None and r0["frac"] is None and r0["ipc_per_sm"] > 0
+    assert bench.issue_roofline(None, 1, 1, 1.0, 1965.0, 148, probe) is None
+    assert bench.issue_roofline(8494, 2049, 26, 0.691e-3, 1965.0, 148, {})["frac"] is None
