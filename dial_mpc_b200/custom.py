@@ -34,23 +34,27 @@ def _sources(reward_path: str):
          reward_path]
 
 
-def _tag(variant: int, dense_nv: Optional[int]) -> str:
+def _tag(variant: int, dense_nv: Optional[int], defines=()) -> str:
     """Build key of a solver instantiation: the variant, plus the dof count for the dense solver
-    (variant 3 is compiled per nv: -DDIAL_DENSE_NV; the stock library carries nv = 22)."""
-    return f"v{variant}" + (f"n{dense_nv}" if variant == 3 and dense_nv not in (None, 22) else "")
+    (variant 3 is compiled per nv: -DDIAL_DENSE_NV; the stock library carries nv = 22), plus a mark
+    for extra compile-time options (``defines``, e.g. DIAL_ROBUST_LS)."""
+    return (f"v{variant}" + (f"n{dense_nv}" if variant == 3 and dense_nv not in (None, 22) else "")
+            + ("x" if defines else ""))
 
 
-def reward_id(reward_path: str, variant: int, dense_nv: Optional[int] = None) -> str:
+def reward_id(reward_path: str, variant: int, dense_nv: Optional[int] = None, defines=()) -> str:
     h = hashlib.sha256()
     for s in _sources(reward_path):
         h.update(open(s, "rb").read())
-    h.update((" ".join(NVCC_FLAGS) + f" variant={_tag(variant, dense_nv)[1:]}").encode())
+    h.update((" ".join(NVCC_FLAGS) + f" variant={_tag(variant, dense_nv)[1:]}"
+              + "".join(f" -D{d}" for d in sorted(defines))).encode())
     return h.hexdigest()[:16]
 
 
-def library_path(reward_path: str, variant: int, dense_nv: Optional[int] = None) -> str:
+def library_path(reward_path: str, variant: int, dense_nv: Optional[int] = None, defines=()) -> str:
     stem = os.path.splitext(os.path.basename(reward_path))[0]
-    return os.path.join(CACHE_DIR, f"libdial_b200_{stem}_{_tag(variant, dense_nv)}_{reward_id(reward_path, variant, dense_nv)}.so")
+    return os.path.join(CACHE_DIR, f"libdial_b200_{stem}_{_tag(variant, dense_nv, defines)}_"
+                                   f"{reward_id(reward_path, variant, dense_nv, defines)}.so")
 
 
 def solver_variant(model) -> int:
@@ -77,8 +81,11 @@ def dense_nv(model) -> Optional[int]:
 
 
 def build_library(reward_path: str, model=None, variant: Optional[int] = None, force: bool = False,
-                  verbose: bool = False) -> str:
-    """Compile (or reuse) the library with ``reward_path`` fused in; returns the ``.so`` path."""
+                  verbose: bool = False, defines=()) -> str:
+    """Compile (or reuse) the library with ``reward_path`` fused in; returns the ``.so`` path.
+    ``defines``: extra compile-time options of the kernels, e.g. ``("DIAL_ROBUST_LS",)`` — the line search
+    with a bracket that only narrows (a documented deviation from the reference's rule)."""
+    defines = tuple(defines)
     reward_path = os.path.abspath(reward_path)
     if not os.path.exists(reward_path):
         raise FileNotFoundError(reward_path)
@@ -87,7 +94,7 @@ def build_library(reward_path: str, model=None, variant: Optional[int] = None, f
             raise ValueError("pass the compiled model (or the solver variant) the library is for")
         variant = solver_variant(model)
     nvd = dense_nv(model) if (model is not None and variant == 3) else None
-    out = library_path(reward_path, variant, nvd)
+    out = library_path(reward_path, variant, nvd, defines)
     if os.path.exists(out) and not force:
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -96,8 +103,8 @@ def build_library(reward_path: str, model=None, variant: Optional[int] = None, f
     os.makedirs(CACHE_DIR, exist_ok=True)
     tmp = out + f".tmp{os.getpid()}"
     cmd = [nvcc] + NVCC_FLAGS + [f'-DDIAL_CUSTOM_REWARD_FILE="{reward_path}"',
-                                 f"-DDIAL_CUSTOM_REWARD_ID={reward_id(reward_path, variant, nvd)}",
-                                 f"-DDIAL_ONLY_VARIANT={variant}"] + ([f"-DDIAL_DENSE_NV={nvd}"] if nvd else []) + [
+                                 f"-DDIAL_CUSTOM_REWARD_ID={reward_id(reward_path, variant, nvd, defines)}",
+                                 f"-DDIAL_ONLY_VARIANT={variant}"] + ([f"-DDIAL_DENSE_NV={nvd}"] if nvd else []) + [f"-D{d}" for d in defines] + [
                                  "-o", tmp, os.path.join(CSRC, "dial_kernels.cu")]
     if verbose:
         print(" ".join(cmd))
@@ -110,7 +117,7 @@ def build_library(reward_path: str, model=None, variant: Optional[int] = None, f
     # superseded builds of the same reward (older kernel or reward sources) are dropped
     import glob
     stem = os.path.splitext(os.path.basename(reward_path))[0]
-    for old in glob.glob(os.path.join(CACHE_DIR, f"libdial_b200_{stem}_{_tag(variant, nvd)}_*.so")):
+    for old in glob.glob(os.path.join(CACHE_DIR, f"libdial_b200_{stem}_{_tag(variant, nvd, defines)}_*.so")):
         if old != out:
             try:
                 os.remove(old)

@@ -27,6 +27,7 @@ from dial_mpc_b200.envs.base_env import BaseEnv, BaseEnvConfig
 class CustomRewardEnv(BaseEnv):
     env_id = _capi.ENV_IDS["custom"]
     reward_source: str = ""          # path of the .cuh reward file
+    build_defines: tuple = ()        # extra compile-time options of the kernels, e.g. ("DIAL_ROBUST_LS",)
     init_keyframe: Optional[str] = "home"
 
     def __init__(self, config: BaseEnvConfig):
@@ -45,7 +46,8 @@ class CustomRewardEnv(BaseEnv):
         """Build of libdial_b200 with this env's reward fused in (compiled on first use)."""
         if self._library_path is None:
             from dial_mpc_b200 import custom
-            self._library_path = custom.build_library(self.reward_source, model=self.sys.model)
+            self._library_path = custom.build_library(self.reward_source, model=self.sys.model,
+                                                       defines=self.build_defines)
         return self._library_path
 
     def _get_obs(self, pipeline_state, info):

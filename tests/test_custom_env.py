@@ -360,3 +360,17 @@ def test_gpu_dense_custom_env_matches_oracle(pincher, built):
     # the planner runs on this build (weights / Ybar finite, mean row last)
     _, Y, info = mb.reverse_once(state, drandom.PRNGKey(3), torch.zeros(Hn + 1, 4, device="cuda"), mb.sigma_control)
     assert torch.isfinite(Y).all() and torch.isfinite(info["rews"]).all() and info["rews"].shape == (N + 1,)
+
+
+def test_custom_build_with_robust_line_search(pincher, built):
+    """`build_defines = ("DIAL_ROBUST_LS",)` on a custom env: a separate library (its own cache key) with the
+    narrowing-bracket line search compiled in; the default build is untouched."""
+    from dial_mpc_b200 import _capi, custom
+    env, _ = pincher
+    default = env.library_path
+    path = custom.build_library(env.reward_source, model=env.sys.model, defines=("DIAL_ROBUST_LS",))
+    assert path != default and "_v3n10x_" in path and os.path.exists(path) and os.path.exists(default)
+    lib = _capi.lib(path)
+    assert lib.dial_custom_reward_id().decode() == custom.reward_id(env.reward_source, 3, 10, ("DIAL_ROBUST_LS",))
+    assert lib.dial_solver_variant(_capi.fill_model_desc(env.sys.model)) == 3
+    assert type(env).build_defines == ()
