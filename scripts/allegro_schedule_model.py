@@ -12,7 +12,7 @@ import numpy as np
 nrows, level = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (14, 0)
 its = np.load(f"scratch/its_{nrows}_{level}.npy")
 lss = pickle.load(open(f"scratch/lss_{nrows}_{level}.pkl", "rb"))
-W, nsub = 14, its.shape[1]
+W, nsub = min(14, nrows), its.shape[1]
 rows = range(W)
 
 
